@@ -1,0 +1,151 @@
+/*
+ * tgp_b200.h — C ABI of libtgpb200.so: B200-native (sm_100a) replacement for the LGSSM
+ * inference hot path of TemporalGPs.jl (Kalman filter / RTS smoother recursions).
+ *
+ * The reference has no FFI; its seam is Julia dispatch on the five L2 entry points called by
+ * the GP layer. Each function below names the reference function it replaces
+ * (file:line relative to the reference tree). A Julia glue module binds these with `ccall`
+ * (see INTEGRATION.md and temporalgps.jl_b200/julia/TemporalGPsB200.jl).
+ *
+ * Conventions
+ *  - Plain pointers and sizes only. All matrices are COLUMN-MAJOR (Julia layout).
+ *  - Every data pointer may be a HOST or a DEVICE pointer (detected with
+ *    cudaPointerGetAttributes). Host inputs are staged to the device, host outputs are copied
+ *    back before the call returns. Device outputs are complete when the call returns.
+ *  - Per-step arrays use a stride in ELEMENTS between consecutive time steps; stride 0 means
+ *    "time-invariant" (Julia `Fill`, src/gp/lti_sde.jl:148-160).
+ *  - Return value: 0 (TGP_OK) on success, else a TGP_E* code; tgp_last_error(h) has the text.
+ *    No exception ever crosses the boundary (reference throws ErrorException at
+ *    src/models/lgssm.jl:202-208 and PosDefException from `cholesky`).
+ *  - Calls on one handle are serialised by the caller; distinct handles are independent.
+ *  - Missing data never crosses the ABI: the caller applies the reference's transform
+ *    (y := 0, R := 1e15, src/models/missings.jl:25-53) and adds the volume compensation.
+ *  - There is NO CPU fallback: without a CUDA device tgp_create fails with TGP_ECUDA.
+ */
+#ifndef TGP_B200_H
+#define TGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGP_OK            0
+#define TGP_EINVAL        1  /* bad argument / dimension mismatch (lgssm.jl:202-208)          */
+#define TGP_ENOTPD        2  /* a covariance that must be factorised is not positive definite  */
+#define TGP_ECUDA         3  /* CUDA runtime failure or no device                              */
+#define TGP_ENOMEM        4
+#define TGP_EUNSUPPORTED  5  /* shape outside what this build supports                         */
+
+#define TGP_FORWARD 0        /* gauss_markov_model.jl:1  — step = predict, then update         */
+#define TGP_REVERSE 1        /* gauss_markov_model.jl:3  — step = update, then predict; t=T..1  */
+
+#define TGP_R_SCALAR 0       /* M == 1: R is one variance per step (ScalarOutputLGC, LGC:225)  */
+#define TGP_R_DIAG   1       /* R is the M diagonal entries per step                           */
+#define TGP_R_DENSE  2       /* R is a dense M x M matrix per step                             */
+
+#define TGP_MAX_D 32         /* latent dimension supported by the small-state kernels          */
+
+/* algorithm selection for tgp_set_option(h, TGP_OPT_ALGO, v) */
+#define TGP_OPT_ALGO         1
+#define TGP_ALGO_AUTO        0  /* steady-state path when the model is time-invariant, else scan  */
+#define TGP_ALGO_SCAN        1  /* always the general 5-tuple associative scan                 */
+#define TGP_OPT_CHUNK        2  /* steps per thread in the scan kernels (0 = auto)              */
+#define TGP_OPT_SS_TOL       3  /* (double bits) relative tolerance for steady-state detection  */
+
+typedef struct tgp_ctx* tgp_handle;
+
+/*
+ * LGSSM descriptor = GaussMarkovModel (gauss_markov_model.jl:20-32) + emissions
+ * (lgssm.jl:9-12; StructArray fields .A/.a/.Q of lti_sde.jl:88-109).
+ *   x[t] = A[t] x[t-1] + a[t] + N(0, Q[t]);   y[t] = H[t] x[t] + h[t] + N(0, R[t]).
+ * Array index t = 0..T-1 is the reference's index 1..T in MEMORY order for both orderings;
+ * for TGP_REVERSE the recursion visits t = T-1 down to 0 (gauss_markov_model.jl:38-40).
+ */
+typedef struct {
+    int32_t D;             /* latent dimension                                                  */
+    int32_t M;             /* observation dimension per step (1 = ScalarOutputLGC)               */
+    int64_t T;             /* number of time steps                                              */
+    int32_t ordering;      /* TGP_FORWARD / TGP_REVERSE                                          */
+    int32_t R_kind;        /* TGP_R_*                                                            */
+    const double* A;  int64_t sA;   /* D x D, stride D*D or 0                                    */
+    const double* a;  int64_t sa;   /* D,     stride D   or 0                                    */
+    const double* Q;  int64_t sQ;   /* D x D                                                     */
+    const double* H;  int64_t sH;   /* M x D  (M == 1: the D entries of the adjoint vector)      */
+    const double* h;  int64_t sh;   /* M                                                         */
+    const double* R;  int64_t sR;   /* 1 | M | M x M according to R_kind                         */
+    const double* m0;               /* D      — x0.m (gaussian.jl:16-19)                         */
+    const double* P0;               /* D x D  — x0.P                                             */
+} tgp_lgssm;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int         tgp_create(tgp_handle* out, int device);      /* one handle = one GPU + stream + workspace */
+void        tgp_destroy(tgp_handle h);
+const char* tgp_last_error(tgp_handle h);                 /* h may be NULL: last create error */
+const char* tgp_version(void);
+int         tgp_set_option(tgp_handle h, int option, int64_t value);
+/* counters since create: kernels launched by this library, bytes copied H2D / D2H */
+int         tgp_get_counters(tgp_handle h, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* run subsequent work of this handle on a caller-owned cudaStream_t (0 = handle's own) */
+int         tgp_set_stream(tgp_handle h, void* cuda_stream);
+
+/* ---- hot path --------------------------------------------------------------------------
+ * tgp_logpdf   replaces logpdf(::LGSSM, y)            src/models/lgssm.jl:147-165
+ *              (scan_emit + step_logpdf: predict LGC:46-52, posterior_and_lml LGC:247-257 /
+ *              129-141). lml_per_step (T doubles, may be NULL) receives the emitted `lmls`.
+ */
+int tgp_logpdf(tgp_handle h, const tgp_lgssm* model, const double* y,
+               double* lml_out, double* lml_per_step);
+
+/* tgp_filter   replaces _filter(::LGSSM, y)           src/models/lgssm.jl:171-187
+ *              m_f[t*s_m + i], P_f[t*s_P + i + D*j]: strides in elements (s_m >= D, s_P >= D*D),
+ *              so a Julia Vector{Gaussian{SVector{D},SMatrix{D,D}}} (records of D+D*D doubles)
+ *              is written in place with m_f = base, P_f = base + D, s_m = s_P = D + D*D.
+ *              Either output may be NULL. lml_out may be NULL.
+ */
+int tgp_filter(tgp_handle h, const tgp_lgssm* model, const double* y,
+               double* m_f, int64_t s_m, double* P_f, int64_t s_P, double* lml_out);
+
+/* tgp_posterior replaces posterior(::LGSSM, y)        src/models/lgssm.jl:193-238
+ *              (step_posterior + invert_dynamics, jitter 1e-10). Emits the reverse-time
+ *              dynamics G (T x D x D), g (T x D), Sig (T x D x D), contiguous per step, and the
+ *              final filtering distribution (m_T, P_T) = x0 of the returned Reverse model.
+ */
+int tgp_posterior(tgp_handle h, const tgp_lgssm* model, const double* y,
+                  double* G, double* g, double* Sig, double* m_T, double* P_T);
+
+/* tgp_marginals replaces marginals(::LGSSM)           src/models/lgssm.jl:99-115
+ *              data-free predict recursion; emits the emission-space marginal per step:
+ *              mean_out (T x M) and cov_out (T x M x M) (M == 1: the variance).
+ */
+int tgp_marginals(tgp_handle h, const tgp_lgssm* model, double* mean_out, double* cov_out);
+
+/* tgp_posterior_marginals fuses the chain used by marginals(::FinitePosteriorLTISDE) at the
+ *              training inputs (src/gp/posterior_lti_sde.jl:27-36):
+ *              posterior(model, y) -> replace_observation_noise_cov(., R_new) -> marginals(.)
+ *              -> diagonal. The (G,g,Sig) dynamics are never materialised. R_new is per step with
+ *              stride sRnew (0 = constant) and the model's R_kind. Outputs mean_out, var_out: T x M.
+ *              lml_out (nullable) receives logpdf(model, y) as a by-product of the forward pass.
+ */
+int tgp_posterior_marginals(tgp_handle h, const tgp_lgssm* model, const double* y,
+                            const double* R_new, int64_t sRnew,
+                            double* mean_out, double* var_out, double* lml_out);
+
+/* ---- time-sharded multi-GPU path (no reference analogue) -------------------
+ * A scan element is (A, b, C, eta, J): 3*D*D + 2*D doubles, matrices column-major, in that
+ * order. tgp_shard_reduce folds a whole shard of steps into ONE element (phase 1). The caller
+ * all-gathers the elements of all ranks (NCCL, 264 B per rank at D = 3), then
+ * tgp_shard_prefix applies elements 0..rank-1 to x0 to obtain the filtering distribution
+ * entering this rank's shard; phase 2 is the ordinary tgp_logpdf / tgp_filter call on the shard
+ * with (m0, P0) := that state.
+ */
+int tgp_elem_size(int D);                                  /* 3*D*D + 2*D */
+int tgp_shard_reduce(tgp_handle h, const tgp_lgssm* shard, const double* y, double* elem_out);
+int tgp_shard_prefix(tgp_handle h, int D, int n_elems, const double* elems /*host*/,
+                     const double* m0, const double* P0, double* m_in, double* P_in /*host*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGP_B200_H */
