@@ -1,0 +1,221 @@
+// tgp_api.cu — the C ABI of libtgpb200.so (include/tgp_b200.h): argument checking, staging of
+// host buffers, and the launch sequences of the small-state scan kernels. No CPU fallback exists:
+// every entry point either runs the sm_100a kernels or returns an error code.
+#include <algorithm>
+#include <new>
+
+#include "tgp_ctx.cuh"
+#include "tgp_dispatch.h"
+
+using namespace tgp;
+
+namespace {
+
+const char* g_create_err = "";
+std::string g_create_err_buf;
+
+// ---- argument checking (the reference throws at lgssm.jl:202-208 / MethodErrors) ---------------
+int validate(tgp_ctx* h, const tgp_lgssm* m, bool need_y, const void* y) {
+    if (!h) return TGP_EINVAL;
+    if (!m) return fail(h, TGP_EINVAL, "model descriptor is NULL");
+    if (m->D < 1 || m->D > TGP_MAX_D) return fail(h, TGP_EUNSUPPORTED, "latent dimension D=%d outside 1..%d", m->D, TGP_MAX_D);
+    if (m->M < 1) return fail(h, TGP_EINVAL, "observation dimension M=%d must be >= 1", m->M);
+    if (m->T < 1) return fail(h, TGP_EINVAL, "Dimension mismatch. length(prior) is %lld", (long long)m->T);
+    if (m->ordering != TGP_FORWARD && m->ordering != TGP_REVERSE) return fail(h, TGP_EINVAL, "ordering must be TGP_FORWARD or TGP_REVERSE");
+    if (m->R_kind < TGP_R_SCALAR || m->R_kind > TGP_R_DENSE) return fail(h, TGP_EINVAL, "R_kind must be one of TGP_R_*");
+    if (m->R_kind == TGP_R_SCALAR && m->M != 1) return fail(h, TGP_EINVAL, "TGP_R_SCALAR requires M == 1");
+    if (!m->A || !m->a || !m->Q || !m->H || !m->h || !m->R || !m->m0 || !m->P0) return fail(h, TGP_EINVAL, "model descriptor has a NULL array");
+    const int64_t D = m->D, M = m->M;
+    const int64_t rin = m->R_kind == TGP_R_SCALAR ? 1 : (m->R_kind == TGP_R_DIAG ? M : M * M);
+    struct { const char* name; int64_t s, inner; } chk[] = {{"sA", m->sA, D * D}, {"sa", m->sa, D},     {"sQ", m->sQ, D * D},
+                                                              {"sH", m->sH, M * D}, {"sh", m->sh, M}, {"sR", m->sR, rin}};
+    for (auto& c : chk)
+        if (c.s != 0 && c.s < c.inner) return fail(h, TGP_EINVAL, "stride %s=%lld must be 0 or >= %lld", c.name, (long long)c.s, (long long)c.inner);
+    if (need_y && !y) return fail(h, TGP_EINVAL, "Dimension mismatch. y is NULL but length(prior) is %lld", (long long)m->T);
+    return TGP_OK;
+}
+
+int require_scalar_obs(tgp_ctx* h, const tgp_lgssm* m) {
+    if (m->M != 1 || m->R_kind != TGP_R_SCALAR)
+        return fail(h, TGP_EUNSUPPORTED, "this build runs scalar observations (M == 1, TGP_R_SCALAR) on the scan path; got M=%d R_kind=%d", m->M, m->R_kind);
+    return TGP_OK;
+}
+
+int begin_call(tgp_ctx* h) {
+    h->err.clear();
+    h->pending.clear();
+    TGP_CUDA(h, cudaSetDevice(h->device));
+    TGP_CUDA(h, h->arena.reset());
+    return TGP_OK;
+}
+
+#define TGP_CASE_D(Dv) case Dv: return CALL(Dv);
+#define TGP_DISPATCH_D(h, Dv)                                                                               \
+    switch (Dv) {                                                                                           \
+        TGP_FOR_EACH_D(TGP_CASE_D)                                                                          \
+        default: return fail(h, TGP_EUNSUPPORTED, "latent dimension D=%d has no kernel instantiation in this build", Dv); \
+    }
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* tgp_version(void) { return "tgp-b200 0.1.0 (sm_100a)"; }
+
+int tgp_create(tgp_handle* out, int device) {
+    if (!out) return TGP_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_err_buf = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                           " (libtgpb200 has no CPU path)";
+        g_create_err = g_create_err_buf.c_str();
+        cudaGetLastError();
+        return TGP_ECUDA;
+    }
+    if (device < 0 || device >= n) {
+        g_create_err_buf = "device index out of range";
+        g_create_err = g_create_err_buf.c_str();
+        return TGP_EINVAL;
+    }
+    tgp_ctx* h = new (std::nothrow) tgp_ctx();
+    if (!h) return TGP_ENOMEM;
+    h->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMallocHost((void**)&h->pinned, 4096)) != cudaSuccess) {
+        g_create_err_buf = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
+        g_create_err = g_create_err_buf.c_str();
+        delete h;
+        return TGP_ECUDA;
+    }
+    h->stream = h->own_stream;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = h;
+    return TGP_OK;
+}
+
+void tgp_destroy(tgp_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->arena.release();
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+const char* tgp_last_error(tgp_handle h) { return h ? h->err.c_str() : g_create_err; }
+
+int tgp_set_option(tgp_handle h, int option, int64_t value) {
+    if (!h) return TGP_EINVAL;
+    switch (option) {
+        case TGP_OPT_ALGO:
+            if (value != TGP_ALGO_AUTO && value != TGP_ALGO_SCAN) return fail(h, TGP_EINVAL, "unknown algorithm %lld", (long long)value);
+            h->algo = (int)value;
+            return TGP_OK;
+        case TGP_OPT_CHUNK:
+            if (value < 0 || value > 4096) return fail(h, TGP_EINVAL, "chunk must be in 0..4096");
+            h->chunk = (int)value;
+            return TGP_OK;
+        case TGP_OPT_SS_TOL: {
+            double v;
+            memcpy(&v, &value, sizeof v);
+            if (!(v >= 0.0) || !(v < 1e-3)) return fail(h, TGP_EINVAL, "steady-state tolerance must be in [0, 1e-3)");
+            h->ss_tol = v;
+            return TGP_OK;
+        }
+        default: return fail(h, TGP_EINVAL, "unknown option %d", option);
+    }
+}
+
+int tgp_get_counters(tgp_handle h, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (!h) return TGP_EINVAL;
+    if (launches) *launches = h->launches;
+    if (h2d_bytes) *h2d_bytes = h->h2d;
+    if (d2h_bytes) *d2h_bytes = h->d2h;
+    return TGP_OK;
+}
+
+int tgp_set_stream(tgp_handle h, void* cuda_stream) {
+    if (!h) return TGP_EINVAL;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return TGP_OK;
+}
+
+int tgp_logpdf(tgp_handle h, const tgp_lgssm* model, const double* y, double* lml_out, double* lml_per_step) {
+    TGP_TRY(validate(h, model, true, y));
+    TGP_TRY(require_scalar_obs(h, model));
+    TGP_TRY(begin_call(h));
+#define CALL(Dv) do_filter<Dv>(h, model, y, nullptr, 0, nullptr, 0, lml_out, lml_per_step)
+    TGP_DISPATCH_D(h, model->D)
+#undef CALL
+}
+
+int tgp_filter(tgp_handle h, const tgp_lgssm* model, const double* y, double* m_f, int64_t s_m, double* P_f, int64_t s_P,
+               double* lml_out) {
+    TGP_TRY(validate(h, model, true, y));
+    TGP_TRY(require_scalar_obs(h, model));
+    if (m_f && s_m < model->D) return fail(h, TGP_EINVAL, "s_m=%lld must be >= D", (long long)s_m);
+    if (P_f && s_P < (int64_t)model->D * model->D) return fail(h, TGP_EINVAL, "s_P=%lld must be >= D*D", (long long)s_P);
+    TGP_TRY(begin_call(h));
+#define CALL(Dv) do_filter<Dv>(h, model, y, m_f, s_m, P_f, s_P, lml_out, nullptr)
+    TGP_DISPATCH_D(h, model->D)
+#undef CALL
+}
+
+int tgp_posterior(tgp_handle h, const tgp_lgssm* model, const double* y, double* G, double* g, double* Sig, double* m_T,
+                  double* P_T) {
+    TGP_TRY(validate(h, model, true, y));
+    TGP_TRY(require_scalar_obs(h, model));
+    TGP_TRY(begin_call(h));
+#define CALL(Dv) do_posterior<Dv>(h, model, y, G, g, Sig, m_T, P_T)
+    TGP_DISPATCH_D(h, model->D)
+#undef CALL
+}
+
+int tgp_marginals(tgp_handle h, const tgp_lgssm* model, double* mean_out, double* cov_out) {
+    TGP_TRY(validate(h, model, false, nullptr));
+    TGP_TRY(require_scalar_obs(h, model));
+    if (!mean_out || !cov_out) return fail(h, TGP_EINVAL, "mean_out and cov_out must be non-NULL");
+    TGP_TRY(begin_call(h));
+#define CALL(Dv) do_marginals<Dv>(h, model, mean_out, cov_out)
+    TGP_DISPATCH_D(h, model->D)
+#undef CALL
+}
+
+int tgp_posterior_marginals(tgp_handle h, const tgp_lgssm* model, const double* y, const double* R_new, int64_t sRnew,
+                            double* mean_out, double* var_out, double* lml_out) {
+    TGP_TRY(validate(h, model, true, y));
+    TGP_TRY(require_scalar_obs(h, model));
+    if (!R_new || !mean_out || !var_out) return fail(h, TGP_EINVAL, "R_new, mean_out and var_out must be non-NULL");
+    if (sRnew != 0 && sRnew < 1) return fail(h, TGP_EINVAL, "sRnew must be 0 or >= 1");
+    TGP_TRY(begin_call(h));
+#define CALL(Dv) do_posterior_marginals<Dv>(h, model, y, R_new, sRnew, mean_out, var_out, lml_out)
+    TGP_DISPATCH_D(h, model->D)
+#undef CALL
+}
+
+int tgp_elem_size(int D) { return 3 * D * D + 2 * D; }
+
+int tgp_shard_reduce(tgp_handle h, const tgp_lgssm* shard, const double* y, double* elem_out) {
+    TGP_TRY(validate(h, shard, true, y));
+    TGP_TRY(require_scalar_obs(h, shard));
+    if (!elem_out) return fail(h, TGP_EINVAL, "elem_out must be non-NULL");
+    TGP_TRY(begin_call(h));
+#define CALL(Dv) do_shard_reduce<Dv>(h, shard, y, elem_out)
+    TGP_DISPATCH_D(h, shard->D)
+#undef CALL
+}
+
+int tgp_shard_prefix(tgp_handle h, int D, int n_elems, const double* elems, const double* m0, const double* P0, double* m_in,
+                     double* P_in) {
+    if (!h) return TGP_EINVAL;
+    if (n_elems < 0 || (n_elems > 0 && !elems) || !m0 || !P0 || !m_in || !P_in) return fail(h, TGP_EINVAL, "bad argument to tgp_shard_prefix");
+#define CALL(Dv) do_shard_prefix<Dv>(n_elems, elems, m0, P0, m_in, P_in)
+    TGP_DISPATCH_D(h, D)
+#undef CALL
+}
+
+}  // extern "C"

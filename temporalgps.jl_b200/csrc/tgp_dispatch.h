@@ -1,0 +1,34 @@
+// tgp_dispatch.h — declarations of the per-dimension drivers (defined in tgp_drivers.cuh,
+// instantiated in tgp_inst.cu once per supported D).
+#pragma once
+#include "tgp_ctx.cuh"
+
+namespace tgp {
+
+template <int D> int do_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* m_f, int64_t s_m, double* P_f,
+                               int64_t s_P, double* lml_out, double* lml_steps);
+template <int D> int do_posterior_marginals(tgp_ctx* h, const tgp_lgssm* m, const double* y, const double* R_new,
+                                            int64_t sRnew, double* mean_out, double* var_out, double* lml_out);
+template <int D> int do_posterior(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* G, double* g, double* Sig,
+                                  double* m_T, double* P_T);
+template <int D> int do_marginals(tgp_ctx* h, const tgp_lgssm* m, double* mean_out, double* var_out);
+template <int D> int do_shard_reduce(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* elem_out);
+template <int D> int do_shard_prefix(int n, const double* elems, const double* m0, const double* P0, double* m_in,
+                                     double* P_in);
+
+#define TGP_DECL_D(Dv)                                                                                               \
+    extern template int do_filter<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, double*, int64_t, double*, int64_t, \
+                                      double*, double*);                                                             \
+    extern template int do_posterior_marginals<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, const double*, int64_t, \
+                                                   double*, double*, double*);                                       \
+    extern template int do_posterior<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, double*, double*, double*,       \
+                                         double*, double*);                                                          \
+    extern template int do_marginals<Dv>(tgp_ctx*, const tgp_lgssm*, double*, double*);                              \
+    extern template int do_shard_reduce<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, double*);                     \
+    extern template int do_shard_prefix<Dv>(int, const double*, const double*, const double*, double*, double*);
+
+// The set of latent dimensions with kernel instantiations (keep in step with build.py's TGP_DIMS).
+#define TGP_FOR_EACH_D(X) X(1) X(2) X(3) X(4) X(5) X(6)
+TGP_FOR_EACH_D(TGP_DECL_D)
+
+}  // namespace tgp

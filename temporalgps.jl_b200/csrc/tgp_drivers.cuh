@@ -1,0 +1,338 @@
+// tgp_drivers.cuh — launch sequences of the small-state scan kernels, templated on the latent
+// dimension D. Included only by tgp_inst.cu (one translation unit per D, -DTGP_D=<D>) so the
+// instantiations compile in parallel; tgp_api.cu sees the declarations in tgp_dispatch.h.
+#pragma once
+#include "tgp_ctx.cuh"
+#include "tgp_scan_small.cuh"
+#include "tgp_steady.cuh"
+
+namespace tgp {
+
+// Model + observations -> device-resident descriptor.
+inline int stage_model(tgp_ctx* h, const tgp_lgssm* m, const double* y, tgp_lgssm* d, const double** dy) {
+    *d = *m;
+    const size_t D = m->D, M = m->M;
+    const size_t rin = m->R_kind == TGP_R_SCALAR ? 1 : (m->R_kind == TGP_R_DIAG ? M : M * M);
+    TGP_TRY(stage_steps(h, m->A, m->sA, m->T, D * D, &d->A));
+    TGP_TRY(stage_steps(h, m->a, m->sa, m->T, D, &d->a));
+    TGP_TRY(stage_steps(h, m->Q, m->sQ, m->T, D * D, &d->Q));
+    TGP_TRY(stage_steps(h, m->H, m->sH, m->T, M * D, &d->H));
+    TGP_TRY(stage_steps(h, m->h, m->sh, m->T, M, &d->h));
+    TGP_TRY(stage_steps(h, m->R, m->sR, m->T, rin, &d->R));
+    TGP_TRY(stage_in(h, m->m0, D, &d->m0));
+    TGP_TRY(stage_in(h, m->P0, D * D, &d->P0));
+    if (dy) TGP_TRY(stage_in(h, y, (size_t)m->T * M, dy));
+    return TGP_OK;
+}
+
+inline bool time_invariant(const tgp_lgssm& m) { return !(m.sA | m.sa | m.sQ | m.sH | m.sh | m.sR); }
+
+// End of a call: copy back host outputs, fetch the failing-step word, wait.
+inline int end_call(tgp_ctx* h, const unsigned long long* err_step, int64_t T, bool reverse_t) {
+    TGP_TRY(flush_outputs(h));
+    unsigned long long* perr = (unsigned long long*)h->pinned;
+    *perr = ~0ull;
+    if (err_step) {
+        TGP_CUDA(h, cudaMemcpyAsync(perr, err_step, sizeof(*perr), cudaMemcpyDeviceToHost, h->stream));
+        h->d2h += 8;
+    }
+    TGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (*perr != ~0ull) {
+        const long long n = (long long)*perr;
+        const long long t = reverse_t ? (long long)T - 1 - n : n;
+        return fail(h, TGP_ENOTPD, "covariance not positive definite at time index %lld (0-based)", t);
+    }
+    return TGP_OK;
+}
+
+// ---- general (time-varying) filter: reduce -> mid -> apply ----------------------------------------
+template <int D>
+int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& rq) {
+    constexpr int SN = D + Sym<D>::N;
+    const int64_t T = d.T;
+    const bool rev = d.ordering == TGP_REVERSE;
+    cudaStream_t st = h->stream;
+    TGP_TRY(dalloc(h, 1, &rq.err));
+    TGP_CUDA(h, cudaMemsetAsync(rq.err, 0xFF, sizeof(unsigned long long), st));
+    TGP_TRY(dalloc(h, SN, &rq.x0buf));
+    TGP_TRY(dalloc(h, SN, &rq.xT));
+    TGP_TRY(dalloc(h, 1, &rq.lml_dev));
+    double* lml_extra = nullptr;
+    TGP_TRY(dalloc(h, 1, &lml_extra));
+    if (rq.keep_ws) TGP_TRY(dalloc(h, (size_t)SN * T, &rq.ws));
+
+    // x0 (and, for Reverse, the leading update of the last memory index; lgssm.jl:161-165)
+    const int64_t tl = T - 1;
+    k_init_state<D><<<1, 32, 0, st>>>(d.m0, d.P0, rq.x0buf, rev ? 1 : 0, d.H + tl * d.sH, d.h + tl * d.sh, d.R + tl * d.sR,
+                                      dy + tl, lml_extra, rq.lml_steps ? rq.lml_steps + tl : nullptr,
+                                      rq.m_f ? rq.m_f + tl * rq.s_m : nullptr, rq.P_f ? rq.P_f + tl * rq.s_P : nullptr,
+                                      rq.ws, T, tl, rq.err);
+    TGP_LAUNCH_CHECK(h);
+
+    const int64_t Ts = rev ? T - 1 : T;  // scan steps: (predict, update) pairs
+    if (Ts == 0) {
+        TGP_CUDA(h, cudaMemcpyAsync(rq.xT, rq.x0buf, SN * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        TGP_CUDA(h, cudaMemcpyAsync(rq.lml_dev, lml_extra, sizeof(double), cudaMemcpyDeviceToDevice, st));
+        return deliver_scalar(h, rq.lml_dev, rq.lml_out);
+    }
+    DevModel dm;
+    if (!rev) {
+        dm = DevModel{d.A, d.a, d.Q, d.H, d.h, d.R, d.sA, d.sa, d.sQ, d.sH, d.sh, d.sR, dy, 1, Ts};
+    } else {  // scan step j: transition of memory index T-1-j, emission / observation of index T-2-j
+        dm = DevModel{d.A + tl * d.sA, d.a + tl * d.sa, d.Q + tl * d.sQ, d.H + (tl - 1) * d.sH, d.h + (tl - 1) * d.sh,
+                      d.R + (tl - 1) * d.sR, -d.sA, -d.sa, -d.sQ, -d.sH, -d.sh, -d.sR, dy + (tl - 1), -1, Ts};
+    }
+    const bool tv = !time_invariant(d);
+    ConstModel<D>* cm = nullptr;
+    if (!tv) {
+        TGP_TRY(dalloc(h, 1, &cm));
+        k_const_model<D><<<1, 32, 0, st>>>(dm, cm);
+        TGP_LAUNCH_CHECK(h);
+    }
+    const int L = h->chunk > 0 ? h->chunk : 16;
+    const int64_t nchunk = (Ts + L - 1) / L;
+    const int64_t grid = (nchunk + kBlock - 1) / kBlock;
+    const int64_t nthreads = grid * kBlock, nwarps = nthreads / 32;
+    double *excl, *wagg, *wstate, *partials;
+    TGP_TRY(dalloc(h, (size_t)Elem<D>::N * nthreads, &excl));
+    TGP_TRY(dalloc(h, (size_t)Elem<D>::N * nwarps, &wagg));
+    TGP_TRY(dalloc(h, (size_t)SN * nwarps, &wstate));
+    TGP_TRY(dalloc(h, (size_t)grid, &partials));
+    if (tv) k_filter_reduce<D, true><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wagg, nwarps);
+    else    k_filter_reduce<D, false><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wagg, nwarps);
+    TGP_LAUNCH_CHECK(h);
+    k_filter_mid<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, rq.x0buf, wstate, rq.xT);
+    TGP_LAUNCH_CHECK(h);
+    FilterOut fo;
+    const int64_t o0 = rev ? tl - 1 : 0;  // memory index of scan step 0
+    const int64_t sg = rev ? -1 : 1;
+    fo.lml_steps = rq.lml_steps ? rq.lml_steps + o0 : nullptr;
+    fo.s_l = sg;
+    fo.m_f = rq.m_f ? rq.m_f + o0 * rq.s_m : nullptr;
+    fo.s_m = sg * rq.s_m;
+    fo.P_f = rq.P_f ? rq.P_f + o0 * rq.s_P : nullptr;
+    fo.s_P = sg * rq.s_P;
+    fo.ws_m = rq.ws;   // forward only (checked by callers): index = scan step = time, stride Ts == T
+    fo.partials = partials;
+    fo.err_step = rq.err;
+    if (tv) k_filter_apply<D, true><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wstate, nwarps, fo);
+    else    k_filter_apply<D, false><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wstate, nwarps, fo);
+    TGP_LAUNCH_CHECK(h);
+    k_sum_partials<<<1, 256, 0, st>>>(partials, grid, lml_extra, rq.lml_dev);
+    TGP_LAUNCH_CHECK(h);
+    return deliver_scalar(h, rq.lml_dev, rq.lml_out);
+}
+
+// Reverse scan steps are offset by one against memory (the leading update is step "-1"):
+// err_step holds a scan step; map it to a memory index for the message.
+inline int64_t err_T(const tgp_lgssm& d) { return d.ordering == TGP_REVERSE ? d.T - 1 : d.T; }
+
+template <int D>
+int do_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* m_f, int64_t s_m, double* P_f, int64_t s_P,
+              double* lml_out, double* lml_steps) {
+    tgp_lgssm d;
+    const double* dy;
+    TGP_TRY(stage_model(h, m, y, &d, &dy));
+    FilterReq rq;
+    rq.lml_out = lml_out;
+    int64_t ds;
+    TGP_TRY(stage_out(h, lml_steps, 1, 1, m->T, &rq.lml_steps, &ds));
+    TGP_TRY(stage_out(h, m_f, D, s_m, m->T, &rq.m_f, &rq.s_m));
+    TGP_TRY(stage_out(h, P_f, D * D, s_P, m->T, &rq.P_f, &rq.s_P));
+    int rc = TGP_EUNSUPPORTED;
+    bool handled = false;
+    if (h->algo == TGP_ALGO_AUTO && m->ordering == TGP_FORWARD && time_invariant(*m)) {
+        rc = filter_steady<D>(h, d, dy, rq, &handled);
+        if (rc != TGP_OK) return rc;
+    }
+    if (!handled) TGP_TRY(filter_general<D>(h, d, dy, rq));
+    return end_call(h, rq.err, err_T(d), m->ordering == TGP_REVERSE);
+}
+
+// ---- backward pass over the stored filtering distributions (posterior marginals) -----------------
+template <int D>
+int do_posterior_marginals(tgp_ctx* h, const tgp_lgssm* m, const double* y, const double* R_new, int64_t sRnew,
+                           double* mean_out, double* var_out, double* lml_out) {
+    if (m->ordering != TGP_FORWARD) return fail(h, TGP_EUNSUPPORTED, "posterior of a Reverse-ordered model is not built yet");
+    constexpr int SN = D + Sym<D>::N;
+    const int64_t T = m->T;
+    cudaStream_t st = h->stream;
+    tgp_lgssm d;
+    const double* dy;
+    TGP_TRY(stage_model(h, m, y, &d, &dy));
+    const double* dRn;
+    TGP_TRY(stage_steps(h, R_new, sRnew, T, 1, &dRn));
+    FilterReq rq;
+    rq.lml_out = lml_out;
+    rq.keep_ws = true;
+    TGP_TRY(filter_general<D>(h, d, dy, rq));
+    double *dmean, *dvar;
+    int64_t s1;
+    TGP_TRY(stage_out(h, mean_out, 1, 1, T, &dmean, &s1));
+    TGP_TRY(stage_out(h, var_out, 1, 1, T, &dvar, &s1));
+
+    SmootherProvider<D> prov;
+    prov.dm = DevModel{d.A, d.a, d.Q, d.H, d.h, d.R, d.sA, d.sa, d.sQ, d.sH, d.sh, d.sR, dy, 1, T};
+    prov.ws = rq.ws;
+    prov.x0buf = rq.x0buf;
+    prov.err_step = rq.err;
+    const int L = h->chunk > 0 ? h->chunk : 16;
+    const int64_t nchunk = (T + L - 1) / L;
+    const int64_t grid = (nchunk + kBlock - 1) / kBlock;
+    const int64_t nthreads = grid * kBlock, nwarps = nthreads / 32;
+    double *excl, *wagg, *wstate;
+    TGP_TRY(dalloc(h, (size_t)Aff<D>::N * nthreads, &excl));
+    TGP_TRY(dalloc(h, (size_t)Aff<D>::N * nwarps, &wagg));
+    TGP_TRY(dalloc(h, (size_t)SN * nwarps, &wstate));
+    k_aff_reduce<D, SmootherProvider<D>><<<(unsigned)grid, kBlock, 0, st>>>(prov, T, L, nthreads, excl, wagg, nwarps);
+    TGP_LAUNCH_CHECK(h);
+    k_aff_mid<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, rq.xT, wstate, nullptr);
+    TGP_LAUNCH_CHECK(h);
+    const int64_t tl = T - 1;
+    EmitOut eo{d.H + tl * d.sH, d.h + tl * d.sh, dRn + tl * sRnew, -d.sH, -d.sh, -sRnew, dmean + tl, dvar + tl, -1};
+    k_aff_apply<D, SmootherProvider<D>><<<(unsigned)grid, kBlock, 0, st>>>(prov, T, L, nthreads, excl, wstate, nwarps, eo, 1);
+    TGP_LAUNCH_CHECK(h);
+    return end_call(h, rq.err, T, false);
+}
+
+template <int D>
+int do_posterior(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* G, double* g, double* Sig, double* m_T, double* P_T) {
+    if (m->ordering != TGP_FORWARD) return fail(h, TGP_EUNSUPPORTED, "posterior of a Reverse-ordered model is not built yet");
+    const int64_t T = m->T;
+    cudaStream_t st = h->stream;
+    tgp_lgssm d;
+    const double* dy;
+    TGP_TRY(stage_model(h, m, y, &d, &dy));
+    FilterReq rq;
+    rq.keep_ws = true;
+    TGP_TRY(filter_general<D>(h, d, dy, rq));
+    double *dG, *dg, *dS, *dmT, *dPT;
+    int64_t s1;
+    TGP_TRY(stage_out(h, G, D * D, D * D, T, &dG, &s1));
+    TGP_TRY(stage_out(h, g, D, D, T, &dg, &s1));
+    TGP_TRY(stage_out(h, Sig, D * D, D * D, T, &dS, &s1));
+    TGP_TRY(stage_out(h, m_T, D, D, 1, &dmT, &s1));
+    TGP_TRY(stage_out(h, P_T, D * D, D * D, 1, &dPT, &s1));
+    SmootherProvider<D> prov;
+    prov.dm = DevModel{d.A, d.a, d.Q, d.H, d.h, d.R, d.sA, d.sa, d.sQ, d.sH, d.sh, d.sR, dy, 1, T};
+    prov.ws = rq.ws;
+    prov.x0buf = rq.x0buf;
+    prov.err_step = rq.err;
+    if (dG && dg && dS) {
+        k_posterior_dynamics<D><<<(unsigned)((T + kBlock - 1) / kBlock), kBlock, 0, st>>>(prov, dG, dg, dS);
+        TGP_LAUNCH_CHECK(h);
+    } else if (dG || dg || dS) {
+        return fail(h, TGP_EINVAL, "G, g and Sig must be all NULL or all non-NULL");
+    }
+    k_unpack_state<D><<<1, 32, 0, st>>>(rq.xT, dmT, dPT);
+    TGP_LAUNCH_CHECK(h);
+    return end_call(h, rq.err, T, false);
+}
+
+template <int D>
+int do_marginals(tgp_ctx* h, const tgp_lgssm* m, double* mean_out, double* var_out) {
+    constexpr int SN = D + Sym<D>::N;
+    const int64_t T = m->T;
+    const bool rev = m->ordering == TGP_REVERSE;
+    cudaStream_t st = h->stream;
+    tgp_lgssm d;
+    TGP_TRY(stage_model(h, m, nullptr, &d, nullptr));
+    double *dmean, *dvar, *x0buf;
+    int64_t s1;
+    TGP_TRY(stage_out(h, mean_out, 1, 1, T, &dmean, &s1));
+    TGP_TRY(stage_out(h, var_out, 1, 1, T, &dvar, &s1));
+    TGP_TRY(dalloc(h, SN, &x0buf));
+    k_init_state<D><<<1, 32, 0, st>>>(d.m0, d.P0, x0buf, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                      nullptr, 0, 0, nullptr);
+    TGP_LAUNCH_CHECK(h);
+    const int64_t tl = T - 1;
+    ModelAffProvider<D> prov;
+    EmitOut eo;
+    if (!rev) {
+        prov.dm = DevModel{d.A, d.a, d.Q, d.H, d.h, d.R, d.sA, d.sa, d.sQ, d.sH, d.sh, d.sR, nullptr, 1, T};
+        eo = EmitOut{d.H, d.h, d.R, d.sH, d.sh, d.sR, dmean, dvar, 1};
+    } else {
+        prov.dm = DevModel{d.A + tl * d.sA, d.a + tl * d.sa, d.Q + tl * d.sQ, d.H, d.h, d.R, -d.sA, -d.sa, -d.sQ, d.sH, d.sh, d.sR, nullptr, 1, T};
+        eo = EmitOut{d.H + tl * d.sH, d.h + tl * d.sh, d.R + tl * d.sR, -d.sH, -d.sh, -d.sR, dmean + tl, dvar + tl, -1};
+    }
+    const int L = h->chunk > 0 ? h->chunk : 16;
+    const int64_t nchunk = (T + L - 1) / L;
+    const int64_t grid = (nchunk + kBlock - 1) / kBlock;
+    const int64_t nthreads = grid * kBlock, nwarps = nthreads / 32;
+    double *excl, *wagg, *wstate;
+    TGP_TRY(dalloc(h, (size_t)Aff<D>::N * nthreads, &excl));
+    TGP_TRY(dalloc(h, (size_t)Aff<D>::N * nwarps, &wagg));
+    TGP_TRY(dalloc(h, (size_t)SN * nwarps, &wstate));
+    k_aff_reduce<D, ModelAffProvider<D>><<<(unsigned)grid, kBlock, 0, st>>>(prov, T, L, nthreads, excl, wagg, nwarps);
+    TGP_LAUNCH_CHECK(h);
+    k_aff_mid<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, x0buf, wstate, nullptr);
+    TGP_LAUNCH_CHECK(h);
+    k_aff_apply<D, ModelAffProvider<D>><<<(unsigned)grid, kBlock, 0, st>>>(prov, T, L, nthreads, excl, wstate, nwarps, eo, rev ? 1 : 0);
+    TGP_LAUNCH_CHECK(h);
+    return end_call(h, nullptr, T, false);
+}
+
+// ---- time-sharded path -----------------------------------------------------------------------------
+template <int D>
+int do_shard_reduce(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* elem_out) {
+    if (m->ordering != TGP_FORWARD) return fail(h, TGP_EUNSUPPORTED, "time sharding runs Forward-ordered models");
+    const int64_t T = m->T;
+    cudaStream_t st = h->stream;
+    tgp_lgssm d;
+    const double* dy;
+    TGP_TRY(stage_model(h, m, y, &d, &dy));
+    double* de;
+    int64_t s1;
+    TGP_TRY(stage_out(h, elem_out, 3 * D * D + 2 * D, 3 * D * D + 2 * D, 1, &de, &s1));
+    DevModel dm{d.A, d.a, d.Q, d.H, d.h, d.R, d.sA, d.sa, d.sQ, d.sH, d.sh, d.sR, dy, 1, T};
+    const bool tv = !time_invariant(d);
+    ConstModel<D>* cm = nullptr;
+    if (!tv) {
+        TGP_TRY(dalloc(h, 1, &cm));
+        k_const_model<D><<<1, 32, 0, st>>>(dm, cm);
+        TGP_LAUNCH_CHECK(h);
+    }
+    const int L = h->chunk > 0 ? h->chunk : 16;
+    const int64_t nchunk = (T + L - 1) / L;
+    const int64_t grid = (nchunk + kBlock - 1) / kBlock;
+    const int64_t nthreads = grid * kBlock, nwarps = nthreads / 32;
+    double *excl, *wagg;
+    TGP_TRY(dalloc(h, (size_t)Elem<D>::N * nthreads, &excl));
+    TGP_TRY(dalloc(h, (size_t)Elem<D>::N * nwarps, &wagg));
+    if (tv) k_filter_reduce<D, true><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wagg, nwarps);
+    else    k_filter_reduce<D, false><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wagg, nwarps);
+    TGP_LAUNCH_CHECK(h);
+    k_elem_total<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, de);
+    TGP_LAUNCH_CHECK(h);
+    return end_call(h, nullptr, T, false);
+}
+
+template <int D>
+int do_shard_prefix(int n, const double* elems, const double* m0, const double* P0, double* m_in, double* P_in) {
+    Vec<D> m;
+    Sym<D> P;
+    for (int i = 0; i < D; ++i) m[i] = m0[i];
+    for (int j = 0; j < D; ++j)
+        for (int i = 0; i <= j; ++i) P(i, j) = P0[i + D * j];
+    const int ES = 3 * D * D + 2 * D;
+    for (int k = 0; k < n; ++k) {
+        const double* p = elems + (size_t)k * ES;
+        Elem<D> E;
+        for (int i = 0; i < D * D; ++i) E.A.v[i] = p[i];
+        for (int i = 0; i < D; ++i) E.b[i] = p[D * D + i];
+        const double* C = p + D * D + D;
+        const double* et = C + D * D;
+        const double* J = et + D;
+        for (int j = 0; j < D; ++j)
+            for (int i = 0; i <= j; ++i) { E.C(i, j) = C[i + D * j]; E.J(i, j) = J[i + D * j]; }
+        for (int i = 0; i < D; ++i) E.eta[i] = et[i];
+        apply_elem(E, m, P);
+    }
+    for (int i = 0; i < D; ++i) m_in[i] = m[i];
+    for (int j = 0; j < D; ++j)
+        for (int i = 0; i < D; ++i) P_in[i + D * j] = P(i, j);
+    return TGP_OK;
+}
+
+
+}  // namespace tgp

@@ -1,0 +1,399 @@
+"""
+gp.py — host-side mirror of the reference's GP layer (src/gp/lti_sde.jl, posterior_lti_sde.jl):
+`GP`, `to_sde`, `f(x, σ²)`, `logpdf`, `posterior`, `marginals`, `mean_and_var`. It is the CALLER of
+the hot path: O(1) (regular spacing) or O(T) (irregular) model set-up on the host with NumPy, then
+every recursion runs in libtgpb200.so through lgssm.py. The storage tag `B200Storage` plays the
+role of the reference's `StorageType` plug-in point (storage_types.jl:1, lti_sde.jl:12-14).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Union
+
+import numpy as np
+from scipy.linalg import expm
+from scipy.special import ive
+
+from . import lgssm as L
+from .lgssm import Fill, Forward, Gaussian, GaussMarkovModel, LGSSM, ScalarEmissions
+
+
+# ---- storage tags (storage_types.jl) -------------------------------------------------------------
+@dataclass(frozen=True)
+class B200Storage:
+    """Selects the B200 library for the LGSSM recursions. dtype is always float64 on this path."""
+    device: int = 0
+
+
+def SArrayStorage(dtype=np.float64):   # accepted for source compatibility; same path
+    return B200Storage()
+
+
+def ArrayStorage(dtype=np.float64):
+    return B200Storage()
+
+
+# ---- inputs --------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class RegularSpacing:
+    """regular_data.jl:8-22 — t0, t0 + Δt, ..., N points."""
+    t0: float
+    dt: float
+    N: int
+
+    def __len__(self):
+        return self.N
+
+    def collect(self):
+        return self.t0 + np.arange(self.N, dtype=np.float64) * self.dt
+
+
+def _times(x):
+    return x.collect() if isinstance(x, RegularSpacing) else np.asarray(x, dtype=np.float64)
+
+
+# ---- kernels with an SDE form (lti_sde.jl:176-373) ------------------------------------------------
+class Kernel:
+    def __add__(self, other):
+        return KernelSum(_flat(KernelSum, self) + _flat(KernelSum, other))
+
+    def __mul__(self, other):
+        if isinstance(other, Kernel):
+            return KernelProduct(_flat(KernelProduct, self) + _flat(KernelProduct, other))
+        return ScaledKernel(self, float(other))
+
+    def __rmul__(self, s):
+        return ScaledKernel(self, float(s))
+
+
+def _flat(cls, k):
+    return list(k.kernels) if isinstance(k, cls) else [k]
+
+
+class Matern12Kernel(Kernel):
+    pass
+
+
+class Matern32Kernel(Kernel):
+    pass
+
+
+class Matern52Kernel(Kernel):
+    pass
+
+
+@dataclass
+class ConstantKernel(Kernel):
+    c: float = 1.0
+
+
+@dataclass
+class ApproxPeriodicKernel(Kernel):
+    N: int = 7
+    r: float = 1.0
+
+
+@dataclass
+class ScaledKernel(Kernel):
+    kernel: Kernel
+    s2: float
+
+
+@dataclass
+class TransformedKernel(Kernel):
+    """kernel ∘ ScaleTransform(s) (lti_sde.jl:346-373)."""
+    kernel: Kernel
+    s: float
+
+
+def with_lengthscale(k: Kernel, ell: float) -> Kernel:
+    return TransformedKernel(k, 1.0 / ell)
+
+
+@dataclass
+class KernelSum(Kernel):
+    kernels: List[Kernel]
+
+
+@dataclass
+class KernelProduct(Kernel):
+    kernels: List[Kernel]
+
+
+def _sde(k):
+    """(F, H, P∞) of a simple kernel: lti_sde.jl:186-235, 290-318. F, P∞ as mathematical matrices."""
+    if isinstance(k, Matern12Kernel):
+        return np.array([[-1.0]]), np.array([1.0]), np.array([[1.0]])
+    if isinstance(k, Matern32Kernel):
+        lam = math.sqrt(3.0)
+        return np.array([[0.0, 1.0], [-lam * lam, -2.0 * lam]]), np.array([1.0, 0.0]), np.array([[1.0, 0.0], [0.0, 3.0]])
+    if isinstance(k, Matern52Kernel):
+        lam = math.sqrt(5.0)
+        kap = 5.0 / 3.0
+        F = np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [-lam ** 3, -3.0 * lam ** 2, -3.0 * lam]])
+        P = np.array([[1.0, 0.0, -kap], [0.0, kap, 0.0], [-kap, 0.0, 25.0]])
+        return F, np.array([1.0, 0.0, 0.0]), P
+    if isinstance(k, ConstantKernel):
+        return np.zeros((1, 1)), np.array([1.0]), np.array([[float(k.c)]])
+    if isinstance(k, ApproxPeriodicKernel):
+        N = k.N
+        F = np.zeros((2 * N, 2 * N))
+        P = np.zeros((2 * N, 2 * N))
+        l2 = 1.0 / (4.0 * k.r ** 2)
+        for i in range(N):
+            w = 2.0 * math.pi * i
+            F[2 * i, 2 * i + 1] = -w
+            F[2 * i + 1, 2 * i] = w
+            q = (1.0 if i == 0 else 2.0) * ive(i, l2)
+            P[2 * i, 2 * i] = P[2 * i + 1, 2 * i + 1] = q
+        return F, np.tile([1.0, 0.0], N), P
+    if isinstance(k, ScaledKernel):
+        F, H, P = _sde(k.kernel)
+        return F, math.sqrt(k.s2) * H, P
+    if isinstance(k, TransformedKernel):
+        F, H, P = _sde(k.kernel)
+        return F * k.s, H, P
+    if isinstance(k, KernelProduct):
+        F, H, P = _sde(k.kernels[0])
+        for kk in k.kernels[1:]:
+            F2, H2, P2 = _sde(kk)
+            F = np.kron(F, np.eye(F2.shape[0])) + np.kron(np.eye(F.shape[0]), F2)
+            H = np.kron(H, H2)
+            P = np.kron(P, P2)
+        return F, H, P
+    raise TypeError(f"no state-space form for kernel {k!r}")
+
+
+def _block_diag(mats):
+    n = sum(m.shape[-1] for m in mats)
+    lead = mats[0].shape[:-2]
+    out = np.zeros(lead + (n, n))
+    i = 0
+    for m in mats:
+        d = m.shape[-1]
+        out[..., i:i + d, i:i + d] = m
+        i += d
+    return out
+
+
+def lgssm_components(k: Kernel, t):
+    """lgssm_components(k, t, storage) — lti_sde.jl:131-174 and the combinators :334-418.
+    -> (As, as, Qs, Hs, hs, x0); per-step arrays are `Fill` when t is a RegularSpacing."""
+    T = len(t)
+    if isinstance(k, KernelSum):
+        parts = [lgssm_components(kk, t) for kk in k.kernels]
+        regular = all(isinstance(p[0], Fill) for p in parts)
+        def cat_m(idx):
+            if regular:
+                return Fill(_block_diag([p[idx].value for p in parts]), T)
+            return _block_diag([_dense(p[idx], T) for p in parts])
+        def cat_v(idx):
+            if all(isinstance(p[idx], Fill) for p in parts):
+                return Fill(np.concatenate([p[idx].value for p in parts]), T)
+            return np.concatenate([_dense(p[idx], T) for p in parts], axis=-1)
+        hs = parts[0][4]
+        for p in parts[1:]:
+            hs = Fill(hs.value + p[4].value, T) if isinstance(hs, Fill) and isinstance(p[4], Fill) else _dense(hs, T) + _dense(p[4], T)
+        x0 = Gaussian(np.concatenate([p[5].m for p in parts]), _block_diag([p[5].P for p in parts]))
+        return cat_m(0), cat_v(1), cat_m(2), cat_v(3), hs, x0
+    if isinstance(k, ScaledKernel):                        # lti_sde.jl:334-338: scales H and h
+        As, as_, Qs, Hs, hs, x0 = lgssm_components(k.kernel, t)
+        s = math.sqrt(k.s2)
+        sc = lambda v: Fill(s * v.value, T) if isinstance(v, Fill) else s * np.asarray(v)
+        return As, as_, Qs, sc(Hs), sc(hs), x0
+    if isinstance(k, TransformedKernel):                   # lti_sde.jl:361-373: rescales time
+        tt = RegularSpacing(k.s * t.t0, k.s * t.dt, t.N) if isinstance(t, RegularSpacing) else k.s * _times(t)
+        return lgssm_components(k.kernel, tt)
+    F, H, P = _sde(k)
+    D = F.shape[0]
+    Psym = np.triu(P) + np.triu(P, 1).T
+    if isinstance(t, RegularSpacing):
+        A = expm(F * t.dt)                       # ONE matrix exponential (lti_sde.jl:152)
+        Q = Psym - A @ Psym @ A.T
+        As, Qs = Fill(A, T), Fill(Q, T)
+    else:
+        tt = _times(t)
+        dts = np.diff(np.concatenate([[tt[0] - 1.0], tt]))   # first transition: Δt = 1 (:139)
+        uniq, inv = np.unique(dts, return_inverse=True)
+        Au = np.stack([expm(F * dt) for dt in uniq])
+        As = Au[inv]
+        Qs = Psym - As @ Psym @ np.swapaxes(As, 1, 2)
+    return As, Fill(np.zeros(D), T), Qs, Fill(H, T), Fill(np.zeros(()), T), Gaussian(np.zeros(D), P)
+
+
+def _dense(v, T):
+    if isinstance(v, Fill):
+        return np.broadcast_to(v.value, (T,) + v.value.shape).copy()
+    return np.asarray(v)
+
+
+# ---- GP objects (AbstractGPs surface) ------------------------------------------------------------
+@dataclass
+class GP:
+    kernel: Kernel
+    mean: Union[None, float, Callable[[float], float]] = None   # ZeroMean | ConstMean | CustomMean
+
+    def __post_init__(self):
+        if isinstance(self.kernel, (int, float)) or callable(self.kernel) and not isinstance(self.kernel, Kernel):
+            raise TypeError("GP(kernel[, mean])")
+
+
+def _mean_vector(mean, t):
+    tt = _times(t)
+    if mean is None:
+        return None
+    if callable(mean):
+        return np.array([mean(v) for v in tt], dtype=np.float64)
+    return np.full(len(tt), float(mean))
+
+
+@dataclass
+class LTISDE:
+    """lti_sde.jl:7-10."""
+    f: GP
+    storage: B200Storage
+
+    def __call__(self, x, noise=1e-12):      # default noise: lti_sde.jl:27-29
+        return FiniteLTISDE(self, x, noise)
+
+
+def to_sde(f: GP, storage=None) -> LTISDE:
+    """to_sde(f::GP, storage) — lti_sde.jl:12-14."""
+    return LTISDE(f, storage or B200Storage())
+
+
+def _noise_to_time_form(x, noise):
+    T = len(x)
+    if np.ndim(noise) == 0:
+        return Fill(float(noise), T)
+    noise = np.asarray(noise, dtype=np.float64)
+    if noise.ndim == 2:
+        noise = np.diag(noise)
+    if noise.shape != (T,):
+        raise L.DimensionMismatch(1, f"Dimension mismatch. length(x) is {T}, noise has shape {noise.shape}")
+    return noise
+
+
+def build_lgssm(f: LTISDE, x, noise) -> LGSSM:
+    """build_lgssm — lti_sde.jl:71-80 (+ mean handling :112-131)."""
+    As, as_, Qs, Hs, hs, x0 = lgssm_components(f.f.kernel, x)
+    mv = _mean_vector(f.f.mean, x)
+    if mv is not None:
+        hs = _dense(hs, len(x)) + mv
+    return LGSSM(GaussMarkovModel(Forward, As, as_, Qs, x0), ScalarEmissions(Hs, hs, _noise_to_time_form(x, noise)))
+
+
+@dataclass
+class FiniteLTISDE:
+    """FiniteGP{<:LTISDE} — lti_sde.jl:24."""
+    f: LTISDE
+    x: object
+    noise: object
+
+    def _handle(self):
+        return L.default_handle(self.f.storage.device)
+
+    def build_lgssm(self):
+        return build_lgssm(self.f, self.x, self.noise)
+
+
+def logpdf(fx, y):
+    """logpdf(ft::FiniteLTISDE, y) — lti_sde.jl:60-68; posterior variant posterior_lti_sde.jl:62-78."""
+    if isinstance(fx, FinitePosteriorLTISDE):
+        return _posterior_logpdf(fx, y)
+    return L.logpdf(fx.build_lgssm(), y, fx._handle())
+
+
+def marginals(fx):
+    """-> (mean, var) of the marginals (lti_sde.jl:33-44, posterior_lti_sde.jl:18-37)."""
+    if isinstance(fx, FinitePosteriorLTISDE):
+        return _posterior_marginals(fx)
+    return L.marginals(fx.build_lgssm(), fx._handle())
+
+
+mean_and_var = marginals
+
+
+def mean(fx):
+    return marginals(fx)[0]
+
+
+def var(fx):
+    return marginals(fx)[1]
+
+
+# ---- posterior (posterior_lti_sde.jl) ------------------------------------------------------------
+@dataclass
+class PosteriorLTISDE:
+    prior: LTISDE
+    y: np.ndarray
+    x: object
+    noise: object
+
+    def __call__(self, x, noise=1e-12):
+        return FinitePosteriorLTISDE(self, x, noise)
+
+
+@dataclass
+class FinitePosteriorLTISDE:
+    f: PosteriorLTISDE
+    x: object
+    noise: object
+
+
+def posterior(fx: FiniteLTISDE, y) -> PosteriorLTISDE:
+    """Lazy (posterior_lti_sde.jl:7-10)."""
+    if len(fx.x) != len(y):
+        raise L.DimensionMismatch(1, f"Dimension mismatch. length(x) is {len(fx.x)}, but length(y) is {len(y)}")
+    return PosteriorLTISDE(fx.f, np.asarray(y, dtype=np.float64), fx.x, fx.noise)
+
+
+def _same_inputs(a, b):
+    if isinstance(a, RegularSpacing) and isinstance(b, RegularSpacing):
+        return a == b
+    ta, tb = _times(a), _times(b)
+    return ta.shape == tb.shape and bool(np.all(ta == tb))
+
+
+def merge_datasets(x1, x2, S1, S2, y1, y2):
+    """posterior_lti_sde.jl:97-123 — stable sort in time; NaN marks missing."""
+    x_raw = np.concatenate([_times(x1), _times(x2)])
+    idx = np.argsort(x_raw, kind="stable")
+    inv = np.argsort(idx, kind="stable")
+    n1 = len(x1)
+    S = np.concatenate([_dense(S1, n1), _dense(S2, len(x2))])[idx]
+    ys = np.concatenate([np.asarray(y1, dtype=np.float64), np.asarray(y2, dtype=np.float64)])[idx]
+    return x_raw[idx], S, ys, inv[:n1], inv[n1:]
+
+
+def _posterior_marginals(fx: FinitePosteriorLTISDE):
+    post = fx.f
+    h = L.default_handle(post.prior.storage.device)
+    if _same_inputs(fx.x, post.x):                       # posterior_lti_sde.jl:27-36
+        model = build_lgssm(post.prior, post.x, post.noise)
+        return L.posterior_marginals(model, post.y, _noise_to_time_form(fx.x, fx.noise), h)
+    n_pr = len(fx.x)                                      # posterior_lti_sde.jl:19-26
+    x, S, ys, _tr, pr = merge_datasets(post.x, fx.x, _noise_to_time_form(post.x, post.noise), Fill(L.LARGE_VAR, n_pr),
+                                       post.y, np.full(n_pr, np.nan))
+    model = build_lgssm(post.prior, x, S)
+    R_pr = np.zeros(len(x))
+    R_pr[pr] = _dense(_noise_to_time_form(fx.x, fx.noise), n_pr)
+    mu, v = L.posterior_marginals(model, ys, R_pr, h)
+    return mu[pr], v[pr]
+
+
+def _posterior_logpdf(fx: FinitePosteriorLTISDE, y_pr):
+    """posterior_lti_sde.jl:62-78."""
+    post = fx.f
+    h = L.default_handle(post.prior.storage.device)
+    n_pr = len(fx.x)
+    S_pr = _noise_to_time_form(fx.x, fx.noise)
+    x, S, ys, tr, pr = merge_datasets(post.x, fx.x, _noise_to_time_form(post.x, post.noise), S_pr, post.y, np.full(n_pr, np.nan))
+    R_pr = np.zeros(len(x))
+    R_pr[pr] = _dense(S_pr, n_pr)
+    y_full = np.full(len(x), np.nan)
+    y_full[pr] = np.asarray(y_pr, dtype=np.float64)
+    model = build_lgssm(post.prior, x, S)
+    model_post = L.replace_observation_noise_cov(L.posterior(model, ys, h), R_pr)
+    return L.logpdf(model_post, y_full, h)

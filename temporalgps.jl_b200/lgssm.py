@@ -1,0 +1,243 @@
+"""
+lgssm.py — host-side mirror of the reference's L2 interface (src/models/lgssm.jl,
+gauss_markov_model.jl, missings.jl) over the C ABI of libtgpb200.so.
+
+Same names and argument meaning as the reference: `LGSSM`, `GaussMarkovModel`, `Forward`/`Reverse`,
+`Gaussian`, `logpdf(model, y)` (lgssm.jl:147), `_filter` (:171), `posterior` (:193), `marginals`
+(:99), plus the missing-data wrappers of missings.jl:8-23 (missing == NaN here). All arithmetic of
+the recursions happens in the CUDA library; this module only lays arrays out the way Julia would
+(column-major blocks, stride 0 for `Fill`) and maps status codes to exceptions.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field, replace
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import DimensionMismatch, Handle, PosDefException, TGPError, default_handle, tgp_lgssm
+
+Forward = "forward"   # gauss_markov_model.jl:1
+Reverse = "reverse"   # gauss_markov_model.jl:3
+
+LARGE_VAR = 1e15      # _large_var_const(), missings.jl:43
+
+
+class Fill:
+    """A time-invariant per-step array (Julia `Fill`, lti_sde.jl:148-160): one value, length T."""
+
+    def __init__(self, value, T: int):
+        self.value = np.asarray(value, dtype=np.float64)
+        self.T = int(T)
+
+    def __len__(self):
+        return self.T
+
+    def __getitem__(self, t):
+        return self.value
+
+    @property
+    def shape(self):
+        return (self.T,) + self.value.shape
+
+
+@dataclass
+class Gaussian:
+    """gaussian.jl:16-19."""
+    m: np.ndarray
+    P: np.ndarray
+
+
+@dataclass
+class GaussMarkovModel:
+    """gauss_markov_model.jl:20-32 — x[t] = A[t] x[t-1] + a[t] + N(0, Q[t])."""
+    ordering: str
+    As: object   # Fill | (T, D, D)
+    as_: object  # Fill | (T, D)
+    Qs: object   # Fill | (T, D, D)
+    x0: Gaussian
+
+    def __len__(self):
+        return len(self.As)
+
+
+@dataclass
+class ScalarEmissions:
+    """StructArray{ScalarOutputLGC} (lti_sde.jl:88-101): y[t] = H[t]·x[t] + h[t] + N(0, R[t])."""
+    Hs: object   # Fill | (T, D)
+    hs: object   # Fill | (T,)
+    Rs: object   # Fill | (T,)
+
+
+@dataclass
+class LGSSM:
+    """lgssm.jl:9-12."""
+    transitions: GaussMarkovModel
+    emissions: ScalarEmissions
+
+    def __len__(self):
+        return len(self.transitions)
+
+    @property
+    def ordering(self):
+        return self.transitions.ordering
+
+    @property
+    def D(self):
+        return int(np.asarray(self.transitions.x0.m).shape[0])
+
+
+def _per_step(x, T, inner_ndim, colmajor=False):
+    """-> (C-contiguous float64 array, stride in elements). Fill / un-batched arrays get stride 0."""
+    if isinstance(x, Fill):
+        v = x.value
+        if colmajor:
+            v = v.T
+        return np.ascontiguousarray(v, dtype=np.float64), 0
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == inner_ndim:
+        return np.ascontiguousarray(x.T if colmajor else x), 0
+    if x.shape[0] != T:
+        raise DimensionMismatch(_lib.TGP_EINVAL, f"Dimension mismatch. per-step array has length {x.shape[0]}, model has {T}")
+    if x.strides[0] == 0:
+        v = x[0]
+        return np.ascontiguousarray(v.T if colmajor else v), 0
+    if colmajor:
+        x = np.swapaxes(x, -1, -2)
+    x = np.ascontiguousarray(x)
+    return x, int(np.prod(x.shape[1:])) if x.ndim > 1 else 1
+
+
+class _Marshalled:
+    """Owns the contiguous column-major copies referenced by a tgp_lgssm descriptor."""
+
+    def __init__(self, model: LGSSM):
+        tr, em = model.transitions, model.emissions
+        T = len(model)
+        D = model.D
+        d = tgp_lgssm()
+        d.D, d.M, d.T = D, 1, T
+        d.ordering = _lib.TGP_FORWARD if tr.ordering == Forward else _lib.TGP_REVERSE
+        d.R_kind = _lib.TGP_R_SCALAR
+        self.keep = []
+        for name, sname, arr, nd, cm in (("A", "sA", tr.As, 2, True), ("a", "sa", tr.as_, 1, False), ("Q", "sQ", tr.Qs, 2, True),
+                                         ("H", "sH", em.Hs, 1, False), ("h", "sh", em.hs, 0, False), ("R", "sR", em.Rs, 0, False)):
+            a, s = _per_step(arr, T, nd, cm)
+            self.keep.append(a)
+            setattr(d, name, a.ctypes.data)
+            setattr(d, sname, s)
+        m0 = np.ascontiguousarray(tr.x0.m, dtype=np.float64)
+        P0 = np.ascontiguousarray(np.asarray(tr.x0.P, dtype=np.float64).T)
+        if m0.shape != (D,) or P0.shape != (D, D):
+            raise DimensionMismatch(_lib.TGP_EINVAL, "Dimension mismatch. x0 has the wrong shape")
+        self.keep += [m0, P0]
+        d.m0, d.P0 = m0.ctypes.data, P0.ctypes.data
+        self.desc = d
+        self.T, self.D = T, D
+
+
+def _check_inputs(model: LGSSM, y):
+    """lgssm.jl:202-208."""
+    if len(model) != len(y):
+        raise DimensionMismatch(_lib.TGP_EINVAL, f"Dimension mismatch. length(prior) is {len(model)}, but length(y) is {len(y)}")
+
+
+def _host_y(y):
+    return np.ascontiguousarray(y, dtype=np.float64)
+
+
+# ---- missing data (missings.jl:25-74): stays on the host, kernels see plain R_t ------------------
+def transform_model_and_obs(model: LGSSM, y):
+    y = np.array(y, dtype=np.float64, copy=True)
+    miss = np.isnan(y)
+    T = len(model)
+    Rs = model.emissions.Rs
+    Rs = np.full(T, float(Rs.value)) if isinstance(Rs, Fill) else np.array(Rs, dtype=np.float64, copy=True)
+    Rs[miss] = LARGE_VAR
+    y[miss] = 0.0
+    new = replace(model, emissions=replace(model.emissions, Rs=Rs))
+    return new, y, int(miss.sum())
+
+
+def _maybe_missing(model, y):
+    y = np.asarray(y, dtype=np.float64)
+    if np.isnan(y).any():
+        return transform_model_and_obs(model, y)
+    return model, y, 0
+
+
+def replace_observation_noise_cov(model: LGSSM, Rs_new) -> LGSSM:
+    """missings.jl:35-41."""
+    return replace(model, emissions=replace(model.emissions, Rs=Rs_new))
+
+
+# ---- the five entry points -----------------------------------------------------------------------
+def logpdf(model: LGSSM, y, handle: Optional[Handle] = None, per_step: bool = False):
+    """logpdf(model::LGSSM, y) — lgssm.jl:147-151 (+ missings.jl:8-13 when y has NaN)."""
+    _check_inputs(model, y)
+    h = handle or default_handle()
+    model, y, n_missing = _maybe_missing(model, y)
+    mm = _Marshalled(model)
+    out = np.zeros(1)
+    steps = np.empty(mm.T) if per_step else None
+    h.logpdf(mm.desc, _host_y(y), out, steps)
+    lml = float(out[0]) + n_missing * math.log(2.0 * math.pi * LARGE_VAR) / 2.0
+    return (lml, steps) if per_step else lml
+
+
+def _filter(model: LGSSM, y, handle: Optional[Handle] = None):
+    """_filter(model, y) — lgssm.jl:171-187. -> (ms (T, D), Ps (T, D, D)) filtering distributions."""
+    _check_inputs(model, y)
+    h = handle or default_handle()
+    model, y, _ = _maybe_missing(model, y)
+    mm = _Marshalled(model)
+    T, D = mm.T, mm.D
+    ms = np.empty((T, D))
+    Ps = np.empty((T, D, D))
+    h.filter(mm.desc, _host_y(y), ms, D, Ps, D * D, None)
+    return ms, np.swapaxes(Ps, 1, 2)
+
+
+def posterior(model: LGSSM, y, handle: Optional[Handle] = None) -> LGSSM:
+    """posterior(prior::LGSSM, y) — lgssm.jl:193-200: the Reverse-ordered posterior LGSSM."""
+    _check_inputs(model, y)
+    h = handle or default_handle()
+    model, y, _ = _maybe_missing(model, y)
+    mm = _Marshalled(model)
+    T, D = mm.T, mm.D
+    G = np.empty((T, D, D)); g = np.empty((T, D)); S = np.empty((T, D, D))
+    mT = np.empty(D); PT = np.empty((D, D))
+    h.posterior(mm.desc, _host_y(y), G, g, S, mT, PT)
+    new_order = Reverse if model.ordering == Forward else Forward
+    tr = GaussMarkovModel(new_order, np.swapaxes(G, 1, 2), g, np.swapaxes(S, 1, 2), Gaussian(mT, PT.T))
+    return LGSSM(tr, model.emissions)
+
+
+def marginals(model: LGSSM, handle: Optional[Handle] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """marginals(model::LGSSM) — lgssm.jl:99-115. -> (means (T,), variances (T,)) in emission space."""
+    h = handle or default_handle()
+    mm = _Marshalled(model)
+    mean = np.empty(mm.T)
+    var = np.empty(mm.T)
+    h.marginals(mm.desc, mean, var)
+    return mean, var
+
+
+def posterior_marginals(model: LGSSM, y, Rs_new, handle: Optional[Handle] = None, return_lml: bool = False):
+    """marginals(replace_observation_noise_cov(posterior(model, y), Rs_new)) — the chain of
+    posterior_lti_sde.jl:27-36 fused in one library call; (G, g, Sigma) are never materialised."""
+    _check_inputs(model, y)
+    h = handle or default_handle()
+    model, y, n_missing = _maybe_missing(model, y)
+    mm = _Marshalled(model)
+    Rn, sRn = _per_step(Rs_new if isinstance(Rs_new, Fill) or np.ndim(Rs_new) else Fill(Rs_new, mm.T), mm.T, 0)
+    Rn = np.atleast_1d(Rn)
+    mean = np.empty(mm.T)
+    var = np.empty(mm.T)
+    lml = np.zeros(1)
+    h.posterior_marginals(mm.desc, _host_y(y), Rn, sRn, mean, var, lml)
+    if return_lml:
+        return mean, var, float(lml[0]) + n_missing * math.log(2.0 * math.pi * LARGE_VAR) / 2.0
+    return mean, var

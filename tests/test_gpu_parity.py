@@ -1,0 +1,235 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libtgpb200.so) against the CPU oracle on the
+same seeded inputs. Tolerances are north_star's: 1e-6 relative on logpdf, 1e-5 on means/variances."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, tgp_oracle as O
+from tests.util import random_lgssm, relerr, sample_y, to_pkg_model
+
+pytestmark = pytest.mark.gpu
+
+LML_RTOL = 1e-6
+MV_RTOL = 1e-5
+
+
+def _check_filter(pkg, handle, m, y, atol=1e-9):
+    pm = to_pkg_model(pkg, m)
+    ms_o, Ps_o, lmls_o = O.filter_(m, y)
+    lml, steps = pkg.lgssm.logpdf(pm, y, handle, per_step=True)
+    assert abs(lml - lmls_o.sum()) <= LML_RTOL * abs(lmls_o.sum()) + 1e-9
+    np.testing.assert_allclose(steps, lmls_o, rtol=1e-6, atol=1e-8)
+    lml2 = pkg.lgssm.logpdf(pm, y, handle)
+    assert abs(lml2 - lmls_o.sum()) <= LML_RTOL * abs(lmls_o.sum()) + 1e-9
+    ms, Ps = pkg.lgssm._filter(pm, y, handle)
+    np.testing.assert_allclose(ms, ms_o, rtol=MV_RTOL, atol=atol)
+    np.testing.assert_allclose(Ps, Ps_o, rtol=MV_RTOL, atol=atol)
+
+
+@pytest.mark.parametrize("algo", ["auto", "scan"])
+@pytest.mark.parametrize("ordering", ["forward", "reverse"])
+@pytest.mark.parametrize("tv", [True, False])
+@pytest.mark.parametrize("D", [1, 2, 3, 4])
+@pytest.mark.parametrize("T", [1, 2, 13, 49, 1000])
+def test_filter_random_models(pkg, handle, T, D, tv, ordering, algo):
+    handle.set_algo(pkg.TGP_ALGO_AUTO if algo == "auto" else pkg.TGP_ALGO_SCAN)
+    rng = np.random.default_rng(1000 * T + 10 * D + tv)
+    m = random_lgssm(rng, T, D, ordering, tv)
+    y = sample_y(rng, m)
+    try:
+        _check_filter(pkg, handle, m, y)
+    finally:
+        handle.set_algo(pkg.TGP_ALGO_AUTO)
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 16, 64])
+def test_chunk_sizes(pkg, handle, chunk):
+    rng = np.random.default_rng(7)
+    m = random_lgssm(rng, 5000, 3, "forward", True)
+    y = sample_y(rng, m)
+    handle.set_chunk(chunk)
+    handle.set_algo(pkg.TGP_ALGO_SCAN)
+    try:
+        _check_filter(pkg, handle, m, y)
+    finally:
+        handle.set_chunk(0)
+        handle.set_algo(pkg.TGP_ALGO_AUTO)
+
+
+KERNELS = {
+    "m12": (lambda p: p.Matern12Kernel(), lambda: O.Matern12()),
+    "m32": (lambda p: p.Matern32Kernel(), lambda: O.Matern32()),
+    "m52": (lambda p: p.Matern52Kernel(), lambda: O.Matern52()),
+    "m52_scaled_stretched": (lambda p: 1.5 * p.with_lengthscale(p.Matern52Kernel(), 2.3),
+                             lambda: 1.5 * O.Matern52().stretch(1 / 2.3)),
+    "sum_m12_m32": (lambda p: p.Matern12Kernel() + 0.7 * p.Matern32Kernel(), lambda: O.Matern12() + 0.7 * O.Matern32()),
+}
+
+
+@pytest.mark.parametrize("regular", [True, False])
+@pytest.mark.parametrize("kname", list(KERNELS))
+def test_gp_logpdf_and_posterior_small(pkg, kname, regular):
+    """The reference's integration checks (test/gp/lti_sde.jl:192-201, posterior_lti_sde.jl:82-89)
+    at its own size N=13, against the oracle AND the dense GP."""
+    kp, ko = KERNELS[kname]
+    N = 13
+    rng = np.random.default_rng(123456)
+    tp = pkg.RegularSpacing(0.0, 0.3, N) if regular else pkg.RegularSpacing(0.0, 0.3, N).collect()
+    to = O.RegularSpacing(0.0, 0.3, N) if regular else O.RegularSpacing(0.0, 0.3, N).collect()
+    y = O.sample_prior(O.build_lgssm(ko(), to, 0.1), rng)
+    fx = pkg.to_sde(pkg.GP(kp()))(tp, 0.1)
+    lml = pkg.gp.logpdf(fx, y)
+    assert abs(lml - O.gp_logpdf(ko(), to, 0.1, y)) <= LML_RTOL * abs(lml)
+    assert abs(lml - O.dense_logpdf(ko(), to, 0.1, y)) <= 1e-6 * abs(lml)
+    mu, var = pkg.gp.marginals(fx)
+    mu_d, var_d = O.dense_prior_marginals(ko(), to, 0.1)
+    np.testing.assert_allclose(mu, mu_d, atol=1e-9)
+    np.testing.assert_allclose(var, var_d, rtol=1e-9)
+    # posterior at the training inputs and at new inputs
+    post = pkg.gp.posterior(fx, y)
+    mu, var = pkg.gp.marginals(post(tp, 0.3))
+    mu_o, var_o = O.gp_posterior_marginals(ko(), to, 0.1, y, None, 0.3)
+    np.testing.assert_allclose(mu, mu_o, rtol=MV_RTOL, atol=1e-8)
+    np.testing.assert_allclose(var, var_o, rtol=MV_RTOL)
+    t_pr = np.sort(rng.uniform(-0.5, 4.5, 5))
+    mu, var = pkg.gp.marginals(post(t_pr, 0.3))
+    mu_d, cov_d = O.dense_posterior(ko(), to, 0.1, y, t_pr, 0.3)
+    np.testing.assert_allclose(mu, mu_d, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(var, np.diag(cov_d), rtol=1e-5)
+    y_pr = rng.standard_normal(5)
+    lp = pkg.gp.logpdf(post(t_pr, 0.3), y_pr)
+    lp_d = O.dense_posterior_logpdf(ko(), to, 0.1, y, t_pr, 0.3, y_pr)
+    assert abs(lp - lp_d) <= 1e-5 * abs(lp_d)
+
+
+@pytest.mark.parametrize("T", [1, 5, 257, 4000])
+@pytest.mark.parametrize("D", [1, 2, 3])
+def test_posterior_marginals_and_dynamics(pkg, handle, T, D):
+    rng = np.random.default_rng(50 + T + D)
+    m = random_lgssm(rng, T, D, "forward", True)
+    y = sample_y(rng, m)
+    pm = to_pkg_model(pkg, m)
+    Rn = rng.uniform(0.01, 0.5, T)
+    post_o = O.posterior(m, y)
+    mu_o, var_o = O.marginals(O.replace_observation_noise_cov(post_o, Rn))
+    mu, var, lml = pkg.lgssm.posterior_marginals(pm, y, Rn, handle, return_lml=True)
+    np.testing.assert_allclose(mu, mu_o, rtol=MV_RTOL, atol=1e-8)
+    np.testing.assert_allclose(var, var_o, rtol=MV_RTOL)
+    assert abs(lml - O.logpdf(m, y)) <= LML_RTOL * abs(lml) + 1e-9
+    post = pkg.lgssm.posterior(pm, y, handle)
+    np.testing.assert_allclose(post.transitions.As, post_o.As, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(post.transitions.as_, post_o.as_, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(post.transitions.Qs, post_o.Qs, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(post.transitions.x0.m, post_o.m0, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(post.transitions.x0.P, post_o.P0, rtol=1e-6, atol=1e-9)
+    # marginals of the materialised Reverse model run through tgp_marginals
+    mu2, var2 = pkg.lgssm.marginals(pkg.lgssm.replace_observation_noise_cov(post, Rn), handle)
+    np.testing.assert_allclose(mu2, mu_o, rtol=MV_RTOL, atol=1e-8)
+    np.testing.assert_allclose(var2, var_o, rtol=MV_RTOL)
+
+
+def test_missing_observations(pkg, handle):
+    """test/models/missings.jl:94-115 — missing == NaN; compared with the oracle's transform."""
+    rng = np.random.default_rng(9)
+    m = random_lgssm(rng, 300, 3, "forward", True)
+    y = sample_y(rng, m)
+    y[rng.uniform(size=300) < 0.3] = np.nan
+    pm = to_pkg_model(pkg, m)
+    lml = pkg.lgssm.logpdf(pm, y, handle)
+    ref = O.logpdf_missing(m, y)
+    assert abs(lml - ref) <= LML_RTOL * abs(ref)
+
+
+def test_cfg1_matern32_readme(pkg, handle):
+    """BASELINE config 1: Matern32, RegularSpacing(0, 0.1, 10_000), sigma^2 = 0.1 (README.md:28-42)."""
+    T = 10_000
+    to = O.RegularSpacing(0.0, 0.1, T)
+    mo = O.build_lgssm(O.Matern32(), to, 0.1)
+    y = O.sample_prior(mo, np.random.default_rng(20261017 + 1))
+    cm = c_oracle.Model.from_lgssm(mo)
+    ref = c_oracle.filter(cm, y)
+    fx = pkg.to_sde(pkg.GP(pkg.Matern32Kernel()), pkg.SArrayStorage(np.float64))(pkg.RegularSpacing(0.0, 0.1, T), 0.1)
+    for algo in (pkg.TGP_ALGO_AUTO, pkg.TGP_ALGO_SCAN):
+        handle.set_algo(algo)
+        try:
+            lml = pkg.gp.logpdf(fx, y)
+            assert abs(lml - ref["lml"]) <= LML_RTOL * abs(ref["lml"])
+            ms, Ps = pkg.lgssm._filter(fx.build_lgssm(), y, handle)
+            np.testing.assert_allclose(ms, ref["m"], rtol=MV_RTOL, atol=1e-9)
+            np.testing.assert_allclose(Ps, ref["P"], rtol=MV_RTOL, atol=1e-12)
+        finally:
+            handle.set_algo(pkg.TGP_ALGO_AUTO)
+    # first 2 000 points against the dense GP (SURVEY.md §8d cfg 1)
+    n = 2000
+    fx2 = pkg.to_sde(pkg.GP(pkg.Matern32Kernel()))(pkg.RegularSpacing(0.0, 0.1, n), 0.1)
+    d = O.dense_logpdf(O.Matern32(), O.RegularSpacing(0.0, 0.1, n), 0.1, y[:n])
+    assert abs(pkg.gp.logpdf(fx2, y[:n]) - d) <= 1e-6 * abs(d)
+    mu, var = pkg.gp.marginals(pkg.gp.posterior(fx, y)(pkg.RegularSpacing(0.0, 0.1, T), 1e-2))
+    mu_o, var_o, _ = c_oracle.posterior_marginals(cm, y, 1e-2)
+    np.testing.assert_allclose(mu, mu_o, rtol=MV_RTOL, atol=1e-8)
+    np.testing.assert_allclose(var, var_o, rtol=MV_RTOL)
+
+
+@pytest.mark.parametrize("T", [10**6])
+def test_cfg2_matern52_large(pkg, handle, T):
+    """BASELINE config 2 shape (Matern52, dt = 0.01, sigma^2 = 0.1) at a size the C oracle runs in
+    well under a second."""
+    to = O.RegularSpacing(0.0, 0.01, T)
+    mo = O.build_lgssm(O.Matern52(), to, 0.1)
+    rng = np.random.default_rng(20261017 + 2)
+    y = np.cumsum(rng.standard_normal(T)) * 0.01 + rng.standard_normal(T) * 0.3
+    cm = c_oracle.Model.from_lgssm(mo)
+    ref = c_oracle.filter(cm, y)
+    fx = pkg.to_sde(pkg.GP(pkg.Matern52Kernel()))(pkg.RegularSpacing(0.0, 0.01, T), 0.1)
+    for algo in (pkg.TGP_ALGO_AUTO, pkg.TGP_ALGO_SCAN):
+        handle.set_algo(algo)
+        try:
+            lml, steps = pkg.lgssm.logpdf(fx.build_lgssm(), y, handle, per_step=True)
+            assert abs(lml - ref["lml"]) <= LML_RTOL * abs(ref["lml"])
+            np.testing.assert_allclose(steps, ref["lml_steps"], rtol=1e-6, atol=1e-8)
+            ms, Ps = pkg.lgssm._filter(fx.build_lgssm(), y, handle)
+            np.testing.assert_allclose(ms, ref["m"], rtol=MV_RTOL, atol=1e-8)
+            np.testing.assert_allclose(Ps, ref["P"], rtol=MV_RTOL, atol=1e-12)
+        finally:
+            handle.set_algo(pkg.TGP_ALGO_AUTO)
+
+
+def test_errors(pkg, handle):
+    rng = np.random.default_rng(3)
+    m = random_lgssm(rng, 20, 2, "forward", True)
+    pm = to_pkg_model(pkg, m)
+    with pytest.raises(pkg.DimensionMismatch):
+        pkg.lgssm.logpdf(pm, np.zeros(19), handle)
+    # negative innovation variance -> PosDefException-like status with the failing index
+    bad = O.LGSSM("forward", m.As, m.as_, m.Qs, m.m0, m.P0, m.Hs, m.hs, np.full(20, -1e6))
+    with pytest.raises(pkg.PosDefException):
+        pkg.lgssm.logpdf(to_pkg_model(pkg, bad), np.zeros(20), handle)
+    big = random_lgssm(rng, 5, 7, "forward", True)
+    with pytest.raises(pkg.TGPError):
+        pkg.lgssm.logpdf(to_pkg_model(pkg, big), np.zeros(5), handle)
+
+
+def test_shard_reduce_prefix(pkg, handle):
+    """Time-sharded logpdf on one GPU: 4 shards, elements folded on the host."""
+    rng = np.random.default_rng(11)
+    T, D, G = 4000, 3, 4
+    m = random_lgssm(rng, T, D, "forward", True)
+    y = sample_y(rng, m)
+    ref = O.logpdf(m, y)
+    ES = 3 * D * D + 2 * D
+    elems = np.zeros((G, ES))
+    bounds = np.linspace(0, T, G + 1).astype(int)
+    shards = []
+    for r in range(G):
+        s, e = bounds[r], bounds[r + 1]
+        sm = O.LGSSM("forward", m.As[s:e], m.as_[s:e], m.Qs[s:e], m.m0, m.P0, m.Hs[s:e], m.hs[s:e], m.Rs[s:e])
+        shards.append(sm)
+        mm = pkg.lgssm._Marshalled(to_pkg_model(pkg, sm))
+        handle.shard_reduce(mm.desc, np.ascontiguousarray(y[s:e]), elems[r])
+    total = 0.0
+    for r in range(G):
+        s, e = bounds[r], bounds[r + 1]
+        m_in, P_in = handle.shard_prefix(D, elems[:r] if r else None, m.m0, m.P0)
+        sm = shards[r]
+        sm2 = O.LGSSM("forward", sm.As, sm.as_, sm.Qs, m_in, P_in, sm.Hs, sm.hs, sm.Rs)
+        total += pkg.lgssm.logpdf(to_pkg_model(pkg, sm2), y[s:e], handle)
+    assert abs(total - ref) <= LML_RTOL * abs(ref)
