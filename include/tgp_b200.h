@@ -53,6 +53,8 @@ extern "C" {
 #define TGP_ALGO_SCAN        1  /* always the general 5-tuple associative scan                 */
 #define TGP_OPT_CHUNK        2  /* steps per thread in the scan kernels (0 = auto)              */
 #define TGP_OPT_SS_TOL       3  /* (double bits) relative tolerance for steady-state detection  */
+#define TGP_OPT_TIMING       4  /* 1: bracket every kernel launch with CUDA events (tgp_get_timing) */
+#define TGP_OPT_SS_PREFIX    5  /* steps filtered by the general scan before the steady-state test */
 
 typedef struct tgp_ctx* tgp_handle;
 
@@ -87,6 +89,10 @@ const char* tgp_version(void);
 int         tgp_set_option(tgp_handle h, int option, int64_t value);
 /* counters since create: kernels launched by this library, bytes copied H2D / D2H */
 int         tgp_get_counters(tgp_handle h, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
+/* Per-kernel device time accumulated since TGP_OPT_TIMING was switched on (measurement aid for
+ * bench.py's roofline leg; synchronises the stream). Writes up to `cap` records sorted by total
+ * time, returns the number of distinct kernels. names[i] points to a static string. */
+int         tgp_get_timing(tgp_handle h, int cap, const char** names, double* total_ms, int64_t* calls);
 /* run subsequent work of this handle on a caller-owned cudaStream_t (0 = handle's own) */
 int         tgp_set_stream(tgp_handle h, void* cuda_stream);
 

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libtgpb200.so")
 TGP_OK, TGP_EINVAL, TGP_ENOTPD, TGP_ECUDA, TGP_ENOMEM, TGP_EUNSUPPORTED = range(6)
 TGP_FORWARD, TGP_REVERSE = 0, 1
 TGP_R_SCALAR, TGP_R_DIAG, TGP_R_DENSE = 0, 1, 2
-TGP_OPT_ALGO, TGP_OPT_CHUNK, TGP_OPT_SS_TOL = 1, 2, 3
+TGP_OPT_ALGO, TGP_OPT_CHUNK, TGP_OPT_SS_TOL, TGP_OPT_TIMING, TGP_OPT_SS_PREFIX = 1, 2, 3, 4, 5
 TGP_ALGO_AUTO, TGP_ALGO_SCAN = 0, 1
 
 
@@ -59,6 +59,7 @@ _SIGS = {
     "tgp_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int64]),
     "tgp_get_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tgp_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tgp_get_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "tgp_logpdf": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgp_filter": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                              C.c_void_p]),
@@ -127,8 +128,8 @@ class Handle:
         self.device = device
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().tgp_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.tgp_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -154,6 +155,17 @@ class Handle:
 
     def set_ss_tol(self, tol):
         self.set_option(TGP_OPT_SS_TOL, int(np.float64(tol).view(np.int64)))
+
+    def set_timing(self, on: bool):
+        self.set_option(TGP_OPT_TIMING, 1 if on else 0)
+
+    def timing(self, cap: int = 32):
+        """-> list of (kernel name, total ms, launches), sorted by total device time."""
+        names = (C.c_char_p * cap)()
+        ms = (C.c_double * cap)()
+        n = (C.c_int64 * cap)()
+        k = lib().tgp_get_timing(self._h, cap, names, ms, n)
+        return [(names[i].decode(), ms[i], n[i]) for i in range(min(k, cap))]
 
     def set_stream(self, cuda_stream: int):
         self.check(lib().tgp_set_stream(self._h, cuda_stream))

@@ -101,6 +101,8 @@ void tgp_destroy(tgp_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     h->arena.release();
+    for (auto& sp : h->spans) { cudaEventDestroy(sp.t0); cudaEventDestroy(sp.t1); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -126,6 +128,18 @@ int tgp_set_option(tgp_handle h, int option, int64_t value) {
             h->ss_tol = v;
             return TGP_OK;
         }
+        case TGP_OPT_TIMING:
+            h->timing = value != 0;
+            if (!h->timing) {
+                cudaStreamSynchronize(h->stream);
+                for (auto& sp : h->spans) { h->ev_pool.push_back(sp.t0); h->ev_pool.push_back(sp.t1); }
+                h->spans.clear();
+            }
+            return TGP_OK;
+        case TGP_OPT_SS_PREFIX:
+            if (value < 0 || value > (int64_t(1) << 24)) return fail(h, TGP_EINVAL, "steady-state prefix must be in 0..2^24");
+            h->ss_prefix = value;
+            return TGP_OK;
         default: return fail(h, TGP_EINVAL, "unknown option %d", option);
     }
 }
@@ -136,6 +150,29 @@ int tgp_get_counters(tgp_handle h, int64_t* launches, int64_t* h2d_bytes, int64_
     if (h2d_bytes) *h2d_bytes = h->h2d;
     if (d2h_bytes) *d2h_bytes = h->d2h;
     return TGP_OK;
+}
+
+int tgp_get_timing(tgp_handle h, int cap, const char** names, double* total_ms, int64_t* calls) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    struct Acc { const char* name; double ms; int64_t n; };
+    std::vector<Acc> acc;
+    for (auto& sp : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.t0, sp.t1) != cudaSuccess) { cudaGetLastError(); continue; }
+        bool found = false;
+        for (auto& a : acc)
+            if (!strcmp(a.name, sp.name)) { a.ms += ms; ++a.n; found = true; break; }
+        if (!found) acc.push_back({sp.name, (double)ms, 1});
+    }
+    std::sort(acc.begin(), acc.end(), [](const Acc& x, const Acc& y) { return x.ms > y.ms; });
+    for (int i = 0; i < (int)acc.size() && i < cap; ++i) {
+        if (names) names[i] = acc[i].name;
+        if (total_ms) total_ms[i] = acc[i].ms;
+        if (calls) calls[i] = acc[i].n;
+    }
+    return (int)acc.size();
 }
 
 int tgp_set_stream(tgp_handle h, void* cuda_stream) {

@@ -65,11 +65,19 @@ struct tgp_ctx {
     int64_t launches = 0, h2d = 0, d2h = 0;
     int algo = TGP_ALGO_AUTO;
     int chunk = 0;
-    double ss_tol = 1e-15;
+    double ss_tol = 1e-13;
+    int64_t ss_prefix = 0;   // 0 = auto
     int sm_count = 148;
     double* pinned = nullptr;  // small pinned scratch for scalar results
     struct Pending { void* host; const void* dev; size_t bytes; size_t width, hpitch, dpitch, rows; };
     std::vector<Pending> pending;  // host outputs to copy back at the end of the call
+    // optional per-kernel timing (TGP_OPT_TIMING): CUDA events around every launch on h->stream
+    bool timing = false;
+    struct Span { const char* name; cudaEvent_t t0, t1; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    const char* cur_name = nullptr;
+    cudaEvent_t cur_t0 = nullptr;
 };
 
 namespace tgp {
@@ -155,12 +163,35 @@ inline int flush_outputs(tgp_ctx* h) {
         if (rc_ != TGP_OK) return rc_; \
     } while (0)
 
+inline cudaEvent_t prof_event(tgp_ctx* h) {
+    cudaEvent_t e = nullptr;
+    if (!h->ev_pool.empty()) { e = h->ev_pool.back(); h->ev_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+// before a launch: remember the kernel's name and (timing mode) record a start event
+inline void prof_begin(tgp_ctx* h, const char* name) {
+    h->cur_name = name;
+    if (h->timing) { h->cur_t0 = prof_event(h); cudaEventRecord(h->cur_t0, h->stream); }
+}
+inline void prof_end(tgp_ctx* h) {
+    if (h->timing && h->cur_t0) {
+        cudaEvent_t t1 = prof_event(h);
+        cudaEventRecord(t1, h->stream);
+        h->spans.push_back({h->cur_name, h->cur_t0, t1});
+        h->cur_t0 = nullptr;
+    }
+}
+#define TGP_K(h, name) tgp::prof_begin(h, name)
+
 #define TGP_LAUNCH_CHECK(h)                                                                     \
     do {                                                                                        \
         cudaError_t e_ = cudaGetLastError();                                                    \
         if (e_ != cudaSuccess)                                                                  \
-            return fail(h, TGP_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return tgp::fail(h, TGP_ECUDA, "launch of %s failed: %s (%s:%d)", (h)->cur_name ? (h)->cur_name : "kernel", \
+                             cudaGetErrorString(e_), __FILE__, __LINE__);                       \
         ++(h)->launches;                                                                        \
+        tgp::prof_end(h);                                                                       \
     } while (0)
 
 template <class T>

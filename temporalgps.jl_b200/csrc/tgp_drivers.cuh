@@ -27,15 +27,28 @@ inline int stage_model(tgp_ctx* h, const tgp_lgssm* m, const double* y, tgp_lgss
 
 inline bool time_invariant(const tgp_lgssm& m) { return !(m.sA | m.sa | m.sQ | m.sH | m.sh | m.sR); }
 
-// End of a call: copy back host outputs, fetch the failing-step word, wait.
-inline int end_call(tgp_ctx* h, const unsigned long long* err_step, int64_t T, bool reverse_t) {
-    TGP_TRY(flush_outputs(h));
+// End of a call: copy back host outputs, fetch the failing-step word (and the steady-state
+// convergence word, if any), wait. *ss_converged is left untouched when ss_flag is NULL.
+inline int end_call(tgp_ctx* h, const unsigned long long* err_step, int64_t T, bool reverse_t, const int* ss_flag = nullptr,
+                    bool* ss_converged = nullptr) {
     unsigned long long* perr = (unsigned long long*)h->pinned;
+    int* pflag = (int*)(h->pinned + 2);
     *perr = ~0ull;
+    *pflag = 1;
+    if (ss_flag) {
+        TGP_CUDA(h, cudaMemcpyAsync(pflag, ss_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        h->d2h += 4;
+    }
     if (err_step) {
         TGP_CUDA(h, cudaMemcpyAsync(perr, err_step, sizeof(*perr), cudaMemcpyDeviceToHost, h->stream));
         h->d2h += 8;
     }
+    if (ss_flag) {  // outputs are only valid if the steady-state test passed: look before copying back
+        TGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (ss_converged) *ss_converged = *pflag != 0;
+        if (*pflag == 0 && *perr == ~0ull) return TGP_OK;
+    }
+    TGP_TRY(flush_outputs(h));
     TGP_CUDA(h, cudaStreamSynchronize(h->stream));
     if (*perr != ~0ull) {
         const long long n = (long long)*perr;
@@ -63,6 +76,7 @@ int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& 
 
     // x0 (and, for Reverse, the leading update of the last memory index; lgssm.jl:161-165)
     const int64_t tl = T - 1;
+    TGP_K(h, "k_init_state");
     k_init_state<D><<<1, 32, 0, st>>>(d.m0, d.P0, rq.x0buf, rev ? 1 : 0, d.H + tl * d.sH, d.h + tl * d.sh, d.R + tl * d.sR,
                                       dy + tl, lml_extra, rq.lml_steps ? rq.lml_steps + tl : nullptr,
                                       rq.m_f ? rq.m_f + tl * rq.s_m : nullptr, rq.P_f ? rq.P_f + tl * rq.s_P : nullptr,
@@ -86,6 +100,7 @@ int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& 
     ConstModel<D>* cm = nullptr;
     if (!tv) {
         TGP_TRY(dalloc(h, 1, &cm));
+        TGP_K(h, "k_const_model");
         k_const_model<D><<<1, 32, 0, st>>>(dm, cm);
         TGP_LAUNCH_CHECK(h);
     }
@@ -98,9 +113,11 @@ int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& 
     TGP_TRY(dalloc(h, (size_t)Elem<D>::N * nwarps, &wagg));
     TGP_TRY(dalloc(h, (size_t)SN * nwarps, &wstate));
     TGP_TRY(dalloc(h, (size_t)grid, &partials));
+    TGP_K(h, "k_filter_reduce");
     if (tv) k_filter_reduce<D, true><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wagg, nwarps);
     else    k_filter_reduce<D, false><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wagg, nwarps);
     TGP_LAUNCH_CHECK(h);
+    TGP_K(h, "k_filter_mid");
     k_filter_mid<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, rq.x0buf, wstate, rq.xT);
     TGP_LAUNCH_CHECK(h);
     FilterOut fo;
@@ -115,9 +132,11 @@ int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& 
     fo.ws_m = rq.ws;   // forward only (checked by callers): index = scan step = time, stride Ts == T
     fo.partials = partials;
     fo.err_step = rq.err;
+    TGP_K(h, "k_filter_apply");
     if (tv) k_filter_apply<D, true><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wstate, nwarps, fo);
     else    k_filter_apply<D, false><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wstate, nwarps, fo);
     TGP_LAUNCH_CHECK(h);
+    TGP_K(h, "k_sum_partials");
     k_sum_partials<<<1, 256, 0, st>>>(partials, grid, lml_extra, rq.lml_dev);
     TGP_LAUNCH_CHECK(h);
     return deliver_scalar(h, rq.lml_dev, rq.lml_out);
@@ -130,23 +149,29 @@ inline int64_t err_T(const tgp_lgssm& d) { return d.ordering == TGP_REVERSE ? d.
 template <int D>
 int do_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* m_f, int64_t s_m, double* P_f, int64_t s_P,
               double* lml_out, double* lml_steps) {
-    tgp_lgssm d;
-    const double* dy;
-    TGP_TRY(stage_model(h, m, y, &d, &dy));
-    FilterReq rq;
-    rq.lml_out = lml_out;
-    int64_t ds;
-    TGP_TRY(stage_out(h, lml_steps, 1, 1, m->T, &rq.lml_steps, &ds));
-    TGP_TRY(stage_out(h, m_f, D, s_m, m->T, &rq.m_f, &rq.s_m));
-    TGP_TRY(stage_out(h, P_f, D * D, s_P, m->T, &rq.P_f, &rq.s_P));
-    int rc = TGP_EUNSUPPORTED;
-    bool handled = false;
-    if (h->algo == TGP_ALGO_AUTO && m->ordering == TGP_FORWARD && time_invariant(*m)) {
-        rc = filter_steady<D>(h, d, dy, rq, &handled);
-        if (rc != TGP_OK) return rc;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        tgp_lgssm d;
+        const double* dy;
+        TGP_TRY(stage_model(h, m, y, &d, &dy));
+        FilterReq rq;
+        rq.lml_out = lml_out;
+        int64_t ds;
+        TGP_TRY(stage_out(h, lml_steps, 1, 1, m->T, &rq.lml_steps, &ds));
+        TGP_TRY(stage_out(h, m_f, D, s_m, m->T, &rq.m_f, &rq.s_m));
+        TGP_TRY(stage_out(h, P_f, D * D, s_P, m->T, &rq.P_f, &rq.s_P));
+        bool handled = false;
+        const int* flag = nullptr;
+        if (attempt == 0 && h->algo == TGP_ALGO_AUTO && m->ordering == TGP_FORWARD && time_invariant(*m))
+            TGP_TRY(filter_steady<D>(h, d, dy, rq, &handled, &flag));
+        if (!handled) TGP_TRY(filter_general<D>(h, d, dy, rq));
+        bool converged = true;
+        TGP_TRY(end_call(h, rq.err, err_T(d), m->ordering == TGP_REVERSE, flag, &converged));
+        if (converged) return TGP_OK;
+        // P had not reached its fixed point after the transient: redo the series with the general scan
+        h->pending.clear();
+        TGP_CUDA(h, h->arena.reset());
     }
-    if (!handled) TGP_TRY(filter_general<D>(h, d, dy, rq));
-    return end_call(h, rq.err, err_T(d), m->ordering == TGP_REVERSE);
+    return fail(h, TGP_ECUDA, "internal: steady-state fallback did not terminate");
 }
 
 // ---- backward pass over the stored filtering distributions (posterior marginals) -----------------
@@ -184,12 +209,15 @@ int do_posterior_marginals(tgp_ctx* h, const tgp_lgssm* m, const double* y, cons
     TGP_TRY(dalloc(h, (size_t)Aff<D>::N * nthreads, &excl));
     TGP_TRY(dalloc(h, (size_t)Aff<D>::N * nwarps, &wagg));
     TGP_TRY(dalloc(h, (size_t)SN * nwarps, &wstate));
+    TGP_K(h, "k_aff_reduce");
     k_aff_reduce<D, SmootherProvider<D>><<<(unsigned)grid, kBlock, 0, st>>>(prov, T, L, nthreads, excl, wagg, nwarps);
     TGP_LAUNCH_CHECK(h);
+    TGP_K(h, "k_aff_mid");
     k_aff_mid<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, rq.xT, wstate, nullptr);
     TGP_LAUNCH_CHECK(h);
     const int64_t tl = T - 1;
     EmitOut eo{d.H + tl * d.sH, d.h + tl * d.sh, dRn + tl * sRnew, -d.sH, -d.sh, -sRnew, dmean + tl, dvar + tl, -1};
+    TGP_K(h, "k_aff_apply");
     k_aff_apply<D, SmootherProvider<D>><<<(unsigned)grid, kBlock, 0, st>>>(prov, T, L, nthreads, excl, wstate, nwarps, eo, 1);
     TGP_LAUNCH_CHECK(h);
     return end_call(h, rq.err, T, false);
@@ -219,11 +247,13 @@ int do_posterior(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* G, dou
     prov.x0buf = rq.x0buf;
     prov.err_step = rq.err;
     if (dG && dg && dS) {
+        TGP_K(h, "k_posterior_dynamics");
         k_posterior_dynamics<D><<<(unsigned)((T + kBlock - 1) / kBlock), kBlock, 0, st>>>(prov, dG, dg, dS);
         TGP_LAUNCH_CHECK(h);
     } else if (dG || dg || dS) {
         return fail(h, TGP_EINVAL, "G, g and Sig must be all NULL or all non-NULL");
     }
+    TGP_K(h, "k_unpack_state");
     k_unpack_state<D><<<1, 32, 0, st>>>(rq.xT, dmT, dPT);
     TGP_LAUNCH_CHECK(h);
     return end_call(h, rq.err, T, false);
@@ -242,6 +272,7 @@ int do_marginals(tgp_ctx* h, const tgp_lgssm* m, double* mean_out, double* var_o
     TGP_TRY(stage_out(h, mean_out, 1, 1, T, &dmean, &s1));
     TGP_TRY(stage_out(h, var_out, 1, 1, T, &dvar, &s1));
     TGP_TRY(dalloc(h, SN, &x0buf));
+    TGP_K(h, "k_init_state");
     k_init_state<D><<<1, 32, 0, st>>>(d.m0, d.P0, x0buf, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                       nullptr, 0, 0, nullptr);
     TGP_LAUNCH_CHECK(h);
@@ -263,10 +294,13 @@ int do_marginals(tgp_ctx* h, const tgp_lgssm* m, double* mean_out, double* var_o
     TGP_TRY(dalloc(h, (size_t)Aff<D>::N * nthreads, &excl));
     TGP_TRY(dalloc(h, (size_t)Aff<D>::N * nwarps, &wagg));
     TGP_TRY(dalloc(h, (size_t)SN * nwarps, &wstate));
+    TGP_K(h, "k_aff_reduce");
     k_aff_reduce<D, ModelAffProvider<D>><<<(unsigned)grid, kBlock, 0, st>>>(prov, T, L, nthreads, excl, wagg, nwarps);
     TGP_LAUNCH_CHECK(h);
+    TGP_K(h, "k_aff_mid");
     k_aff_mid<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, x0buf, wstate, nullptr);
     TGP_LAUNCH_CHECK(h);
+    TGP_K(h, "k_aff_apply");
     k_aff_apply<D, ModelAffProvider<D>><<<(unsigned)grid, kBlock, 0, st>>>(prov, T, L, nthreads, excl, wstate, nwarps, eo, rev ? 1 : 0);
     TGP_LAUNCH_CHECK(h);
     return end_call(h, nullptr, T, false);
@@ -289,6 +323,7 @@ int do_shard_reduce(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* ele
     ConstModel<D>* cm = nullptr;
     if (!tv) {
         TGP_TRY(dalloc(h, 1, &cm));
+        TGP_K(h, "k_const_model");
         k_const_model<D><<<1, 32, 0, st>>>(dm, cm);
         TGP_LAUNCH_CHECK(h);
     }
@@ -299,9 +334,11 @@ int do_shard_reduce(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* ele
     double *excl, *wagg;
     TGP_TRY(dalloc(h, (size_t)Elem<D>::N * nthreads, &excl));
     TGP_TRY(dalloc(h, (size_t)Elem<D>::N * nwarps, &wagg));
+    TGP_K(h, "k_filter_reduce");
     if (tv) k_filter_reduce<D, true><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wagg, nwarps);
     else    k_filter_reduce<D, false><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wagg, nwarps);
     TGP_LAUNCH_CHECK(h);
+    TGP_K(h, "k_elem_total");
     k_elem_total<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, de);
     TGP_LAUNCH_CHECK(h);
     return end_call(h, nullptr, T, false);

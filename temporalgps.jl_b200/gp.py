@@ -240,9 +240,9 @@ class GP:
 
 
 def _mean_vector(mean, t):
-    tt = _times(t)
     if mean is None:
         return None
+    tt = _times(t)
     if callable(mean):
         return np.array([mean(v) for v in tt], dtype=np.float64)
     return np.full(len(tt), float(mean))
@@ -346,7 +346,7 @@ def posterior(fx: FiniteLTISDE, y) -> PosteriorLTISDE:
     """Lazy (posterior_lti_sde.jl:7-10)."""
     if len(fx.x) != len(y):
         raise L.DimensionMismatch(1, f"Dimension mismatch. length(x) is {len(fx.x)}, but length(y) is {len(y)}")
-    return PosteriorLTISDE(fx.f, np.asarray(y, dtype=np.float64), fx.x, fx.noise)
+    return PosteriorLTISDE(fx.f, y if isinstance(y, np.ma.MaskedArray) else np.asarray(y, dtype=np.float64), fx.x, fx.noise)
 
 
 def _same_inputs(a, b):
@@ -356,15 +356,22 @@ def _same_inputs(a, b):
     return ta.shape == tb.shape and bool(np.all(ta == tb))
 
 
+def _nan_missing(y):
+    if isinstance(y, np.ma.MaskedArray):
+        return y.astype(np.float64).filled(np.nan)
+    return np.asarray(y, dtype=np.float64)
+
+
 def merge_datasets(x1, x2, S1, S2, y1, y2):
-    """posterior_lti_sde.jl:97-123 — stable sort in time; NaN marks missing."""
+    """posterior_lti_sde.jl:97-123 — stable sort in time. NaN marks missing internally; the result
+    is handed to the LGSSM layer as a masked array."""
     x_raw = np.concatenate([_times(x1), _times(x2)])
     idx = np.argsort(x_raw, kind="stable")
     inv = np.argsort(idx, kind="stable")
     n1 = len(x1)
     S = np.concatenate([_dense(S1, n1), _dense(S2, len(x2))])[idx]
-    ys = np.concatenate([np.asarray(y1, dtype=np.float64), np.asarray(y2, dtype=np.float64)])[idx]
-    return x_raw[idx], S, ys, inv[:n1], inv[n1:]
+    ys = np.concatenate([_nan_missing(y1), _nan_missing(y2)])[idx]
+    return x_raw[idx], S, np.ma.masked_invalid(ys), inv[:n1], inv[n1:]
 
 
 def _posterior_marginals(fx: FinitePosteriorLTISDE):
@@ -396,4 +403,4 @@ def _posterior_logpdf(fx: FinitePosteriorLTISDE, y_pr):
     y_full[pr] = np.asarray(y_pr, dtype=np.float64)
     model = build_lgssm(post.prior, x, S)
     model_post = L.replace_observation_noise_cov(L.posterior(model, ys, h), R_pr)
-    return L.logpdf(model_post, y_full, h)
+    return L.logpdf(model_post, np.ma.masked_invalid(y_full), h)

@@ -4,7 +4,9 @@ gauss_markov_model.jl, missings.jl) over the C ABI of libtgpb200.so.
 
 Same names and argument meaning as the reference: `LGSSM`, `GaussMarkovModel`, `Forward`/`Reverse`,
 `Gaussian`, `logpdf(model, y)` (lgssm.jl:147), `_filter` (:171), `posterior` (:193), `marginals`
-(:99), plus the missing-data wrappers of missings.jl:8-23 (missing == NaN here). All arithmetic of
+(:99), plus the missing-data wrappers of missings.jl:8-23. Like the reference, the missing-data
+path is selected by the TYPE of y — `numpy.ma.MaskedArray` plays `Vector{Union{Missing,T}}` (masked
+== missing); a plain float array is never scanned for NaN. All arithmetic of
 the recursions happens in the CUDA library; this module only lays arrays out the way Julia would
 (column-major blocks, stride 0 for `Fill`) and maps status codes to exceptions.
 """
@@ -145,13 +147,17 @@ def _check_inputs(model: LGSSM, y):
 
 
 def _host_y(y):
+    """Observations as the library takes them: a C-contiguous float64 host array, or a device-resident
+    torch tensor passed through by address (the library detects device pointers)."""
+    if hasattr(y, "data_ptr"):
+        return y
     return np.ascontiguousarray(y, dtype=np.float64)
 
 
 # ---- missing data (missings.jl:25-74): stays on the host, kernels see plain R_t ------------------
 def transform_model_and_obs(model: LGSSM, y):
-    y = np.array(y, dtype=np.float64, copy=True)
-    miss = np.isnan(y)
+    miss = np.ma.getmaskarray(y)
+    y = np.array(np.ma.getdata(y), dtype=np.float64, copy=True)
     T = len(model)
     Rs = model.emissions.Rs
     Rs = np.full(T, float(Rs.value)) if isinstance(Rs, Fill) else np.array(Rs, dtype=np.float64, copy=True)
@@ -162,8 +168,7 @@ def transform_model_and_obs(model: LGSSM, y):
 
 
 def _maybe_missing(model, y):
-    y = np.asarray(y, dtype=np.float64)
-    if np.isnan(y).any():
+    if isinstance(y, np.ma.MaskedArray):          # dispatch on type, as missings.jl:8-23 does
         return transform_model_and_obs(model, y)
     return model, y, 0
 

@@ -76,7 +76,7 @@ def test_gp_logpdf_and_posterior_small(pkg, kname, regular):
     tp = pkg.RegularSpacing(0.0, 0.3, N) if regular else pkg.RegularSpacing(0.0, 0.3, N).collect()
     to = O.RegularSpacing(0.0, 0.3, N) if regular else O.RegularSpacing(0.0, 0.3, N).collect()
     y = O.sample_prior(O.build_lgssm(ko(), to, 0.1), rng)
-    fx = pkg.to_sde(pkg.GP(kp()))(tp, 0.1)
+    fx = pkg.to_sde(pkg.GP(kp(pkg)))(tp, 0.1)
     lml = pkg.gp.logpdf(fx, y)
     assert abs(lml - O.gp_logpdf(ko(), to, 0.1, y)) <= LML_RTOL * abs(lml)
     assert abs(lml - O.dense_logpdf(ko(), to, 0.1, y)) <= 1e-6 * abs(lml)
@@ -134,7 +134,7 @@ def test_missing_observations(pkg, handle):
     y = sample_y(rng, m)
     y[rng.uniform(size=300) < 0.3] = np.nan
     pm = to_pkg_model(pkg, m)
-    lml = pkg.lgssm.logpdf(pm, y, handle)
+    lml = pkg.lgssm.logpdf(pm, np.ma.masked_invalid(y), handle)
     ref = O.logpdf_missing(m, y)
     assert abs(lml - ref) <= LML_RTOL * abs(ref)
 
