@@ -278,9 +278,11 @@ def _noise_to_time_form(x, noise):
 def build_lgssm(f: LTISDE, x, noise) -> LGSSM:
     """build_lgssm — lti_sde.jl:71-80 (+ mean handling :112-131)."""
     As, as_, Qs, Hs, hs, x0 = lgssm_components(f.f.kernel, x)
-    mv = _mean_vector(f.f.mean, x)
-    if mv is not None:
-        hs = _dense(hs, len(x)) + mv
+    mean = f.f.mean
+    if mean is not None and not callable(mean) and isinstance(hs, Fill):
+        hs = Fill(hs.value + float(mean), len(x))          # ConstMean: mean_vector is a Fill, hs stays a Fill
+    elif mean is not None:
+        hs = _dense(hs, len(x)) + _mean_vector(mean, x)
     return LGSSM(GaussMarkovModel(Forward, As, as_, Qs, x0), ScalarEmissions(Hs, hs, _noise_to_time_form(x, noise)))
 
 

@@ -233,3 +233,52 @@ def test_shard_reduce_prefix(pkg, handle):
         sm2 = O.LGSSM("forward", sm.As, sm.as_, sm.Qs, m_in, P_in, sm.Hs, sm.hs, sm.Rs)
         total += pkg.lgssm.logpdf(to_pkg_model(pkg, sm2), y[s:e], handle)
     assert abs(total - ref) <= LML_RTOL * abs(ref)
+
+
+@pytest.mark.parametrize("T", [65536, 65537, 70001, 300_000])
+@pytest.mark.parametrize("kname", ["m12", "m32", "m52", "sum_m12_m32"])
+def test_steady_state_path_edges(pkg, handle, kname, T):
+    """Time-invariant models long enough for the steady-state kernels: ragged tails, every output kind,
+    strided (Julia Vector{Gaussian}-style) filter records; checked against the C oracle."""
+    kp, ko = KERNELS[kname]
+    to = O.RegularSpacing(0.0, 0.05, T)
+    mo = O.build_lgssm(ko(), to, 0.2, 0.7)
+    rng = np.random.default_rng(T)
+    y = np.sin(np.arange(T) * 0.003) + 0.7 + 0.4 * rng.standard_normal(T)
+    cm = c_oracle.Model.from_lgssm(mo)
+    ref = c_oracle.filter(cm, y)
+    fx = pkg.to_sde(pkg.GP(kp(pkg), 0.7))(pkg.RegularSpacing(0.0, 0.05, T), 0.2)
+    model = fx.build_lgssm()
+    c0 = handle.counters()["launches"]
+    lml, steps = pkg.lgssm.logpdf(model, y, handle, per_step=True)
+    assert handle.counters()["launches"] - c0 == 2, "expected the two-launch steady-state path"
+    assert abs(lml - ref["lml"]) <= LML_RTOL * abs(ref["lml"])
+    np.testing.assert_allclose(steps, ref["lml_steps"], rtol=1e-6, atol=1e-8)
+    ms, Ps = pkg.lgssm._filter(model, y, handle)
+    np.testing.assert_allclose(ms, ref["m"], rtol=MV_RTOL, atol=1e-8)
+    np.testing.assert_allclose(Ps, ref["P"], rtol=MV_RTOL, atol=1e-12)
+    # strided records: m at +0, P at +D of each (D + D*D)-double record
+    D = mo.D
+    rec = np.zeros((T, D + D * D))
+    mm = pkg.lgssm._Marshalled(model)
+    out = np.zeros(1)
+    base = rec.ctypes.data
+    handle.filter(mm.desc, np.ascontiguousarray(y), base, D + D * D, base + 8 * D, D + D * D, out)
+    np.testing.assert_allclose(rec[:, :D], ref["m"], rtol=MV_RTOL, atol=1e-8)
+    np.testing.assert_allclose(rec[:, D:].reshape(T, D, D), np.swapaxes(ref["P"], 1, 2), rtol=MV_RTOL, atol=1e-12)
+    assert abs(out[0] - ref["lml"]) <= LML_RTOL * abs(ref["lml"])
+
+
+def test_steady_state_fallback_when_not_converged(pkg, handle):
+    """A model whose covariance has not converged within the transient budget (dt tiny against the length
+    scale) must silently rerun through the general scan and still match."""
+    T = 100_000
+    mo = O.build_lgssm(O.Matern52(), O.RegularSpacing(0.0, 1e-6, T), 0.5)
+    rng = np.random.default_rng(5)
+    y = 0.3 * rng.standard_normal(T)
+    ref = c_oracle.filter(c_oracle.Model.from_lgssm(mo), y, want_mp=False)
+    fx = pkg.to_sde(pkg.GP(pkg.Matern52Kernel()))(pkg.RegularSpacing(0.0, 1e-6, T), 0.5)
+    c0 = handle.counters()["launches"]
+    lml = pkg.lgssm.logpdf(fx.build_lgssm(), y, handle)
+    assert handle.counters()["launches"] - c0 > 2   # steady attempt + general rerun
+    assert abs(lml - ref["lml"]) <= LML_RTOL * abs(ref["lml"])
