@@ -15,15 +15,17 @@
 //                the covariance has converged (usually the first block), emits the requested outputs
 //                of those steps, then derives every constant of the steady phase (gain, powers of
 //                Abar for the scans) on the device.
-//   k_ss_main    persistent cooperative kernel over the remaining steps, CTA b owning a contiguous
-//                range of R steps:
-//       phase 1  tile by tile (cp.async double-buffered into padded shared memory): per-thread
-//                chunk fold of the zero-state response, warp scan by shuffles, tile-exclusive
-//                prefix per thread -> 24 B / chunk scratch (stays in L2); range aggregate;
-//       barrier  one grid-wide counter barrier; every CTA folds the aggregates before it;
-//       phase 2  tile by tile: start state per thread = power * tile-in state + its prefix, then
-//                the sequential (predict, update) per step: v_t² (and optionally lml_t, m_t, P∞).
-// HBM traffic: y once (second pass is served by L2) + the requested outputs.
+//   k_ss_main    persistent cooperative kernel, one 512-thread CTA per SM. Every WARP owns a contiguous
+//                range of Rw steps and streams it in warp tiles of 32*L steps through its own ring of
+//                cp.async stages in padded shared memory; warps never wait for each other except at the
+//                one grid barrier (no __syncthreads in the streaming loops):
+//       phase 1  per warp tile: per-lane chunk fold of the zero-state response, warp scan by shuffles,
+//                tile-exclusive prefix per lane -> 24 B / chunk scratch (stays in L2); warp aggregate;
+//       barrier  one grid-wide counter barrier; every CTA folds the warp aggregates before it;
+//       phase 2  per warp tile: lane start state = Abar^(L lane) * tile-in state + its prefix, then the
+//                sequential (predict, update) per step: v_t² (and optionally lml_t, m_t, P∞).
+// HBM traffic: y once (phase-1 loads carry an L2 evict_last policy so the second pass hits L2) + the
+// requested outputs.
 #pragma once
 #include <cuda_pipeline.h>
 #include <cuda_runtime.h>
@@ -35,7 +37,7 @@
 
 namespace tgp {
 
-constexpr int kSSThreads = 256;
+constexpr int kSSThreads = 512;
 constexpr int kSSWarps = kSSThreads / 32;
 constexpr int kTrThreads = 128;              // transient CTA
 constexpr int kTrWarps = kTrThreads / 32;
@@ -47,17 +49,16 @@ template <int D>
 struct SSConst {
     int converged;
     int n_blocks;
-    long long N0, Ts, R;  // transient length used, steady steps, steps per CTA range
+    long long N0, Ts, Rw;  // transient length used, steady steps, steps per WARP range
     double S, invS, logS, hh, conv_err;
     Vec<D> K, w, a, c, x_in;  // x_in: filtered mean after the transient
     Mat<D> A, Abar;
     double PfFull[D * D];     // P∞, full column-major
     Mat<D> P2[5];             // Abar^(L 2^k)
-    Mat<D> Pw[kSSWarps];      // Abar^(32 L w)
-    Mat<D> PhiTile;           // Abar^(NT L)
-    Mat<D> PR[5];             // PhiR^(2^k), PhiR = Abar^R
-    Mat<D> PRw;               // PhiR^32
-    Mat<D> PRt;               // PhiR^NT
+    Mat<D> Pt;                // Abar^(32 L): one warp tile
+    Mat<D> PR[5];             // Phi^(2^k), Phi = Abar^Rw
+    Mat<D> PRw;               // Phi^32
+    Mat<D> PRt;               // Phi^NT
     Mat<D> Plane[32];         // Abar^(L lane)
 };
 
@@ -247,24 +248,24 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
     __syncwarp();
     const long long N0 = (long long)nb * kTrBlock;
     const long long Ts = dm.T - N0;
-    const long long tile = (long long)kSSThreads * ssL;
-    long long Rr = (Ts + G - 1) / G;
-    Rr = (Rr + tile - 1) / tile * tile;
-    if (Rr < tile) Rr = tile;
+    const long long wt = 32ll * ssL;               // warp tile
+    const long long nwarps = (long long)G * kSSWarps;
+    long long Rw = (Ts + nwarps - 1) / nwarps;
+    Rw = (Rw + wt - 1) / wt * wt;
+    if (Rw < wt) Rw = wt;
     cst->Plane[lane] = pow_from_squares<D>(sq, (unsigned long long)ssL * lane);
     if (lane < 5) cst->P2[lane] = pow_from_squares<D>(sq, (unsigned long long)ssL << lane);
-    else if (lane < 5 + kSSWarps) cst->Pw[lane - 5] = pow_from_squares<D>(sq, 32ull * ssL * (lane - 5));
-    else if (lane == 13) cst->PhiTile = pow_from_squares<D>(sq, (unsigned long long)tile);
+    else if (lane == 5) cst->Pt = pow_from_squares<D>(sq, (unsigned long long)wt);
     else if (lane == 14) {
-        Mat<D> p = pow_from_squares<D>(sq, (unsigned long long)Rr);
+        Mat<D> p = pow_from_squares<D>(sq, (unsigned long long)Rw);
         for (int k = 0; k < 5; ++k) { cst->PR[k] = p; p = matmul(p, p); }
-        cst->PRw = p;                               // PhiR^32
-        for (int k = 0; k < 3; ++k) p = matmul(p, p);
-        cst->PRt = p;                               // PhiR^256
+        cst->PRw = p;                               // Phi^32
+        for (int k = 0; k < 4; ++k) p = matmul(p, p);
+        cst->PRt = p;                               // Phi^512
     } else if (lane == 15) {
         cst->converged = s_conv;
         cst->n_blocks = nb;
-        cst->N0 = N0; cst->Ts = Ts; cst->R = Rr;
+        cst->N0 = N0; cst->Ts = Ts; cst->Rw = Rw;
         cst->S = S; cst->invS = invS; cst->logS = log(S); cst->hh = hh; cst->conv_err = conv_err;
         cst->K = K; cst->w = w; cst->a = a; cst->x_in = mT;
 #pragma unroll
@@ -277,7 +278,7 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
         counters[0] = 0u;
         counters[1] = 0u;
     }
-    static_assert(kSSThreads == 256, "PRt assumes 256 threads");
+    static_assert(kSSThreads == 512, "PRt assumes 512 threads");
 }
 
 // =============================================================================================
@@ -316,33 +317,55 @@ __device__ __forceinline__ Vec<D> cta_decayed_sum(Vec<D> z, const Mat<D>* Bk, co
     return r;
 }
 
-template <int D, int L>
+// ---- cp.async helpers (LDGSTS) with L2 cache-policy hints ---------------------------------------
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* g, unsigned long long pol) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async8_zfill(double* smem_dst, const double* g, bool ok) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int D, int L, int NS>
 struct SSLayout {
     static constexpr int CW = (sizeof(SSConst<D>) + 7) / 8;
-    static constexpr int YS = L + 1;                 // padded chunk stride (odd: conflict-free LDS.64)
-    static constexpr int YB = kSSThreads * YS;       // one tile buffer
-    static constexpr int MS = L * D + 1;             // padded chunk stride of the m_f staging tile
-    static constexpr int o_red = CW;
-    static constexpr int o_win = o_red + (kSSWarps + 1) * D;
-    static constexpr int o_mt = o_win + kSSWarps * D;
-    static constexpr int o_y = o_mt + D + ((o_mt + D) & 1);
-    static constexpr int o_ms = o_y + 2 * YB;
-    static size_t bytes(bool stage_m) { return (size_t)(o_ms + (stage_m ? kSSThreads * MS : 0)) * sizeof(double); }
+    static constexpr int YS = L + 2;           // padded chunk stride: rows stay 16-byte aligned for cp.async.16;
+                                               // LDS.64 at this stride is 2-way conflicted (1 LDS per ~17 DFMA)
+    static constexpr int WT = 32 * L;          // steps per warp tile
+    static constexpr int YB = 32 * YS;         // one stage of one warp
+    static constexpr int MS = L * D + 1;       // padded chunk stride of the per-warp m_f staging tile
+    static constexpr int o_red = CW + (CW & 1);
+    static constexpr int o_y = o_red + 2 * (kSSWarps + 2) * D + ((2 * (kSSWarps + 2) * D) & 1);
+    static constexpr int o_ms = o_y + kSSWarps * NS * YB;
+    static size_t bytes(bool stage_m) { return (size_t)(o_ms + (stage_m ? kSSWarps * 32 * MS : 0)) * sizeof(double); }
 };
 
-template <int D, int L>
-__global__ void __launch_bounds__(kSSThreads, 2)
+template <int D, int L, int NS>
+__global__ void __launch_bounds__(kSSThreads, 1)
 k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, double* __restrict__ zbuf, long long zstride,
           double* __restrict__ agg, unsigned* __restrict__ counters, const SSOut out) {
-    using LY = SSLayout<D, L>;
+    using LY = SSLayout<D, L, NS>;
+    static_assert(L % 2 == 0 && (128 % L) == 0 && NS >= 2, "layout assumptions");
     extern __shared__ __align__(16) double smem[];
     SSConst<D>& c = *reinterpret_cast<SSConst<D>*>(smem);
     double* red = smem + LY::o_red;
-    double* win = smem + LY::o_win;
-    double* mt = smem + LY::o_mt;
-    double* ybuf = smem + LY::o_y;
-    double* mstage = smem + LY::o_ms;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    double* ybuf = smem + LY::o_y + wp * (NS * LY::YB);          // this warp's ring
+    double* mstage = smem + LY::o_ms + wp * (32 * LY::MS);       // this warp's m_f staging tile
     const int G = gridDim.x, b = blockIdx.x;
     {
         const double* src = reinterpret_cast<const double*>(cg);
@@ -351,87 +374,97 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
     __syncthreads();
     if (!c.converged) return;  // uniform: the host reruns the series with the general scan
 
-    constexpr long long tile = (long long)kSSThreads * L;
-    const long long N0 = c.N0, Ts = c.Ts, Rr = c.R;
+    constexpr long long WT = LY::WT;
+    const long long N0 = c.N0, Ts = c.Ts, Rw = c.Rw;
     const double* __restrict__ y = y_all + N0;
-    const long long r0 = min((long long)b * Rr, Ts);
-    const long long r1 = min(r0 + Rr, Ts);
+    const long long gw = (long long)b * kSSWarps + wp;           // global warp index = range index
+    const long long r0 = min(gw * Rw, Ts);
+    const long long r1 = min(r0 + Rw, Ts);
     const Vec<D> K = c.K;
+    const bool y16 = ((reinterpret_cast<unsigned long long>(y) & 15ull) == 0);   // r0, ts are multiples of WT
 
-    auto issue_tile = [&](long long ts, int buf) {
-        double* dst = ybuf + buf * LY::YB;
+    // Warp tile ts -> stage `st` of this warp's ring. Lane copies pairs p = lane + 32 k (elements 2p, 2p+1, same
+    // chunk since L is even): destination 2p + (2p / L) * 2 = p0 + k * (64 + 128 / L): immediates after unrolling.
+    const int p0 = 2 * lane + ((2 * lane) / L) * 2;
+    auto issue_tile = [&](long long ts, int st, unsigned long long pol) {
+        double* dst = ybuf + st * LY::YB + p0;
+        if (y16 && ts + WT <= r1) {
+            const double* src = y + ts + 2 * lane;
 #pragma unroll
-        for (int k = 0; k < L; ++k) {
-            const int e = tid + k * kSSThreads;
-            const long long t = ts + e;
-            const bool ok = t < r1;
-            __pipeline_memcpy_async(dst + e + e / L, y + (ok ? t : r1 - 1), 8, ok ? 0 : 8);
+            for (int k = 0; k < L / 2; ++k) cp_async16(dst + k * (64 + 128 / L), src + k * 64, pol);
+        } else {
+#pragma unroll
+            for (int k = 0; k < L / 2; ++k)
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const long long t = ts + 2 * lane + k * 64 + hlf;
+                    const bool ok = t < r1;
+                    cp_async8_zfill(dst + k * (64 + 128 / L) + hlf, y + (ok ? t : r1 - 1), ok);
+                }
         }
     };
+    const long long ntiles = (r1 - r0 + WT - 1) / WT;
 
-    // ---- phase 1: zero-state responses ------------------------------------------------------------
+    // ---- phase 1: zero-state responses, warp by warp ----------------------------------------------------
     {
-        Vec<D> Zr = vzero<D>();
-        if (r0 < r1) issue_tile(r0, 0);
-        __pipeline_commit();
-        int it = 0;
-        for (long long ts = r0; ts < r1; ts += tile, ++it) {
-            if (ts + tile < r1) issue_tile(ts + tile, (it + 1) & 1);
-            __pipeline_commit();
-            __pipeline_wait_prior(1);
-            __syncthreads();
-            const double* yc = ybuf + (it & 1) * LY::YB + tid * LY::YS;
+        const unsigned long long pol = l2_policy_evict_last();
+        Vec<D> Zw = vzero<D>();
+#pragma unroll
+        for (int s = 0; s < NS - 1; ++s) {
+            if (s < ntiles) issue_tile(r0 + s * WT, s, pol);
+            cp_async_commit();
+        }
+        const Mat<D> Ab = c.Abar;
+        const Vec<D> cc = c.c;
+        for (long long it = 0; it < ntiles; ++it) {
+            const long long ts = r0 + it * WT;
+            cp_async_wait<NS - 2>();
+            __syncwarp();                                   // tile `it` visible to the warp; tile it-1 fully consumed
+            if (it + NS - 1 < ntiles) issue_tile(ts + (NS - 1) * WT, (int)((it + NS - 1) % NS), pol);
+            cp_async_commit();
+            const double* yc = ybuf + (int)(it % NS) * LY::YB + lane * LY::YS;
             Vec<D> z = vzero<D>();
-            {
-                const Mat<D> Ab = c.Abar;
-                const Vec<D> cc = c.c;
 #pragma unroll
-                for (int j = 0; j < L; ++j) {
-                    const double yv = yc[j];
-                    Vec<D> u;
+            for (int j = 0; j < L; ++j) {
+                const double yv = yc[j];
+                Vec<D> u;
 #pragma unroll
-                    for (int i = 0; i < D; ++i) u[i] = fma(K[i], yv, cc[i]);
-                    z = affine(Ab, z, u);
-                }
+                for (int i = 0; i < D; ++i) u[i] = fma(K[i], yv, cc[i]);
+                z = affine(Ab, z, u);
             }
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const Vec<D> zu = shfl_up_vec(z, 1 << k);
                 if (lane >= (1 << k)) z = affine(c.P2[k], zu, z);
             }
-            if (lane == 31) {
+            Vec<D> tot, ze = shfl_up_vec(z, 1);
 #pragma unroll
-                for (int i = 0; i < D; ++i) red[wp * D + i] = z[i];
-            }
-            __syncthreads();
-            if (tid == 0) {
-                Vec<D> acc = vzero<D>();
-                for (int ww = 0; ww < kSSWarps; ++ww) {
-                    Vec<D> t;
-#pragma unroll
-                    for (int i = 0; i < D; ++i) { win[ww * D + i] = acc[i]; t[i] = red[ww * D + i]; }
-                    acc = affine(c.Pw[1], acc, t);
-                }
-                Zr = affine(c.PhiTile, Zr, acc);
-            }
-            __syncthreads();
-            Vec<D> ze = shfl_up_vec(z, 1);
+            for (int i = 0; i < D; ++i) tot[i] = __shfl_sync(0xffffffffu, z[i], 31);
             if (lane == 0) ze = vzero<D>();
-            Vec<D> mw;
+            Zw = affine(c.Pt, Zw, tot);
+            const long long cidx = ts / L + lane;
 #pragma unroll
-            for (int i = 0; i < D; ++i) mw[i] = win[wp * D + i];
-            const Vec<D> zx = affine(c.Plane[lane], mw, ze);
-            const long long cidx = ts / L + tid;
-#pragma unroll
-            for (int i = 0; i < D; ++i) __stcg(zbuf + i * zstride + cidx, zx[i]);
+            for (int i = 0; i < D; ++i) __stcg(zbuf + i * zstride + cidx, ze[i]);
         }
-        // a range shorter than Rr (the last one) is never consumed, so no alignment fix-up is needed
-        if (r0 < r1) issue_tile(r0, 0);  // prefetch the first tile of phase 2 across the barrier
-        __pipeline_commit();
-        if (tid == 0) {
+        cp_async_wait<0>();
+        __syncwarp();
+        // a range shorter than Rw (the last ones) is never consumed, so no alignment fix-up is needed.
+        // Prefetch the first tiles of phase 2 across the barrier.
+        {
+            const unsigned long long pol2 = l2_policy_evict_first();
 #pragma unroll
-            for (int i = 0; i < D; ++i) __stcg(agg + (size_t)b * D + i, Zr[i]);
-            __threadfence();
+            for (int s = 0; s < NS - 1; ++s) {
+                if (s < ntiles) issue_tile(r0 + s * WT, s, pol2);
+                cp_async_commit();
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) __stcg(agg + (size_t)gw * D + i, Zw[i]);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
             atomicAdd(counters, 1u);
             while (*reinterpret_cast<volatile unsigned*>(counters) < (unsigned)G) { __nanosleep(32); }
             __threadfence();
@@ -439,9 +472,11 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
         __syncthreads();
     }
 
-    // ---- mean entering this CTA's range: PhiR^b x_in + sum_{e<b} PhiR^(b-1-e) Z_e ------------------
+    // ---- mean entering this warp's range: Phi^gw x_in + sum_{e<gw} Phi^(gw-1-e) Z_e -----------------------
+    Vec<D> m_tile;
     {
-        const long long n = (long long)b + 1;   // virtual elements V[0] = x_in, V[e] = Z_{e-1}
+        // CTA level: state entering the CTA's first warp range (virtual elements V[0] = x_in, V[e] = Z_{e-1})
+        const long long n = (long long)b * kSSWarps + 1;
         const long long J = (n + kSSThreads - 1) / kSSThreads;
         const long long pad = J * kSSThreads - n;
         const Mat<D> Bt = c.PRt;
@@ -456,43 +491,41 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             }
             z = affine(Bt, z, u);
         }
-        const Vec<D> m_in = cta_decayed_sum<D>(z, c.PR, c.PRw, red);
-        if (tid == 0) {
+        Vec<D> m = cta_decayed_sum<D>(z, c.PR, c.PRw, red);
+        // warp level: chain through the ranges of the warps before this one in the CTA
+        for (int w2 = 0; w2 < wp; ++w2) {
+            Vec<D> u;
 #pragma unroll
-            for (int i = 0; i < D; ++i) mt[i] = m_in[i];
+            for (int i = 0; i < D; ++i) u[i] = __ldcg(agg + ((size_t)b * kSSWarps + w2) * D + i);
+            m = affine(c.PR[0], m, u);
         }
-        __syncthreads();
+        m_tile = m;
     }
 
     // ---- phase 2 ------------------------------------------------------------------------------------
     double q = 0.0;
     {
+        const unsigned long long pol = l2_policy_evict_first();
         const Mat<D> A = c.A;
         const Vec<D> av = c.a, wv = c.w;
         const double hh = c.hh, invS = c.invS;
         const double lc = -0.5 * (kLog2Pi + c.logS);
         const bool m_contig = out.m_f && out.s_m == D;
-        int it = 0;
-        for (long long ts = r0; ts < r1; ts += tile, ++it) {
-            if (ts + tile < r1) issue_tile(ts + tile, (it + 1) & 1);
-            __pipeline_commit();
-            const long long cidx = ts / L + tid;
+        const bool staged_out = out.lml_steps || m_contig || out.P_f;
+        for (long long it = 0; it < ntiles; ++it) {
+            const long long ts = r0 + it * WT;
+            const long long cidx = ts / L + lane;
             Vec<D> zx;
 #pragma unroll
             for (int i = 0; i < D; ++i) zx[i] = __ldcg(zbuf + i * zstride + cidx);
-            __pipeline_wait_prior(1);
-            __syncthreads();
-            Vec<D> m;
-            {
-                Vec<D> mti;
-#pragma unroll
-                for (int i = 0; i < D; ++i) mti[i] = mt[i];
-                const Vec<D> mw = matvec(c.Pw[wp], mti);
-                m = affine(c.Plane[lane], mw, zx);
-            }
-            double* yc = ybuf + (it & 1) * LY::YB + tid * LY::YS;
-            double* mc = mstage + tid * LY::MS;
-            const long long t0 = ts + (long long)tid * L;
+            cp_async_wait<NS - 2>();
+            __syncwarp();
+            if (it + NS - 1 < ntiles) issue_tile(ts + (NS - 1) * WT, (int)((it + NS - 1) % NS), pol);
+            cp_async_commit();
+            Vec<D> m = affine(c.Plane[lane], m_tile, zx);
+            double* yc = ybuf + (int)(it % NS) * LY::YB + lane * LY::YS;
+            double* mc = mstage + lane * LY::MS;
+            const long long t0 = ts + (long long)lane * L;
             const int nv = (int)max(0ll, min((long long)L, r1 - t0));  // valid steps of this chunk
             if (nv == L) {
 #pragma unroll
@@ -538,40 +571,41 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
 #pragma unroll
                     for (int ii = 0; ii <= jj; ++ii) out.xT[D + Sym<D>::idx(ii, jj)] = c.PfFull[ii + D * jj];
             }
-            __syncthreads();  // every thread has read mt
-            if (tid == kSSThreads - 1) {
 #pragma unroll
-                for (int i = 0; i < D; ++i) mt[i] = m[i];  // state entering the next tile
-            }
-            const long long nt = min(tile, r1 - ts);
-            if (out.lml_steps) {
-                const double* yb = ybuf + (it & 1) * LY::YB;
-                for (int e = tid; e < nt; e += kSSThreads) out.lml_steps[N0 + ts + e] = yb[e + e / L];
-            }
-            if (m_contig) {
-                const int ne = (int)nt * D;
-                double* dst = out.m_f + (N0 + ts) * D;
-                for (int g = tid; g < ne; g += kSSThreads) dst[g] = mstage[g + g / (L * D)];
-            }
-            if (out.P_f) {
-                if (out.s_P == D * D) {
-                    const int ne = (int)nt * D * D;
-                    double* dst = out.P_f + (N0 + ts) * D * D;
-                    for (int g = tid; g < ne; g += kSSThreads) dst[g] = c.PfFull[g % (D * D)];
-                } else {
-                    for (int e = tid; e < nt; e += kSSThreads)
-#pragma unroll
-                        for (int k = 0; k < D * D; ++k) out.P_f[(N0 + ts + e) * out.s_P + k] = c.PfFull[k];
+            for (int i = 0; i < D; ++i) m_tile[i] = __shfl_sync(0xffffffffu, m[i], 31);  // state entering the next tile
+            if (staged_out) {
+                __syncwarp();
+                const int nt = (int)min(WT, r1 - ts);
+                if (out.lml_steps) {
+                    const double* yb = ybuf + (int)(it % NS) * LY::YB;
+                    for (int e = lane; e < nt; e += 32) out.lml_steps[N0 + ts + e] = yb[e + (e / L) * 2];
                 }
+                if (m_contig) {
+                    const int ne = nt * D;
+                    double* dst = out.m_f + (N0 + ts) * D;
+                    for (int g = lane; g < ne; g += 32) dst[g] = mstage[g + g / (L * D)];
+                }
+                if (out.P_f) {
+                    if (out.s_P == D * D) {
+                        const int ne = nt * D * D;
+                        double* dst = out.P_f + (N0 + ts) * D * D;
+                        for (int g = lane; g < ne; g += 32) dst[g] = c.PfFull[g % (D * D)];
+                    } else {
+                        for (int e = lane; e < nt; e += 32)
+#pragma unroll
+                            for (int k = 0; k < D * D; ++k) out.P_f[(N0 + ts + e) * out.s_P + k] = c.PfFull[k];
+                    }
+                }
+                __syncwarp();
             }
-            __syncthreads();
         }
-        __pipeline_wait_prior(0);
+        cp_async_wait<0>();
     }
 
     // ---- log-likelihood: fixed-order reduction, last CTA finishes ----------------------------------
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) q += __shfl_down_sync(0xffffffffu, q, off);
+    __syncthreads();
     if (lane == 0) red[wp] = q;
     __syncthreads();
     if (tid == 0) {
@@ -592,34 +626,23 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
 // Forward declaration: a non-converged series is redone by the general scan driver (tgp_drivers.cuh).
 template <int D> int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& rq);
 
-template <int D, int L>
+template <int D, int L, int NS>
 int launch_ss_main(tgp_ctx* h, bool stage_m, const SSConst<D>* cst, const double* dy, int64_t T, int G, double* agg,
                    unsigned* counters, const SSOut& so) {
-    using LY = SSLayout<D, L>;
-    const size_t smem = LY::bytes(stage_m);
-    double* zbuf;
-    const long long zstride = (T + (long long)G * kSSThreads * L) / L + kSSThreads;
-    TGP_TRY(dalloc(h, (size_t)zstride * D, &zbuf));
-    void* args[] = {(void*)&cst, (void*)&dy, (void*)&zbuf, (void*)&zstride, (void*)&agg, (void*)&counters, (void*)&so};
-    TGP_K(h, "k_ss_main");
-    TGP_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_ss_main<D, L>, dim3((unsigned)G), dim3(kSSThreads), args, smem, h->stream));
-    TGP_LAUNCH_CHECK(h);
-    return TGP_OK;
-}
-
-template <int D, int L>
-int ss_grid(tgp_ctx* h, bool stage_m, int* G) {
-    using LY = SSLayout<D, L>;
+    using LY = SSLayout<D, L, NS>;
     const size_t smem = LY::bytes(stage_m);
     static bool attr_set = false;
     if (!attr_set) {
-        TGP_CUDA(h, cudaFuncSetAttribute(k_ss_main<D, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        TGP_CUDA(h, cudaFuncSetAttribute(k_ss_main<D, L, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    int occ = 0;
-    TGP_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ss_main<D, L>, kSSThreads, smem));
-    if (occ < 1) return fail(h, TGP_ECUDA, "steady-state kernel does not fit on an SM (%zu B of shared memory)", smem);
-    *G = std::min(occ, 2) * h->sm_count;  // a whole number of CTAs per SM: the FP64 pipe is the bound, keep SMs balanced
+    double* zbuf;
+    const long long zstride = (T + (long long)G * kSSWarps * LY::WT) / L + 64;
+    TGP_TRY(dalloc(h, (size_t)zstride * D, &zbuf));
+    void* args[] = {(void*)&cst, (void*)&dy, (void*)&zbuf, (void*)&zstride, (void*)&agg, (void*)&counters, (void*)&so};
+    TGP_K(h, "k_ss_main");
+    TGP_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_ss_main<D, L, NS>, dim3((unsigned)G), dim3(kSSThreads), args, smem, h->stream));
+    TGP_LAUNCH_CHECK(h);
     return TGP_OK;
 }
 
@@ -636,10 +659,8 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
     max_blocks = std::max<int64_t>(1, std::min<int64_t>(max_blocks, T / (2 * kTrBlock)));
     cudaStream_t st = h->stream;
     const bool stage_m = rq.m_f && rq.s_m == D;
-    const bool small_L = rq.m_f != nullptr;   // m_f staging tile must fit next to the y tiles
-    int G = 0;
-    if (small_L) TGP_TRY((ss_grid<D, 8>(h, stage_m, &G)));
-    else TGP_TRY((ss_grid<D, 16>(h, stage_m, &G)));
+    const bool small_L = rq.m_f != nullptr || h->chunk == 8;   // m_f staging tile must fit next to the y ring
+    const int G = h->sm_count;                                  // one 512-thread CTA per SM
     const int L = small_L ? 8 : 16;
 
     SSConst<D>* cst;
@@ -648,7 +669,7 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
     TGP_TRY(dalloc(h, 1, &rq.err));
     TGP_CUDA(h, cudaMemsetAsync(rq.err, 0xFF, sizeof(unsigned long long), st));
     TGP_TRY(dalloc(h, 1, &cst));
-    TGP_TRY(dalloc(h, (size_t)(G + 1) * D, &agg));
+    TGP_TRY(dalloc(h, (size_t)(G * kSSWarps + 1) * D, &agg));
     TGP_TRY(dalloc(h, (size_t)G, &partials));
     TGP_TRY(dalloc(h, D + Sym<D>::N, &xT));
     TGP_TRY(dalloc(h, 2, &counters));
@@ -672,8 +693,14 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
     so.partials = partials;
     so.lml_prefix = lml_prefix;
     so.lml_out = rq.lml_dev;
-    if (small_L) TGP_TRY((launch_ss_main<D, 8>(h, stage_m, cst, dy, T, G, agg, counters, so)));
-    else TGP_TRY((launch_ss_main<D, 16>(h, stage_m, cst, dy, T, G, agg, counters, so)));
+    constexpr size_t kSmemMax = 227 * 1024;
+    if (small_L) {
+        if (SSLayout<D, 8, 3>::bytes(stage_m) <= kSmemMax) TGP_TRY((launch_ss_main<D, 8, 3>(h, stage_m, cst, dy, T, G, agg, counters, so)));
+        else TGP_TRY((launch_ss_main<D, 8, 2>(h, stage_m, cst, dy, T, G, agg, counters, so)));
+    } else {
+        if (SSLayout<D, 16, 3>::bytes(stage_m) <= kSmemMax) TGP_TRY((launch_ss_main<D, 16, 3>(h, stage_m, cst, dy, T, G, agg, counters, so)));
+        else TGP_TRY((launch_ss_main<D, 16, 2>(h, stage_m, cst, dy, T, G, agg, counters, so)));
+    }
     rq.xT = xT;
     rq.x0buf = nullptr;
     *flag = &cst->converged;
