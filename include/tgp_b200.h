@@ -148,6 +148,7 @@ int tgp_posterior_marginals(tgp_handle h, const tgp_lgssm* model, const double* 
  */
 int tgp_elem_size(int D);                                  /* 3*D*D + 2*D */
 int tgp_shard_reduce(tgp_handle h, const tgp_lgssm* shard, const double* y, double* elem_out);
+/* tgp_shard_prefix is host-side arithmetic only; h may be NULL. */
 int tgp_shard_prefix(tgp_handle h, int D, int n_elems, const double* elems /*host*/,
                      const double* m0, const double* P0, double* m_in, double* P_in /*host*/);
 

@@ -196,13 +196,21 @@ class Handle:
         self.check(lib().tgp_shard_reduce(self._h, C.byref(desc), ptr(y), ptr(elem_out)))
 
     def shard_prefix(self, D, elems, m0, P0):
-        n = 0 if elems is None else int(np.asarray(elems).shape[0])
-        m_in = np.empty(D)
-        P_in = np.empty((D, D))
-        e = None if n == 0 else np.ascontiguousarray(elems, dtype=np.float64)
-        self.check(lib().tgp_shard_prefix(self._h, int(D), n, ptr(e), ptr(np.ascontiguousarray(m0, dtype=np.float64)),
-                                          ptr(np.ascontiguousarray(P0, dtype=np.float64)), ptr(m_in), ptr(P_in)))
-        return m_in, P_in
+        return shard_prefix(D, elems, m0, P0, self)
+
+
+def shard_prefix(D, elems, m0, P0, handle=None):
+    """tgp_shard_prefix: fold scan elements 0..n-1 into (m0, P0). Host arithmetic; works without a device."""
+    n = 0 if elems is None else int(np.asarray(elems).shape[0])
+    m_in = np.empty(D)
+    P_in = np.empty((D, D))
+    e = None if n == 0 else np.ascontiguousarray(elems, dtype=np.float64)
+    rc = lib().tgp_shard_prefix(handle._h if handle is not None else None, int(D), n, ptr(e),
+                                ptr(np.ascontiguousarray(m0, dtype=np.float64)), ptr(np.ascontiguousarray(P0, dtype=np.float64)),
+                                ptr(m_in), ptr(P_in))
+    if rc != TGP_OK:
+        raise TGPError(rc, "tgp_shard_prefix failed")
+    return m_in, P_in
 
 
 _default = {}

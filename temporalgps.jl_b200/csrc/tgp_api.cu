@@ -248,7 +248,7 @@ int tgp_shard_reduce(tgp_handle h, const tgp_lgssm* shard, const double* y, doub
 
 int tgp_shard_prefix(tgp_handle h, int D, int n_elems, const double* elems, const double* m0, const double* P0, double* m_in,
                      double* P_in) {
-    if (!h) return TGP_EINVAL;
+    // pure host arithmetic (no device work): h may be NULL
     if (n_elems < 0 || (n_elems > 0 && !elems) || !m0 || !P0 || !m_in || !P_in) return fail(h, TGP_EINVAL, "bad argument to tgp_shard_prefix");
 #define CALL(Dv) do_shard_prefix<Dv>(n_elems, elems, m0, P0, m_in, P_in)
     TGP_DISPATCH_D(h, D)

@@ -229,6 +229,7 @@ struct FilterReq {
     double* x0buf = nullptr;      // packed x0
     double* lml_dev = nullptr;
     unsigned long long* err = nullptr;
+    bool packed_result = false;   // err points at a result block {u64 err_step, double lml, int converged}
 };
 
 

@@ -30,26 +30,40 @@ inline bool time_invariant(const tgp_lgssm& m) { return !(m.sA | m.sa | m.sQ | m
 // End of a call: copy back host outputs, fetch the failing-step word (and the steady-state
 // convergence word, if any), wait. *ss_converged is left untouched when ss_flag is NULL.
 inline int end_call(tgp_ctx* h, const unsigned long long* err_step, int64_t T, bool reverse_t, const int* ss_flag = nullptr,
-                    bool* ss_converged = nullptr) {
+                    bool* ss_converged = nullptr, const FilterReq* packed = nullptr) {
     unsigned long long* perr = (unsigned long long*)h->pinned;
+    double* plml = h->pinned + 1;
     int* pflag = (int*)(h->pinned + 2);
     *perr = ~0ull;
     *pflag = 1;
-    if (ss_flag) {
-        TGP_CUDA(h, cudaMemcpyAsync(pflag, ss_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        h->d2h += 4;
-    }
-    if (err_step) {
-        TGP_CUDA(h, cudaMemcpyAsync(perr, err_step, sizeof(*perr), cudaMemcpyDeviceToHost, h->stream));
-        h->d2h += 8;
-    }
-    if (ss_flag) {  // outputs are only valid if the steady-state test passed: look before copying back
+    if (packed && packed->packed_result) {   // {err, lml, flag} contiguous on the device: one copy
+        TGP_CUDA(h, cudaMemcpyAsync(perr, packed->err, 24, cudaMemcpyDeviceToHost, h->stream));
+        h->d2h += 24;
         TGP_CUDA(h, cudaStreamSynchronize(h->stream));
         if (ss_converged) *ss_converged = *pflag != 0;
         if (*pflag == 0 && *perr == ~0ull) return TGP_OK;
+        if (packed->lml_out && !is_device_ptr(packed->lml_out)) *packed->lml_out = *plml;
+        if (!h->pending.empty()) {
+            TGP_TRY(flush_outputs(h));
+            TGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        }
+    } else {
+        if (ss_flag) {
+            TGP_CUDA(h, cudaMemcpyAsync(pflag, ss_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            h->d2h += 4;
+        }
+        if (err_step) {
+            TGP_CUDA(h, cudaMemcpyAsync(perr, err_step, sizeof(*perr), cudaMemcpyDeviceToHost, h->stream));
+            h->d2h += 8;
+        }
+        if (ss_flag) {  // outputs are only valid if the steady-state test passed: look before copying back
+            TGP_CUDA(h, cudaStreamSynchronize(h->stream));
+            if (ss_converged) *ss_converged = *pflag != 0;
+            if (*pflag == 0 && *perr == ~0ull) return TGP_OK;
+        }
+        TGP_TRY(flush_outputs(h));
+        TGP_CUDA(h, cudaStreamSynchronize(h->stream));
     }
-    TGP_TRY(flush_outputs(h));
-    TGP_CUDA(h, cudaStreamSynchronize(h->stream));
     if (*perr != ~0ull) {
         const long long n = (long long)*perr;
         const long long t = reverse_t ? (long long)T - 1 - n : n;
@@ -165,7 +179,7 @@ int do_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* m_f, int6
             TGP_TRY(filter_steady<D>(h, d, dy, rq, &handled, &flag));
         if (!handled) TGP_TRY(filter_general<D>(h, d, dy, rq));
         bool converged = true;
-        TGP_TRY(end_call(h, rq.err, err_T(d), m->ordering == TGP_REVERSE, flag, &converged));
+        TGP_TRY(end_call(h, rq.err, err_T(d), m->ordering == TGP_REVERSE, flag, &converged, &rq));
         if (converged) return TGP_OK;
         // P had not reached its fixed point after the transient: redo the series with the general scan
         h->pending.clear();

@@ -39,7 +39,7 @@ namespace tgp {
 
 constexpr int kSSThreads = 512;
 constexpr int kSSWarps = kSSThreads / 32;
-constexpr int kTrThreads = 128;              // transient CTA
+constexpr int kTrThreads = 128;              // transient CTA (measured: 256 threads x L=8 is slower, 38 vs 31 us)
 constexpr int kTrWarps = kTrThreads / 32;
 constexpr int kTrL = 16;
 constexpr int kTrBlock = kTrThreads * kTrL;  // 2048 steps per transient block
@@ -71,7 +71,9 @@ struct SSOut {
     double* xT;         // packed final filtering distribution
     double* partials;   // one per CTA
     const double* lml_prefix;  // lml of the transient (device)
-    double* lml_out;    // total
+    double* lml_out;    // total (result block)
+    double* lml_user;   // caller's device destination, nullable
+    int* flag_out;      // convergence word next to lml in the result block
 };
 
 template <int D> __device__ __forceinline__ Vec<D> shfl_up_vec(const Vec<D>& v, int off) {
@@ -107,7 +109,8 @@ template <int D> __device__ __forceinline__ Mat<D> pow_from_squares(const Mat<D>
 template <int D>
 __global__ void __launch_bounds__(kTrThreads)
 k_transient(const DevModel dm, const double* __restrict__ m0, const double* __restrict__ P0, int max_blocks, double tol, int ssL,
-            int G, const FilterOut out, SSConst<D>* __restrict__ cst, unsigned* __restrict__ counters, double* __restrict__ lml_prefix) {
+            int G, const FilterOut out, SSConst<D>* __restrict__ cst, unsigned* __restrict__ counters, double* __restrict__ lml_prefix,
+            int* __restrict__ flag_out) {
     __shared__ Elem<D> tot[kTrWarps];
     __shared__ double blk_state[2][D + Sym<D>::N];
     __shared__ double red[kTrWarps];
@@ -123,6 +126,7 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
     if (tid == 0) {
         store_state<D>(blk_state[0], 1, 0, ldg_vec<D>(m0), ldg_sym_full<D>(P0));
         s_conv = 0;
+        *out.err_step = ~0ull;
     }
     __syncthreads();
     double quad_sum = 0.0, lml_direct = 0.0;
@@ -264,6 +268,7 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
         cst->PRt = p;                               // Phi^512
     } else if (lane == 15) {
         cst->converged = s_conv;
+        *flag_out = s_conv;
         cst->n_blocks = nb;
         cst->N0 = N0; cst->Ts = Ts; cst->Rw = Rw;
         cst->S = S; cst->invS = invS; cst->logS = log(S); cst->hh = hh; cst->conv_err = conv_err;
@@ -349,12 +354,12 @@ struct SSLayout {
     static constexpr int YB = 32 * YS;         // one stage of one warp
     static constexpr int MS = L * D + 1;       // padded chunk stride of the per-warp m_f staging tile
     static constexpr int o_red = CW + (CW & 1);
-    static constexpr int o_y = o_red + 2 * (kSSWarps + 2) * D + ((2 * (kSSWarps + 2) * D) & 1);
+    static constexpr int o_y = o_red + 2 * (kSSWarps + 2) * D + ((2 * (kSSWarps + 2) * D) & 1);   // red: scratch + this CTA's warp aggregates
     static constexpr int o_ms = o_y + kSSWarps * NS * YB;
     static size_t bytes(bool stage_m) { return (size_t)(o_ms + (stage_m ? kSSWarps * 32 * MS : 0)) * sizeof(double); }
 };
 
-template <int D, int L, int NS>
+template <int D, int L, int NS, bool OUTS>
 __global__ void __launch_bounds__(kSSThreads, 1)
 k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, double* __restrict__ zbuf, long long zstride,
           double* __restrict__ agg, unsigned* __restrict__ counters, const SSOut out) {
@@ -460,7 +465,10 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
         }
         if (lane == 0) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) __stcg(agg + (size_t)gw * D + i, Zw[i]);
+            for (int i = 0; i < D; ++i) {
+                __stcg(agg + (size_t)gw * D + i, Zw[i]);
+                red[(kSSWarps + 2 + wp) * D + i] = Zw[i];   // this CTA's warp aggregates stay in shared memory
+            }
         }
         __threadfence();
         __syncthreads();
@@ -496,7 +504,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
         for (int w2 = 0; w2 < wp; ++w2) {
             Vec<D> u;
 #pragma unroll
-            for (int i = 0; i < D; ++i) u[i] = __ldcg(agg + ((size_t)b * kSSWarps + w2) * D + i);
+            for (int i = 0; i < D; ++i) u[i] = red[(kSSWarps + 2 + w2) * D + i];
             m = affine(c.PR[0], m, u);
         }
         m_tile = m;
@@ -506,12 +514,12 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
     double q = 0.0;
     {
         const unsigned long long pol = l2_policy_evict_first();
-        const Mat<D> A = c.A;
-        const Vec<D> av = c.a, wv = c.w;
+        const Mat<D> Ab = c.Abar;
+        const Vec<D> cc = c.c, wv = c.w;
         const double hh = c.hh, invS = c.invS;
         const double lc = -0.5 * (kLog2Pi + c.logS);
-        const bool m_contig = out.m_f && out.s_m == D;
-        const bool staged_out = out.lml_steps || m_contig || out.P_f;
+        const bool m_contig = OUTS && out.m_f && out.s_m == D;
+        const bool staged_out = OUTS && (out.lml_steps || m_contig || out.P_f);
         for (long long it = 0; it < ntiles; ++it) {
             const long long ts = r0 + it * WT;
             const long long cidx = ts / L + lane;
@@ -530,36 +538,46 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             if (nv == L) {
 #pragma unroll
                 for (int j = 0; j < L; ++j) {
-                    const double v = yc[j] - hh - dot(wv, m);
+                    // v = y - (H(A m + a) + h);  m <- A m + a + K v  ==  Abar m + (K y + c): same arithmetic as
+                    // step_logpdf, arranged so the loop-carried chain is one 3-deep matvec instead of dot -> gain -> matvec
+                    const double yv = yc[j];
+                    double v = yv - hh;
+                    Vec<D> u;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) { v = fma(-wv[i], m[i], v); u[i] = fma(K[i], yv, cc[i]); }
                     q = fma(v, v, q);
-                    Vec<D> kv;
+                    m = affine(Ab, m, u);
+                    if (OUTS) {
+                        if (out.lml_steps) yc[j] = fma(-0.5 * invS * v, v, lc);
+                        if (m_contig) {
 #pragma unroll
-                    for (int i = 0; i < D; ++i) kv[i] = fma(K[i], v, av[i]);
-                    m = affine(A, m, kv);
-                    if (out.lml_steps) yc[j] = fma(-0.5 * invS * v, v, lc);
-                    if (m_contig) {
+                            for (int i = 0; i < D; ++i) mc[j * D + i] = m[i];
+                        } else if (out.m_f) {
 #pragma unroll
-                        for (int i = 0; i < D; ++i) mc[j * D + i] = m[i];
-                    } else if (out.m_f) {
-#pragma unroll
-                        for (int i = 0; i < D; ++i) out.m_f[(N0 + t0 + j) * out.s_m + i] = m[i];
+                            for (int i = 0; i < D; ++i) out.m_f[(N0 + t0 + j) * out.s_m + i] = m[i];
+                        }
                     }
                 }
             } else {
                 for (int j = 0; j < nv; ++j) {
-                    const double v = yc[j] - hh - dot(wv, m);
+                    // v = y - (H(A m + a) + h);  m <- A m + a + K v  ==  Abar m + (K y + c): same arithmetic as
+                    // step_logpdf, arranged so the loop-carried chain is one 3-deep matvec instead of dot -> gain -> matvec
+                    const double yv = yc[j];
+                    double v = yv - hh;
+                    Vec<D> u;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) { v = fma(-wv[i], m[i], v); u[i] = fma(K[i], yv, cc[i]); }
                     q = fma(v, v, q);
-                    Vec<D> kv;
+                    m = affine(Ab, m, u);
+                    if (OUTS) {
+                        if (out.lml_steps) yc[j] = fma(-0.5 * invS * v, v, lc);
+                        if (m_contig) {
 #pragma unroll
-                    for (int i = 0; i < D; ++i) kv[i] = fma(K[i], v, av[i]);
-                    m = affine(A, m, kv);
-                    if (out.lml_steps) yc[j] = fma(-0.5 * invS * v, v, lc);
-                    if (m_contig) {
+                            for (int i = 0; i < D; ++i) mc[j * D + i] = m[i];
+                        } else if (out.m_f) {
 #pragma unroll
-                        for (int i = 0; i < D; ++i) mc[j * D + i] = m[i];
-                    } else if (out.m_f) {
-#pragma unroll
-                        for (int i = 0; i < D; ++i) out.m_f[(N0 + t0 + j) * out.s_m + i] = m[i];
+                            for (int i = 0; i < D; ++i) out.m_f[(N0 + t0 + j) * out.s_m + i] = m[i];
+                        }
                     }
                 }
             }
@@ -618,7 +636,9 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             __threadfence();
             double s = 0.0;
             for (int i = 0; i < G; ++i) s += __ldcg(out.partials + i);
-            *out.lml_out = *out.lml_prefix + (double)Ts * (-0.5 * (kLog2Pi + c.logS)) - 0.5 * c.invS * s;
+            const double lml = *out.lml_prefix + (double)Ts * (-0.5 * (kLog2Pi + c.logS)) - 0.5 * c.invS * s;
+            *out.lml_out = lml;
+            if (out.lml_user) *out.lml_user = lml;
         }
     }
 }
@@ -626,14 +646,14 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
 // Forward declaration: a non-converged series is redone by the general scan driver (tgp_drivers.cuh).
 template <int D> int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& rq);
 
-template <int D, int L, int NS>
+template <int D, int L, int NS, bool OUTS>
 int launch_ss_main(tgp_ctx* h, bool stage_m, const SSConst<D>* cst, const double* dy, int64_t T, int G, double* agg,
                    unsigned* counters, const SSOut& so) {
     using LY = SSLayout<D, L, NS>;
     const size_t smem = LY::bytes(stage_m);
     static bool attr_set = false;
     if (!attr_set) {
-        TGP_CUDA(h, cudaFuncSetAttribute(k_ss_main<D, L, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TGP_CUDA(h, cudaFuncSetAttribute(k_ss_main<D, L, NS, OUTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     double* zbuf;
@@ -641,7 +661,8 @@ int launch_ss_main(tgp_ctx* h, bool stage_m, const SSConst<D>* cst, const double
     TGP_TRY(dalloc(h, (size_t)zstride * D, &zbuf));
     void* args[] = {(void*)&cst, (void*)&dy, (void*)&zbuf, (void*)&zstride, (void*)&agg, (void*)&counters, (void*)&so};
     TGP_K(h, "k_ss_main");
-    TGP_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_ss_main<D, L, NS>, dim3((unsigned)G), dim3(kSSThreads), args, smem, h->stream));
+    TGP_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_ss_main<D, L, NS, OUTS>, dim3((unsigned)G), dim3(kSSThreads), args, smem,
+                                            h->stream));
     TGP_LAUNCH_CHECK(h);
     return TGP_OK;
 }
@@ -666,15 +687,17 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
     SSConst<D>* cst;
     double *agg, *partials, *xT, *lml_prefix;
     unsigned* counters;
-    TGP_TRY(dalloc(h, 1, &rq.err));
-    TGP_CUDA(h, cudaMemsetAsync(rq.err, 0xFF, sizeof(unsigned long long), st));
+    // result block: [0] err_step (u64), [1] lml, [2] converged flag -> one D2H copy at the end of the call
+    unsigned long long* resblk;
+    TGP_TRY(dalloc(h, 4, &resblk));
+    rq.err = resblk;
     TGP_TRY(dalloc(h, 1, &cst));
     TGP_TRY(dalloc(h, (size_t)(G * kSSWarps + 1) * D, &agg));
     TGP_TRY(dalloc(h, (size_t)G, &partials));
     TGP_TRY(dalloc(h, D + Sym<D>::N, &xT));
     TGP_TRY(dalloc(h, 2, &counters));
     TGP_TRY(dalloc(h, 1, &lml_prefix));
-    TGP_TRY(dalloc(h, 1, &rq.lml_dev));
+    rq.lml_dev = reinterpret_cast<double*>(resblk + 1);
     DevModel dm{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, dy, 1, T};
     FilterOut fo;
     fo.lml_steps = rq.lml_steps; fo.s_l = 1;
@@ -683,7 +706,8 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
     fo.ws_m = nullptr; fo.partials = nullptr;
     fo.err_step = rq.err;
     TGP_K(h, "k_transient");
-    k_transient<D><<<1, kTrThreads, 0, st>>>(dm, d.m0, d.P0, (int)max_blocks, h->ss_tol, L, G, fo, cst, counters, lml_prefix);
+    k_transient<D><<<1, kTrThreads, 0, st>>>(dm, d.m0, d.P0, (int)max_blocks, h->ss_tol, L, G, fo, cst, counters, lml_prefix,
+                                             reinterpret_cast<int*>(resblk + 2));
     TGP_LAUNCH_CHECK(h);
     SSOut so;
     so.lml_steps = rq.lml_steps;
@@ -693,19 +717,31 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
     so.partials = partials;
     so.lml_prefix = lml_prefix;
     so.lml_out = rq.lml_dev;
+    so.lml_user = (rq.lml_out && is_device_ptr(rq.lml_out)) ? rq.lml_out : nullptr;   // device destination: written by the kernel
+    so.flag_out = reinterpret_cast<int*>(resblk + 2);
     constexpr size_t kSmemMax = 227 * 1024;
-    if (small_L) {
-        if (SSLayout<D, 8, 3>::bytes(stage_m) <= kSmemMax) TGP_TRY((launch_ss_main<D, 8, 3>(h, stage_m, cst, dy, T, G, agg, counters, so)));
-        else TGP_TRY((launch_ss_main<D, 8, 2>(h, stage_m, cst, dy, T, G, agg, counters, so)));
+    const bool outs = rq.lml_steps || rq.m_f || rq.P_f;
+    if (!outs) {          // logpdf: no per-step output, branch-free inner loops
+        if (small_L) {
+            if (SSLayout<D, 8, 3>::bytes(false) <= kSmemMax) TGP_TRY((launch_ss_main<D, 8, 3, false>(h, false, cst, dy, T, G, agg, counters, so)));
+            else TGP_TRY((launch_ss_main<D, 8, 2, false>(h, false, cst, dy, T, G, agg, counters, so)));
+        } else {
+            if (SSLayout<D, 16, 3>::bytes(false) <= kSmemMax) TGP_TRY((launch_ss_main<D, 16, 3, false>(h, false, cst, dy, T, G, agg, counters, so)));
+            else TGP_TRY((launch_ss_main<D, 16, 2, false>(h, false, cst, dy, T, G, agg, counters, so)));
+        }
+    } else if (small_L) {
+        if (SSLayout<D, 8, 3>::bytes(stage_m) <= kSmemMax) TGP_TRY((launch_ss_main<D, 8, 3, true>(h, stage_m, cst, dy, T, G, agg, counters, so)));
+        else TGP_TRY((launch_ss_main<D, 8, 2, true>(h, stage_m, cst, dy, T, G, agg, counters, so)));
     } else {
-        if (SSLayout<D, 16, 3>::bytes(stage_m) <= kSmemMax) TGP_TRY((launch_ss_main<D, 16, 3>(h, stage_m, cst, dy, T, G, agg, counters, so)));
-        else TGP_TRY((launch_ss_main<D, 16, 2>(h, stage_m, cst, dy, T, G, agg, counters, so)));
+        if (SSLayout<D, 16, 3>::bytes(stage_m) <= kSmemMax) TGP_TRY((launch_ss_main<D, 16, 3, true>(h, stage_m, cst, dy, T, G, agg, counters, so)));
+        else TGP_TRY((launch_ss_main<D, 16, 2, true>(h, stage_m, cst, dy, T, G, agg, counters, so)));
     }
     rq.xT = xT;
     rq.x0buf = nullptr;
-    *flag = &cst->converged;
+    *flag = reinterpret_cast<const int*>(resblk + 2);
     *handled = true;
-    return deliver_scalar(h, rq.lml_dev, rq.lml_out);
+    rq.packed_result = true;     // end_call fetches (err, lml, flag) with one copy
+    return TGP_OK;
 }
 
 }  // namespace tgp

@@ -122,3 +122,31 @@ extern "C" int emul_smooth_scan(const tgp_lgssm* md, const double* m_f, const do
         default: return TGP_EUNSUPPORTED;
     }
 }
+
+// Phase 1 of the time-sharded path on the CPU (test stand-in for tgp_shard_reduce): folds a whole shard into ONE
+// element in the ABI's shard format (A, b, C, eta, J; full column-major matrices).
+template <int D>
+static int shard_reduce(const tgp_lgssm* md, const double* y, double* out) {
+    Elem<D> E = elem_identity<D>();
+    for (int64_t t = 0; t < md->T; ++t) fold_step(E, step_const<D>(md, t), y[t]);
+    double* p = out;
+    for (int k = 0; k < D * D; ++k) p[k] = E.A.v[k];
+    p += D * D;
+    for (int k = 0; k < D; ++k) p[k] = E.b.v[k];
+    p += D;
+    for (int j = 0; j < D; ++j) for (int i = 0; i < D; ++i) p[i + D * j] = E.C(i, j);
+    p += D * D;
+    for (int k = 0; k < D; ++k) p[k] = E.eta.v[k];
+    p += D;
+    for (int j = 0; j < D; ++j) for (int i = 0; i < D; ++i) p[i + D * j] = E.J(i, j);
+    return TGP_OK;
+}
+extern "C" int emul_shard_reduce(const tgp_lgssm* md, const double* y, double* out) {
+    switch (md->D) {
+        case 1: return shard_reduce<1>(md, y, out);
+        case 2: return shard_reduce<2>(md, y, out);
+        case 3: return shard_reduce<3>(md, y, out);
+        case 4: return shard_reduce<4>(md, y, out);
+        default: return TGP_EUNSUPPORTED;
+    }
+}
