@@ -45,7 +45,7 @@ class ShardedLogpdf:
         self.part = torch.zeros(1, dtype=torch.float64, device=device)
         self.m0 = np.array(marshalled.keep[-2])
         self.P0 = np.array(marshalled.keep[-1])
-        self.desc2 = copy.copy(marshalled.desc)
+        self.desc2 = type(marshalled.desc).from_buffer_copy(marshalled.desc)   # ctypes structs with pointers cannot be copy.copy'd
         self._ybuf = None
 
     def logpdf(self, y_dev, lml_out_dev):
