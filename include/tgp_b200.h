@@ -152,6 +152,17 @@ int tgp_shard_reduce(tgp_handle h, const tgp_lgssm* shard, const double* y, doub
 int tgp_shard_prefix(tgp_handle h, int D, int n_elems, const double* elems /*host*/,
                      const double* m0, const double* P0, double* m_in, double* P_in /*host*/);
 
+/* Steady-state variant for TIME-INVARIANT shards (RegularSpacing + homoscedastic noise; every shard >= 65536 steps):
+ * the exchange shrinks to one affine record (Phi_shard, Z_shard) = D*D + D doubles per rank (96 B at D = 3) and no
+ * host round trip is needed: tgp_shard_phase1 enqueues the zero-state pass and leaves this rank's record in
+ * xchg_out (DEVICE memory) without synchronising; the caller all-gathers the records on the same stream
+ * (ncclAllGather); tgp_shard_phase2 filters the shard from the mean folded out of the records of the ranks before it
+ * and writes the shard's log-likelihood to lml_partial (DEVICE); the caller sums the partials (ncclAllReduce).
+ * y must stay valid (and, if it is a host pointer, unchanged) between the two calls. */
+int tgp_shard_xchg_size(int D);                            /* D*D + D */
+int tgp_shard_phase1(tgp_handle h, const tgp_lgssm* shard, const double* y, int rank, int world, double* xchg_out);
+int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,9 @@ _SIGS = {
                                           C.c_void_p, C.c_void_p]),
     "tgp_elem_size": (C.c_int, [C.c_int]),
     "tgp_shard_reduce": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p]),
+    "tgp_shard_xchg_size": (C.c_int, [C.c_int]),
+    "tgp_shard_phase1": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "tgp_shard_phase2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgp_shard_prefix": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
@@ -197,6 +200,12 @@ class Handle:
 
     def shard_prefix(self, D, elems, m0, P0):
         return shard_prefix(D, elems, m0, P0, self)
+
+    def shard_phase1(self, desc, y, rank, world, xchg_out):
+        self.check(lib().tgp_shard_phase1(self._h, C.byref(desc), ptr(y), int(rank), int(world), ptr(xchg_out)))
+
+    def shard_phase2(self, xchg_all, lml_partial):
+        self.check(lib().tgp_shard_phase2(self._h, ptr(xchg_all), ptr(lml_partial)))
 
 
 def shard_prefix(D, elems, m0, P0, handle=None):

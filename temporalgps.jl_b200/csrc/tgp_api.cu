@@ -246,6 +246,27 @@ int tgp_shard_reduce(tgp_handle h, const tgp_lgssm* shard, const double* y, doub
 #undef CALL
 }
 
+int tgp_shard_phase1(tgp_handle h, const tgp_lgssm* shard, const double* y, int rank, int world, double* xchg_out) {
+    TGP_TRY(validate(h, shard, true, y));
+    TGP_TRY(require_scalar_obs(h, shard));
+    if (rank < 0 || world < 1 || rank >= world || !xchg_out) return fail(h, TGP_EINVAL, "bad rank / world / xchg_out");
+    TGP_TRY(begin_call(h));
+#define CALL(Dv) do_shard_phase1<Dv>(h, shard, y, rank, world, xchg_out)
+    TGP_DISPATCH_D(h, shard->D)
+#undef CALL
+}
+
+int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial) {
+    if (!h) return TGP_EINVAL;
+    if (!xchg_all || !lml_partial) return fail(h, TGP_EINVAL, "xchg_all and lml_partial must be non-NULL");
+    TGP_CUDA(h, cudaSetDevice(h->device));
+#define CALL(Dv) do_shard_phase2<Dv>(h, xchg_all, lml_partial)
+    TGP_DISPATCH_D(h, h->shard.D)
+#undef CALL
+}
+
+int tgp_shard_xchg_size(int D) { return D * D + D; }
+
 int tgp_shard_prefix(tgp_handle h, int D, int n_elems, const double* elems, const double* m0, const double* P0, double* m_in,
                      double* P_in) {
     // pure host arithmetic (no device work): h may be NULL

@@ -56,6 +56,15 @@ struct Arena {
 
 }  // namespace tgp
 
+// State kept between the two phases of a time-sharded steady-state run (tgp_shard_phase1 / tgp_shard_phase2).
+struct tgp_shard_state {
+    bool active = false;
+    int D = 0, rank = 0, world = 0;
+    int64_t T = 0;
+    const double* dy = nullptr;
+    alignas(8) char work[256];   // tgp::SSWork<D>: device pointers of the run's workspace
+};
+
 struct tgp_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -78,6 +87,7 @@ struct tgp_ctx {
     std::vector<cudaEvent_t> ev_pool;
     const char* cur_name = nullptr;
     cudaEvent_t cur_t0 = nullptr;
+    tgp_shard_state shard;
 };
 
 namespace tgp {

@@ -13,6 +13,8 @@ template <int D> int do_posterior(tgp_ctx* h, const tgp_lgssm* m, const double* 
                                   double* m_T, double* P_T);
 template <int D> int do_marginals(tgp_ctx* h, const tgp_lgssm* m, double* mean_out, double* var_out);
 template <int D> int do_shard_reduce(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* elem_out);
+template <int D> int do_shard_phase1(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, int world, double* xchg_out);
+template <int D> int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double* lml_partial);
 template <int D> int do_shard_prefix(int n, const double* elems, const double* m0, const double* P0, double* m_in,
                                      double* P_in);
 
@@ -25,6 +27,8 @@ template <int D> int do_shard_prefix(int n, const double* elems, const double* m
                                          double*, double*);                                                          \
     extern template int do_marginals<Dv>(tgp_ctx*, const tgp_lgssm*, double*, double*);                              \
     extern template int do_shard_reduce<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, double*);                     \
+    extern template int do_shard_phase1<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, int, int, double*);           \
+    extern template int do_shard_phase2<Dv>(tgp_ctx*, const double*, double*);                                       \
     extern template int do_shard_prefix<Dv>(int, const double*, const double*, const double*, double*, double*);
 
 // The set of latent dimensions with kernel instantiations (keep in step with build.py's TGP_DIMS).

@@ -358,6 +358,38 @@ int do_shard_reduce(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* ele
     return end_call(h, nullptr, T, false);
 }
 
+// Time-sharded steady-state logpdf (time-invariant models): phase 1 leaves this rank's record (Phi, Z) in xchg_out
+// (device, D*D + D doubles) without synchronising; the caller all-gathers the records; phase 2 filters the shard from
+// the folded incoming mean and writes the shard's log-likelihood to lml_partial (device).
+template <int D>
+int do_shard_phase1(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, int world, double* xchg_out) {
+    if (m->ordering != TGP_FORWARD || !time_invariant(*m))
+        return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path runs Forward, time-invariant models (use tgp_shard_reduce otherwise)");
+    if (!is_device_ptr(xchg_out)) return fail(h, TGP_EINVAL, "xchg_out must be a device pointer");
+    tgp_lgssm d;
+    const double* dy;
+    TGP_TRY(stage_model(h, m, y, &d, &dy));
+    return shard_phase1<D>(h, &h->shard, d, dy, rank, world, xchg_out);
+}
+
+template <int D>
+int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double* lml_partial) {
+    if (!h->shard.active || h->shard.D != D) return fail(h, TGP_EINVAL, "tgp_shard_phase2 without a matching tgp_shard_phase1");
+    if (!is_device_ptr(xchg_all) || !is_device_ptr(lml_partial)) return fail(h, TGP_EINVAL, "xchg_all and lml_partial must be device pointers");
+    const int64_t T = h->shard.T;
+    SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(h->shard.work);
+    TGP_TRY(shard_phase2<D>(h, &h->shard, xchg_all, lml_partial));
+    FilterReq rq;
+    rq.err = w.resblk;
+    rq.packed_result = true;
+    bool converged = true;
+    TGP_TRY(end_call(h, rq.err, T, false, reinterpret_cast<const int*>(w.resblk + 2), &converged, &rq));
+    if (!converged)
+        return fail(h, TGP_EUNSUPPORTED, "the filtering covariance did not converge within the transient budget on this shard; "
+                                         "use the general sharded path (tgp_shard_reduce / tgp_shard_prefix)");
+    return TGP_OK;
+}
+
 template <int D>
 int do_shard_prefix(int n, const double* elems, const double* m0, const double* P0, double* m_in, double* P_in) {
     Vec<D> m;

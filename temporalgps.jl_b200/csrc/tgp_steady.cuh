@@ -76,6 +76,16 @@ struct SSOut {
     int* flag_out;      // convergence word next to lml in the result block
 };
 
+// Time-sharded (multi-GPU) use of the steady kernel: phase 0 = whole filter in one launch (single GPU);
+// phase 1 = zero-state pass only, ending with the shard record (Phi_shard, Z_shard) in xchg_out; phase 2 = the
+// per-step pass, starting from the mean folded out of the gathered records of the ranks before this one.
+struct SSShard {
+    int phase, rank, world;
+    double* xchg_out;         // D*D + D doubles (phase 1)
+    const double* xchg_all;   // world x (D*D + D) doubles (phase 2)
+    const void* sq;           // Mat<D>[kSqN]: squares table Abar^(2^k) (global memory)
+};
+
 template <int D> __device__ __forceinline__ Vec<D> shfl_up_vec(const Vec<D>& v, int off) {
     Vec<D> r;
 #pragma unroll
@@ -110,7 +120,7 @@ template <int D>
 __global__ void __launch_bounds__(kTrThreads)
 k_transient(const DevModel dm, const double* __restrict__ m0, const double* __restrict__ P0, int max_blocks, double tol, int ssL,
             int G, const FilterOut out, SSConst<D>* __restrict__ cst, unsigned* __restrict__ counters, double* __restrict__ lml_prefix,
-            int* __restrict__ flag_out) {
+            int* __restrict__ flag_out, Mat<D>* __restrict__ sq_out, int constants_only) {
     __shared__ Elem<D> tot[kTrWarps];
     __shared__ double blk_state[2][D + Sym<D>::N];
     __shared__ double red[kTrWarps];
@@ -221,7 +231,7 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
         double t = 0.0;
 #pragma unroll
         for (int i = 0; i < kTrWarps; ++i) t += red[i];
-        *lml_prefix = t;
+        *lml_prefix = constants_only ? 0.0 : t;   // constants_only: a later shard of a time-sharded series; its steps are all steady
     }
     if (wp != 0) return;
     // ---- constants of the steady phase (warp 0) ---------------------------------------------------
@@ -245,12 +255,12 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
     {   // squares table (every lane computes it; lane 0 publishes)
         Mat<D> p = Abar;
         for (int k = 0; k < kSqN; ++k) {
-            if (lane == 0) sq[k] = p;
+            if (lane == 0) { sq[k] = p; sq_out[k] = p; }
             p = matmul(p, p);
         }
     }
     __syncwarp();
-    const long long N0 = (long long)nb * kTrBlock;
+    const long long N0 = constants_only ? 0 : (long long)nb * kTrBlock;
     const long long Ts = dm.T - N0;
     const long long wt = 32ll * ssL;               // warp tile
     const long long nwarps = (long long)G * kSSWarps;
@@ -272,7 +282,7 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
         cst->n_blocks = nb;
         cst->N0 = N0; cst->Ts = Ts; cst->Rw = Rw;
         cst->S = S; cst->invS = invS; cst->logS = log(S); cst->hh = hh; cst->conv_err = conv_err;
-        cst->K = K; cst->w = w; cst->a = a; cst->x_in = mT;
+        cst->K = K; cst->w = w; cst->a = a; cst->x_in = constants_only ? vzero<D>() : mT;
 #pragma unroll
         for (int i = 0; i < D; ++i) cst->c[i] = fma(-K[i], hh, a[i]);
         cst->A = A; cst->Abar = Abar;
@@ -362,7 +372,7 @@ struct SSLayout {
 template <int D, int L, int NS, bool OUTS>
 __global__ void __launch_bounds__(kSSThreads, 1)
 k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, double* __restrict__ zbuf, long long zstride,
-          double* __restrict__ agg, unsigned* __restrict__ counters, const SSOut out) {
+          double* __restrict__ agg, unsigned* __restrict__ counters, const SSOut out, const SSShard sh) {
     using LY = SSLayout<D, L, NS>;
     static_assert(L % 2 == 0 && (128 % L) == 0 && NS >= 2, "layout assumptions");
     extern __shared__ __align__(16) double smem[];
@@ -411,8 +421,9 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
     const long long ntiles = (r1 - r0 + WT - 1) / WT;
 
     // ---- phase 1: zero-state responses, warp by warp ----------------------------------------------------
-    {
+    if (sh.phase != 2) {
         const unsigned long long pol = l2_policy_evict_last();
+        const Mat<D>* sqt = reinterpret_cast<const Mat<D>*>(sh.sq);
         Vec<D> Zw = vzero<D>();
 #pragma unroll
         for (int s = 0; s < NS - 1; ++s) {
@@ -428,15 +439,28 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             if (it + NS - 1 < ntiles) issue_tile(ts + (NS - 1) * WT, (int)((it + NS - 1) % NS), pol);
             cp_async_commit();
             const double* yc = ybuf + (int)(it % NS) * LY::YB + lane * LY::YS;
-            Vec<D> z = vzero<D>();
+            const bool tail = sh.phase == 1 && ts + WT > Ts;   // the shard's last, partial tile: its aggregate is consumed
+            Vec<D> z = vzero<D>();                             // by the next rank, so it must be aligned at step Ts-1 exactly
+            if (!tail) {
 #pragma unroll
-            for (int j = 0; j < L; ++j) {
-                const double yv = yc[j];
-                Vec<D> u;
+                for (int j = 0; j < L; ++j) {
+                    const double yv = yc[j];
+                    Vec<D> u;
 #pragma unroll
-                for (int i = 0; i < D; ++i) u[i] = fma(K[i], yv, cc[i]);
-                z = affine(Ab, z, u);
+                    for (int i = 0; i < D; ++i) u[i] = fma(K[i], yv, cc[i]);
+                    z = affine(Ab, z, u);
+                }
+            } else {
+                const int nv = (int)max(0ll, min((long long)L, Ts - ts - (long long)lane * L));
+                for (int j = 0; j < nv; ++j) {
+                    const double yv = yc[j];
+                    Vec<D> u;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) u[i] = fma(K[i], yv, cc[i]);
+                    z = affine(Ab, z, u);
+                }
             }
+            const Vec<D> zraw = z;
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 const Vec<D> zu = shfl_up_vec(z, 1 << k);
@@ -446,31 +470,81 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
 #pragma unroll
             for (int i = 0; i < D; ++i) tot[i] = __shfl_sync(0xffffffffu, z[i], 31);
             if (lane == 0) ze = vzero<D>();
-            Zw = affine(c.Pt, Zw, tot);
+            if (!tail) {
+                Zw = affine(c.Pt, Zw, tot);
+            } else {   // exact: Abar^nvp * incl[lf-1] + raw[lf], then Abar^nt * Zw + that
+                const int nt = (int)(Ts - ts), lf = nt / L, nvp = nt % L;
+                Vec<D> zi = vzero<D>(), zr = vzero<D>();
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    const double a1 = __shfl_sync(0xffffffffu, z[i], (lf + 31) & 31);
+                    const double a2 = __shfl_sync(0xffffffffu, zraw[i], lf & 31);
+                    zi[i] = lf > 0 ? a1 : 0.0;
+                    zr[i] = nvp > 0 ? a2 : 0.0;
+                }
+                const Vec<D> zt = affine(pow_from_squares<D>(sqt, (unsigned long long)nvp), zi, zr);
+                Zw = affine(pow_from_squares<D>(sqt, (unsigned long long)nt), Zw, zt);
+            }
             const long long cidx = ts / L + lane;
 #pragma unroll
             for (int i = 0; i < D; ++i) __stcg(zbuf + i * zstride + cidx, ze[i]);
         }
         cp_async_wait<0>();
         __syncwarp();
-        // a range shorter than Rw (the last ones) is never consumed, so no alignment fix-up is needed.
-        // Prefetch the first tiles of phase 2 across the barrier.
-        {
-            const unsigned long long pol2 = l2_policy_evict_first();
-#pragma unroll
-            for (int s = 0; s < NS - 1; ++s) {
-                if (s < ntiles) issue_tile(r0 + s * WT, s, pol2);
-                cp_async_commit();
-            }
-        }
         if (lane == 0) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-                __stcg(agg + (size_t)gw * D + i, Zw[i]);
-                red[(kSSWarps + 2 + wp) * D + i] = Zw[i];   // this CTA's warp aggregates stay in shared memory
-            }
+            for (int i = 0; i < D; ++i) __stcg(agg + (size_t)gw * D + i, Zw[i]);
         }
         __threadfence();
+    }
+    if (sh.phase == 1) {
+        // ---- shard record by the last CTA to finish: Z_shard = Abar^rem * (sum of the full ranges) + last range ----
+        int* s_last = reinterpret_cast<int*>(red + 2 * (kSSWarps + 2) * D - 1);   // last word of the scratch area
+        __syncthreads();
+        if (tid == 0) *s_last = (atomicAdd(counters, 1u) == (unsigned)G - 1) ? 1 : 0;
+        __syncthreads();
+        if (!*s_last) return;
+        __threadfence();
+        const Mat<D>* sqt = reinterpret_cast<const Mat<D>*>(sh.sq);
+        const long long e_last = Ts > 0 ? (Ts - 1) / Rw : 0;
+        const long long rem = Ts - e_last * Rw;
+        const long long J = (e_last + kSSThreads - 1) / kSSThreads;
+        const long long pad = J * kSSThreads - e_last;
+        const Mat<D> Bt = c.PRt;
+        Vec<D> z = vzero<D>();
+        for (long long j = 0; j < J; ++j) {
+            const long long e = j * kSSThreads + tid - pad;
+            Vec<D> u = vzero<D>();
+            if (e >= 0) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) u[i] = __ldcg(agg + (size_t)e * D + i);
+            }
+            z = affine(Bt, z, u);
+        }
+        const Vec<D> Sfull = cta_decayed_sum<D>(z, c.PR, c.PRw, red);
+        if (tid == 0) {
+            Vec<D> zl;
+#pragma unroll
+            for (int i = 0; i < D; ++i) zl[i] = __ldcg(agg + (size_t)e_last * D + i);
+            Vec<D> Z = affine(pow_from_squares<D>(sqt, (unsigned long long)rem), Sfull, zl);
+            const Mat<D> Phi = pow_from_squares<D>(sqt, (unsigned long long)Ts);
+            if (sh.rank == 0) Z = affine(Phi, c.x_in, Z);     // rank 0 knows its incoming mean: ship the end STATE
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) sh.xchg_out[i] = Phi.v[i];
+#pragma unroll
+            for (int i = 0; i < D; ++i) sh.xchg_out[D * D + i] = Z[i];
+        }
+        return;
+    }
+    {   // prefetch the first tiles of phase 2 (across the barrier when phase == 0)
+        const unsigned long long pol2 = l2_policy_evict_first();
+#pragma unroll
+        for (int s = 0; s < NS - 1; ++s) {
+            if (s < ntiles) issue_tile(r0 + s * WT, s, pol2);
+            cp_async_commit();
+        }
+    }
+    if (sh.phase == 0) {
         __syncthreads();
         if (tid == 0) {
             atomicAdd(counters, 1u);
@@ -479,6 +553,27 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
         }
         __syncthreads();
     }
+    // this CTA's warp aggregates -> shared memory (phase 2 of a sharded run reads what phase 1 left in agg)
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) red[(kSSWarps + 2 + wp) * D + i] = __ldcg(agg + (size_t)gw * D + i);
+    }
+    Vec<D> x_in = c.x_in;
+    if (sh.phase == 2 && sh.rank > 0) {   // fold the records of the ranks before this one: x <- Phi_r x + Z_r
+        Vec<D> x = vzero<D>();
+        for (int r = 0; r < sh.rank; ++r) {
+            const double* rec = sh.xchg_all + (size_t)r * (D * D + D);
+            Mat<D> Ph;
+            Vec<D> Zr;
+#pragma unroll
+            for (int i = 0; i < D * D; ++i) Ph.v[i] = __ldg(rec + i);
+#pragma unroll
+            for (int i = 0; i < D; ++i) Zr[i] = __ldg(rec + D * D + i);
+            x = affine(Ph, x, Zr);
+        }
+        x_in = x;
+    }
+    __syncthreads();
 
     // ---- mean entering this warp's range: Phi^gw x_in + sum_{e<gw} Phi^(gw-1-e) Z_e -----------------------
     Vec<D> m_tile;
@@ -492,7 +587,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
         for (long long j = 0; j < J; ++j) {
             const long long e = j * kSSThreads + tid - pad;
             Vec<D> u = vzero<D>();
-            if (e == 0) u = c.x_in;
+            if (e == 0) u = x_in;
             else if (e > 0) {
 #pragma unroll
                 for (int i = 0; i < D; ++i) u[i] = __ldcg(agg + (size_t)(e - 1) * D + i);
@@ -647,22 +742,84 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
 template <int D> int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& rq);
 
 template <int D, int L, int NS, bool OUTS>
-int launch_ss_main(tgp_ctx* h, bool stage_m, const SSConst<D>* cst, const double* dy, int64_t T, int G, double* agg,
-                   unsigned* counters, const SSOut& so) {
+int launch_ss_main(tgp_ctx* h, bool stage_m, const SSConst<D>* cst, const double* dy, double* zbuf, long long zstride, int G, double* agg,
+                   unsigned* counters, const SSOut& so, const SSShard& sh) {
     using LY = SSLayout<D, L, NS>;
     const size_t smem = LY::bytes(stage_m);
-    static bool attr_set = false;
-    if (!attr_set) {
-        TGP_CUDA(h, cudaFuncSetAttribute(k_ss_main<D, L, NS, OUTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+    static size_t attr_smem = 0;   // opt in to exactly what this instantiation needs (static + dynamic must stay <= 227 KB)
+    if (smem > attr_smem) {
+        TGP_CUDA(h, cudaFuncSetAttribute(k_ss_main<D, L, NS, OUTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
     }
-    double* zbuf;
-    const long long zstride = (T + (long long)G * kSSWarps * LY::WT) / L + 64;
-    TGP_TRY(dalloc(h, (size_t)zstride * D, &zbuf));
-    void* args[] = {(void*)&cst, (void*)&dy, (void*)&zbuf, (void*)&zstride, (void*)&agg, (void*)&counters, (void*)&so};
-    TGP_K(h, "k_ss_main");
+    void* args[] = {(void*)&cst, (void*)&dy, (void*)&zbuf, (void*)&zstride, (void*)&agg, (void*)&counters, (void*)&so, (void*)&sh};
+    TGP_K(h, sh.phase == 1 ? "k_ss_main(phase1)" : (sh.phase == 2 ? "k_ss_main(phase2)" : "k_ss_main"));
     TGP_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_ss_main<D, L, NS, OUTS>, dim3((unsigned)G), dim3(kSSThreads), args, smem,
                                             h->stream));
+    TGP_LAUNCH_CHECK(h);
+    return TGP_OK;
+}
+
+// Picks the (L, stages, outputs) instantiation that fits shared memory and launches it.
+template <int D>
+int dispatch_ss_main(tgp_ctx* h, bool small_L, bool outs, bool stage_m, const SSConst<D>* cst, const double* dy, double* zbuf,
+                     long long zstride, int G, double* agg, unsigned* counters, const SSOut& so, const SSShard& sh) {
+    constexpr size_t kSmemMax = 227 * 1024;
+#define TGP_SS_LAUNCH(Lv, Ov, sm)                                                                                          \
+    do {                                                                                                                   \
+        if (SSLayout<D, Lv, 3>::bytes(sm) <= kSmemMax) return launch_ss_main<D, Lv, 3, Ov>(h, sm, cst, dy, zbuf, zstride, G, agg, counters, so, sh); \
+        return launch_ss_main<D, Lv, 2, Ov>(h, sm, cst, dy, zbuf, zstride, G, agg, counters, so, sh);                      \
+    } while (0)
+    if (!outs) {          // logpdf: no per-step output, branch-free inner loops
+        if (small_L) TGP_SS_LAUNCH(8, false, false);
+        TGP_SS_LAUNCH(16, false, false);
+    }
+    if (small_L) TGP_SS_LAUNCH(8, true, stage_m);
+    TGP_SS_LAUNCH(16, true, stage_m);
+#undef TGP_SS_LAUNCH
+}
+
+// Workspace of one steady-state run (kept in the handle between the two phases of a sharded run).
+template <int D>
+struct SSWork {
+    SSConst<D>* cst;
+    Mat<D>* sq;
+    double *agg, *partials, *xT, *lml_prefix, *zbuf;
+    long long zstride;
+    unsigned* counters;
+    unsigned long long* resblk;   // {u64 err_step, double lml, int converged}
+    int G, L;
+};
+
+template <int D>
+int ss_alloc(tgp_ctx* h, int64_t T, bool small_L, SSWork<D>* w) {
+    w->G = h->sm_count;                       // one 512-thread CTA per SM
+    w->L = small_L ? 8 : 16;
+    TGP_TRY(dalloc(h, 4, &w->resblk));
+    TGP_TRY(dalloc(h, 1, &w->cst));
+    TGP_TRY(dalloc(h, kSqN, &w->sq));
+    TGP_TRY(dalloc(h, (size_t)(w->G * kSSWarps + 1) * D, &w->agg));
+    TGP_TRY(dalloc(h, (size_t)w->G, &w->partials));
+    TGP_TRY(dalloc(h, D + Sym<D>::N, &w->xT));
+    TGP_TRY(dalloc(h, 2, &w->counters));
+    TGP_TRY(dalloc(h, 1, &w->lml_prefix));
+    w->zstride = (T + (long long)w->G * kSSWarps * 32 * w->L) / w->L + 64;
+    TGP_TRY(dalloc(h, (size_t)w->zstride * D, &w->zbuf));
+    return TGP_OK;
+}
+
+template <int D>
+int ss_transient(tgp_ctx* h, const tgp_lgssm& d, const double* dy, const FilterReq& rq, const SSWork<D>& w, int64_t max_blocks,
+                 int constants_only) {
+    DevModel dm{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, dy, 1, d.T};
+    FilterOut fo;
+    fo.lml_steps = rq.lml_steps; fo.s_l = 1;
+    fo.m_f = rq.m_f; fo.s_m = rq.s_m;
+    fo.P_f = rq.P_f; fo.s_P = rq.s_P;
+    fo.ws_m = nullptr; fo.partials = nullptr;
+    fo.err_step = w.resblk;
+    TGP_K(h, "k_transient");
+    k_transient<D><<<1, kTrThreads, 0, h->stream>>>(dm, d.m0, d.P0, (int)max_blocks, h->ss_tol, w.L, w.G, fo, w.cst, w.counters, w.lml_prefix,
+                                                    reinterpret_cast<int*>(w.resblk + 2), w.sq, constants_only);
     TGP_LAUNCH_CHECK(h);
     return TGP_OK;
 }
@@ -678,69 +835,71 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
     if (rq.keep_ws || T < 65536) return TGP_OK;
     int64_t max_blocks = h->ss_prefix > 0 ? (h->ss_prefix + kTrBlock - 1) / kTrBlock : 8;
     max_blocks = std::max<int64_t>(1, std::min<int64_t>(max_blocks, T / (2 * kTrBlock)));
-    cudaStream_t st = h->stream;
     const bool stage_m = rq.m_f && rq.s_m == D;
     const bool small_L = rq.m_f != nullptr || h->chunk == 8;   // m_f staging tile must fit next to the y ring
-    const int G = h->sm_count;                                  // one 512-thread CTA per SM
-    const int L = small_L ? 8 : 16;
-
-    SSConst<D>* cst;
-    double *agg, *partials, *xT, *lml_prefix;
-    unsigned* counters;
-    // result block: [0] err_step (u64), [1] lml, [2] converged flag -> one D2H copy at the end of the call
-    unsigned long long* resblk;
-    TGP_TRY(dalloc(h, 4, &resblk));
-    rq.err = resblk;
-    TGP_TRY(dalloc(h, 1, &cst));
-    TGP_TRY(dalloc(h, (size_t)(G * kSSWarps + 1) * D, &agg));
-    TGP_TRY(dalloc(h, (size_t)G, &partials));
-    TGP_TRY(dalloc(h, D + Sym<D>::N, &xT));
-    TGP_TRY(dalloc(h, 2, &counters));
-    TGP_TRY(dalloc(h, 1, &lml_prefix));
-    rq.lml_dev = reinterpret_cast<double*>(resblk + 1);
-    DevModel dm{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, dy, 1, T};
-    FilterOut fo;
-    fo.lml_steps = rq.lml_steps; fo.s_l = 1;
-    fo.m_f = rq.m_f; fo.s_m = rq.s_m;
-    fo.P_f = rq.P_f; fo.s_P = rq.s_P;
-    fo.ws_m = nullptr; fo.partials = nullptr;
-    fo.err_step = rq.err;
-    TGP_K(h, "k_transient");
-    k_transient<D><<<1, kTrThreads, 0, st>>>(dm, d.m0, d.P0, (int)max_blocks, h->ss_tol, L, G, fo, cst, counters, lml_prefix,
-                                             reinterpret_cast<int*>(resblk + 2));
-    TGP_LAUNCH_CHECK(h);
+    SSWork<D> w;
+    TGP_TRY(ss_alloc<D>(h, T, small_L, &w));
+    rq.err = w.resblk;
+    rq.lml_dev = reinterpret_cast<double*>(w.resblk + 1);
+    TGP_TRY(ss_transient<D>(h, d, dy, rq, w, max_blocks, 0));
     SSOut so;
     so.lml_steps = rq.lml_steps;
     so.m_f = rq.m_f; so.s_m = rq.s_m;
     so.P_f = rq.P_f; so.s_P = rq.s_P;
-    so.xT = xT;
-    so.partials = partials;
-    so.lml_prefix = lml_prefix;
+    so.xT = w.xT;
+    so.partials = w.partials;
+    so.lml_prefix = w.lml_prefix;
     so.lml_out = rq.lml_dev;
     so.lml_user = (rq.lml_out && is_device_ptr(rq.lml_out)) ? rq.lml_out : nullptr;   // device destination: written by the kernel
-    so.flag_out = reinterpret_cast<int*>(resblk + 2);
-    constexpr size_t kSmemMax = 227 * 1024;
+    so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
+    const SSShard sh{0, 0, 1, nullptr, nullptr, w.sq};
     const bool outs = rq.lml_steps || rq.m_f || rq.P_f;
-    if (!outs) {          // logpdf: no per-step output, branch-free inner loops
-        if (small_L) {
-            if (SSLayout<D, 8, 3>::bytes(false) <= kSmemMax) TGP_TRY((launch_ss_main<D, 8, 3, false>(h, false, cst, dy, T, G, agg, counters, so)));
-            else TGP_TRY((launch_ss_main<D, 8, 2, false>(h, false, cst, dy, T, G, agg, counters, so)));
-        } else {
-            if (SSLayout<D, 16, 3>::bytes(false) <= kSmemMax) TGP_TRY((launch_ss_main<D, 16, 3, false>(h, false, cst, dy, T, G, agg, counters, so)));
-            else TGP_TRY((launch_ss_main<D, 16, 2, false>(h, false, cst, dy, T, G, agg, counters, so)));
-        }
-    } else if (small_L) {
-        if (SSLayout<D, 8, 3>::bytes(stage_m) <= kSmemMax) TGP_TRY((launch_ss_main<D, 8, 3, true>(h, stage_m, cst, dy, T, G, agg, counters, so)));
-        else TGP_TRY((launch_ss_main<D, 8, 2, true>(h, stage_m, cst, dy, T, G, agg, counters, so)));
-    } else {
-        if (SSLayout<D, 16, 3>::bytes(stage_m) <= kSmemMax) TGP_TRY((launch_ss_main<D, 16, 3, true>(h, stage_m, cst, dy, T, G, agg, counters, so)));
-        else TGP_TRY((launch_ss_main<D, 16, 2, true>(h, stage_m, cst, dy, T, G, agg, counters, so)));
-    }
-    rq.xT = xT;
+    TGP_TRY(dispatch_ss_main<D>(h, small_L, outs, stage_m, w.cst, dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh));
+    rq.xT = w.xT;
     rq.x0buf = nullptr;
-    *flag = reinterpret_cast<const int*>(resblk + 2);
+    *flag = reinterpret_cast<const int*>(w.resblk + 2);
     *handled = true;
     rq.packed_result = true;     // end_call fetches (err, lml, flag) with one copy
+    return TGP_OK;
+}
+
+// ---- time-sharded steady-state logpdf: two stream-ordered phases around the caller's all-gather -------------------
+template <int D>
+int shard_phase1(tgp_ctx* h, tgp_shard_state* st, const tgp_lgssm& d, const double* dy, int rank, int world, double* xchg_out) {
+    static_assert(sizeof(SSWork<D>) <= sizeof(st->work), "SSWork must fit tgp_shard_state::work");
+    const int64_t T = d.T;
+    const int64_t max_blocks = std::max<int64_t>(1, std::min<int64_t>(h->ss_prefix > 0 ? (h->ss_prefix + kTrBlock - 1) / kTrBlock : 8,
+                                                                      T / (2 * kTrBlock)));
+    if (T < 65536) return fail(h, TGP_EUNSUPPORTED, "time shards must hold at least 65536 steps for the steady-state sharded path");
+    SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(st->work);
+    TGP_TRY(ss_alloc<D>(h, T, false, &w));
+    FilterReq rq;
+    TGP_TRY(ss_transient<D>(h, d, dy, rq, w, max_blocks, rank > 0 ? 1 : 0));
+    SSOut so{};
+    so.xT = w.xT;
+    so.partials = w.partials;
+    so.lml_prefix = w.lml_prefix;
+    so.lml_out = reinterpret_cast<double*>(w.resblk + 1);
+    so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
+    const SSShard sh{1, rank, world, xchg_out, nullptr, w.sq};
+    TGP_TRY(dispatch_ss_main<D>(h, false, false, false, w.cst, dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh));
+    st->active = true; st->D = D; st->rank = rank; st->world = world; st->T = T; st->dy = dy;
+    return TGP_OK;
+}
+
+template <int D>
+int shard_phase2(tgp_ctx* h, tgp_shard_state* st, const double* xchg_all, double* lml_partial_dev) {
+    SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(st->work);
+    SSOut so{};
+    so.xT = w.xT;
+    so.partials = w.partials;
+    so.lml_prefix = w.lml_prefix;
+    so.lml_out = reinterpret_cast<double*>(w.resblk + 1);
+    so.lml_user = lml_partial_dev;
+    so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
+    const SSShard sh{2, st->rank, st->world, nullptr, xchg_all, w.sq};
+    TGP_TRY(dispatch_ss_main<D>(h, false, false, false, w.cst, st->dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh));
+    st->active = false;
     return TGP_OK;
 }
 

@@ -7,6 +7,10 @@ D = 3) over NCCL/NVLink; every rank folds the elements of the ranks before it in
 (tgp_shard_prefix) to obtain the filtering distribution entering its shard; phase 2 is the ordinary
 tgp_logpdf on the shard from that state; the partial log-likelihoods are summed with one all-reduce.
 The reference has no analogue (single-threaded); host logic only here — arithmetic is in the library.
+
+Time-invariant models (RegularSpacing + homoscedastic noise) take the steady-state route instead: the exchange is one
+affine record (Phi, Z) of D*D + D doubles per rank, produced and consumed on the device, so a step is
+[tgp_shard_phase1] -> all_gather -> [tgp_shard_phase2] -> all_reduce on ONE stream with no host round trip in between.
 """
 from __future__ import annotations
 
@@ -47,10 +51,22 @@ class ShardedLogpdf:
         self.P0 = np.array(marshalled.keep[-1])
         self.desc2 = type(marshalled.desc).from_buffer_copy(marshalled.desc)   # ctypes structs with pointers cannot be copy.copy'd
         self._ybuf = None
+        d = marshalled.desc
+        self.time_invariant = not (d.sA or d.sa or d.sQ or d.sH or d.sh or d.sR) and d.ordering == 0 and d.T >= 65536
+        XS = self.D * self.D + self.D
+        self.rec = torch.zeros(XS, dtype=torch.float64, device=device)
+        self.recs = torch.zeros(world * XS, dtype=torch.float64, device=device)
 
     def logpdf(self, y_dev, lml_out_dev):
         """y_dev: this rank's shard, resident on its GPU. lml_out_dev: 1-element CUDA tensor (all ranks get the total)."""
         h, dist = self.h, self.dist
+        if self.time_invariant:
+            h.shard_phase1(self.mm.desc, y_dev, self.rank, self.world, self.rec)
+            dist.all_gather_into_tensor(self.recs, self.rec)
+            h.shard_phase2(self.recs, self.part)
+            dist.all_reduce(self.part)
+            lml_out_dev.copy_(self.part)
+            return
         h.shard_reduce(self.mm.desc, y_dev, self.elem)
         dist.all_gather_into_tensor(self.all, self.elem)
         elems = self.all.cpu().numpy().reshape(self.world, self.ES)

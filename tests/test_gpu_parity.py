@@ -282,3 +282,42 @@ def test_steady_state_fallback_when_not_converged(pkg, handle):
     lml = pkg.lgssm.logpdf(fx.build_lgssm(), y, handle)
     assert handle.counters()["launches"] - c0 > 2   # steady attempt + general rerun
     assert abs(lml - ref["lml"]) <= LML_RTOL * abs(ref["lml"])
+
+
+@pytest.mark.parametrize("world,T", [(2, 70_000), (3, 65_536 + 777), (4, 131_072), (8, 100_001)])
+def test_steady_sharded_phases_single_device(pkg, world, T):
+    """The two-phase steady-state sharded logpdf (tgp_shard_phase1 / tgp_shard_phase2) with every 'rank' played by its
+    own handle on cuda:0 and the all-gather done by hand: exercises the exact end-of-shard alignment (ragged last
+    tile) and the record fold; compared with the sequential C oracle on the whole series."""
+    import torch
+    dev = torch.device("cuda:0")
+    Ttot = T * world
+    mo = O.build_lgssm(O.Matern52(), O.RegularSpacing(0.0, 0.02, Ttot), 0.3, 0.4)
+    rng = np.random.default_rng(world * 1000 + T)
+    y = np.cos(np.arange(Ttot) * 0.001) + 0.4 + 0.5 * rng.standard_normal(Ttot)
+    ref = c_oracle.logpdf(c_oracle.Model.from_lgssm(mo), y)
+    fx = pkg.to_sde(pkg.GP(pkg.Matern52Kernel(), 0.4))(pkg.RegularSpacing(0.0, 0.02, T), 0.3)
+    mm = pkg.lgssm._Marshalled(fx.build_lgssm())
+    D = mm.D
+    XS = D * D + D
+    handles = [pkg.Handle(0) for _ in range(world)]
+    ys = [torch.from_numpy(np.ascontiguousarray(y[r * T:(r + 1) * T])).to(dev) for r in range(world)]
+    recs = torch.zeros(world * XS, dtype=torch.float64, device=dev)
+    for r in range(world):
+        handles[r].shard_phase1(mm.desc, ys[r], r, world, recs[r * XS:(r + 1) * XS])
+    parts = torch.zeros(world, dtype=torch.float64, device=dev)
+    for r in range(world):
+        handles[r].shard_phase2(recs, parts[r:r + 1])
+    torch.cuda.synchronize()
+    total = float(parts.sum().item())
+    assert abs(total - ref) <= LML_RTOL * abs(ref), (total, ref)
+    # the records chain to the sequential filter's mean at every shard boundary
+    ms = c_oracle.filter(c_oracle.Model.from_lgssm(mo), y, want_steps=False)["m"]
+    R = recs.cpu().numpy().reshape(world, XS)
+    x = np.zeros(D)
+    for r in range(world - 1):
+        Phi = R[r, :D * D].reshape(D, D).T
+        x = Phi @ x + R[r, D * D:]
+        np.testing.assert_allclose(x, ms[(r + 1) * T - 1], rtol=1e-6, atol=1e-8)
+    for h in handles:
+        h.close()
