@@ -161,7 +161,10 @@ int tgp_shard_prefix(tgp_handle h, int D, int n_elems, const double* elems /*hos
  * y must stay valid (and, if it is a host pointer, unchanged) between the two calls. */
 int tgp_shard_xchg_size(int D);                            /* D*D + D */
 int tgp_shard_phase1(tgp_handle h, const tgp_lgssm* shard, const double* y, int rank, int world, double* xchg_out);
-int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial);
+int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial);   /* returns WITHOUT synchronising */
+/* Waits for the handle's stream and returns the status of work that was enqueued without synchronisation
+ * (tgp_shard_phase2: TGP_ENOTPD / TGP_EUNSUPPORTED "not converged"). The next call on the handle does the same. */
+int tgp_synchronize(tgp_handle h);
 
 #ifdef __cplusplus
 }

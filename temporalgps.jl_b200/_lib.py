@@ -73,6 +73,7 @@ _SIGS = {
     "tgp_shard_xchg_size": (C.c_int, [C.c_int]),
     "tgp_shard_phase1": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tgp_shard_phase2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tgp_synchronize": (C.c_int, [C.c_void_p]),
     "tgp_shard_prefix": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
@@ -203,6 +204,9 @@ class Handle:
 
     def shard_phase1(self, desc, y, rank, world, xchg_out):
         self.check(lib().tgp_shard_phase1(self._h, C.byref(desc), ptr(y), int(rank), int(world), ptr(xchg_out)))
+
+    def synchronize(self):
+        self.check(lib().tgp_synchronize(self._h))
 
     def shard_phase2(self, xchg_all, lml_partial):
         self.check(lib().tgp_shard_phase2(self._h, ptr(xchg_all), ptr(lml_partial)))

@@ -41,10 +41,28 @@ int require_scalar_obs(tgp_ctx* h, const tgp_lgssm* m) {
     return TGP_OK;
 }
 
+// Collect the status of a call that returned without synchronising (tgp_shard_phase2).
+int resolve_deferred(tgp_ctx* h) {
+    if (!h->deferred_res) return TGP_OK;
+    const unsigned long long* res = h->deferred_res;
+    h->deferred_res = nullptr;
+    unsigned long long* perr = (unsigned long long*)h->pinned;
+    int* pflag = (int*)(h->pinned + 2);
+    TGP_CUDA(h, cudaMemcpyAsync(perr, res, 24, cudaMemcpyDeviceToHost, h->stream));
+    h->d2h += 24;
+    TGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (*perr != ~0ull) return fail(h, TGP_ENOTPD, "covariance not positive definite at time index %lld (0-based)", (long long)*perr);
+    if (*pflag == 0)
+        return fail(h, TGP_EUNSUPPORTED, "the filtering covariance did not converge within the transient budget on this shard; "
+                                         "use the general sharded path (tgp_shard_reduce / tgp_shard_prefix)");
+    return TGP_OK;
+}
+
 int begin_call(tgp_ctx* h) {
     h->err.clear();
     h->pending.clear();
     TGP_CUDA(h, cudaSetDevice(h->device));
+    TGP_TRY(resolve_deferred(h));
     TGP_CUDA(h, h->arena.reset());
     return TGP_OK;
 }
@@ -266,6 +284,14 @@ int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial) 
 }
 
 int tgp_shard_xchg_size(int D) { return D * D + D; }
+
+int tgp_synchronize(tgp_handle h) {
+    if (!h) return TGP_EINVAL;
+    TGP_CUDA(h, cudaSetDevice(h->device));
+    if (h->deferred_res) return resolve_deferred(h);
+    TGP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return TGP_OK;
+}
 
 int tgp_shard_prefix(tgp_handle h, int D, int n_elems, const double* elems, const double* m0, const double* P0, double* m_in,
                      double* P_in) {

@@ -88,6 +88,8 @@ struct tgp_ctx {
     const char* cur_name = nullptr;
     cudaEvent_t cur_t0 = nullptr;
     tgp_shard_state shard;
+    const unsigned long long* deferred_res = nullptr;   // result block {err, lml, converged} of an un-synchronised call
+    int64_t deferred_T = 0;
 };
 
 namespace tgp {

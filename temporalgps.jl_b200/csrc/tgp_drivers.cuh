@@ -379,14 +379,10 @@ int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double* lml_partial) {
     const int64_t T = h->shard.T;
     SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(h->shard.work);
     TGP_TRY(shard_phase2<D>(h, &h->shard, xchg_all, lml_partial));
-    FilterReq rq;
-    rq.err = w.resblk;
-    rq.packed_result = true;
-    bool converged = true;
-    TGP_TRY(end_call(h, rq.err, T, false, reinterpret_cast<const int*>(w.resblk + 2), &converged, &rq));
-    if (!converged)
-        return fail(h, TGP_EUNSUPPORTED, "the filtering covariance did not converge within the transient budget on this shard; "
-                                         "use the general sharded path (tgp_shard_reduce / tgp_shard_prefix)");
+    // no synchronisation here: the caller enqueues its all-reduce right behind this kernel; status (convergence,
+    // positive-definiteness) is collected by tgp_synchronize() or by the next call on this handle.
+    h->deferred_res = w.resblk;
+    h->deferred_T = T;
     return TGP_OK;
 }
 

@@ -63,9 +63,9 @@ class ShardedLogpdf:
         if self.time_invariant:
             h.shard_phase1(self.mm.desc, y_dev, self.rank, self.world, self.rec)
             dist.all_gather_into_tensor(self.recs, self.rec)
-            h.shard_phase2(self.recs, self.part)
-            dist.all_reduce(self.part)
-            lml_out_dev.copy_(self.part)
+            h.shard_phase2(self.recs, lml_out_dev)     # enqueued, not synchronised
+            dist.all_reduce(lml_out_dev)
+            h.synchronize()                             # status of the shard (convergence, positive-definiteness)
             return
         h.shard_reduce(self.mm.desc, y_dev, self.elem)
         dist.all_gather_into_tensor(self.all, self.elem)

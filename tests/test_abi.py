@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     txt = open(os.path.join(ROOT, "include", "tgp_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(tgp_[a-z_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(tgp_[a-z_0-9]+)\s*\(", txt)))
 
 
 def test_library_exports_every_declared_symbol(pkg):
