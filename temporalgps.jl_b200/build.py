@@ -20,12 +20,12 @@ BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtgpb200.so")
 
 # keep in step with TGP_FOR_EACH_D in csrc/tgp_dispatch.h
-TGP_DIMS = (1, 2, 3, 4, 5, 6)
+TGP_DIMS = (1, 2, 3, 4, 5, 6, 8, 10)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
-]
+] + os.environ.get("TGP_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

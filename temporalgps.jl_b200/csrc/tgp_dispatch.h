@@ -32,7 +32,7 @@ template <int D> int do_shard_prefix(int n, const double* elems, const double* m
     extern template int do_shard_prefix<Dv>(int, const double*, const double*, const double*, double*, double*);
 
 // The set of latent dimensions with kernel instantiations (keep in step with build.py's TGP_DIMS).
-#define TGP_FOR_EACH_D(X) X(1) X(2) X(3) X(4) X(5) X(6)
+#define TGP_FOR_EACH_D(X) X(1) X(2) X(3) X(4) X(5) X(6) X(8) X(10)
 TGP_FOR_EACH_D(TGP_DECL_D)
 
 }  // namespace tgp

@@ -175,8 +175,10 @@ int do_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* m_f, int6
         TGP_TRY(stage_out(h, P_f, D * D, s_P, m->T, &rq.P_f, &rq.s_P));
         bool handled = false;
         const int* flag = nullptr;
-        if (attempt == 0 && h->algo == TGP_ALGO_AUTO && m->ordering == TGP_FORWARD && time_invariant(*m))
-            TGP_TRY(filter_steady<D>(h, d, dy, rq, &handled, &flag));
+        if constexpr (D <= TGP_REG_D) {
+            if (attempt == 0 && h->algo == TGP_ALGO_AUTO && m->ordering == TGP_FORWARD && time_invariant(*m))
+                TGP_TRY(filter_steady<D>(h, d, dy, rq, &handled, &flag));
+        }
         if (!handled) TGP_TRY(filter_general<D>(h, d, dy, rq));
         bool converged = true;
         TGP_TRY(end_call(h, rq.err, err_T(d), m->ordering == TGP_REVERSE, flag, &converged, &rq));
@@ -366,24 +368,32 @@ int do_shard_phase1(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, i
     if (m->ordering != TGP_FORWARD || !time_invariant(*m))
         return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path runs Forward, time-invariant models (use tgp_shard_reduce otherwise)");
     if (!is_device_ptr(xchg_out)) return fail(h, TGP_EINVAL, "xchg_out must be a device pointer");
-    tgp_lgssm d;
-    const double* dy;
-    TGP_TRY(stage_model(h, m, y, &d, &dy));
-    return shard_phase1<D>(h, &h->shard, d, dy, rank, world, xchg_out);
+    if constexpr (D <= TGP_REG_D) {
+        tgp_lgssm d;
+        const double* dy;
+        TGP_TRY(stage_model(h, m, y, &d, &dy));
+        return shard_phase1<D>(h, &h->shard, d, dy, rank, world, xchg_out);
+    } else {
+        return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path is instantiated for D <= %d", TGP_REG_D);
+    }
 }
 
 template <int D>
 int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double* lml_partial) {
     if (!h->shard.active || h->shard.D != D) return fail(h, TGP_EINVAL, "tgp_shard_phase2 without a matching tgp_shard_phase1");
     if (!is_device_ptr(xchg_all) || !is_device_ptr(lml_partial)) return fail(h, TGP_EINVAL, "xchg_all and lml_partial must be device pointers");
-    const int64_t T = h->shard.T;
-    SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(h->shard.work);
-    TGP_TRY(shard_phase2<D>(h, &h->shard, xchg_all, lml_partial));
-    // no synchronisation here: the caller enqueues its all-reduce right behind this kernel; status (convergence,
-    // positive-definiteness) is collected by tgp_synchronize() or by the next call on this handle.
-    h->deferred_res = w.resblk;
-    h->deferred_T = T;
-    return TGP_OK;
+    if constexpr (D <= TGP_REG_D) {
+        const int64_t T = h->shard.T;
+        SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(h->shard.work);
+        TGP_TRY(shard_phase2<D>(h, &h->shard, xchg_all, lml_partial));
+        // no synchronisation here: the caller enqueues its all-reduce right behind this kernel; status (convergence,
+        // positive-definiteness) is collected by tgp_synchronize() or by the next call on this handle.
+        h->deferred_res = w.resblk;
+        h->deferred_T = T;
+        return TGP_OK;
+    } else {
+        return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path is instantiated for D <= %d", TGP_REG_D);
+    }
 }
 
 template <int D>

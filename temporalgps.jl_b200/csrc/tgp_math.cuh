@@ -23,8 +23,25 @@
 #define TGP_HD inline __attribute__((always_inline))
 #endif
 
+// Latent dimensions up to TGP_REG_D keep every small matrix in registers (loops fully unrolled); larger D fall back
+// to rolled loops over thread-local arrays (correct, slower: the warp-cooperative layout for large D is future work).
+#ifndef TGP_REG_D
+#define TGP_REG_D 6
+#endif
+// Each latent dimension is its own translation unit (tgp_inst.cu, -DTGP_D=<D>), so the choice is a plain macro.
+#if defined(TGP_D) && TGP_D > TGP_REG_D
+#if defined(TGP_ROLLED_PRAGMA1)
+#define TGP_UNROLL _Pragma("unroll 1")
+#else
+#define TGP_UNROLL   /* no pragma: the compiler's own heuristics (forcing "unroll 1" miscompiles apply_elem) */
+#endif
+#else
+#define TGP_UNROLL _Pragma("unroll")
+#endif
+
 namespace tgp {
 
+constexpr int kRegD = TGP_REG_D;
 constexpr double kLog2Pi = 1.8378770664093454835606594728112;
 constexpr double kInvertJitter = 1e-10;  // lgssm.jl:235
 
@@ -52,31 +69,31 @@ struct Sym {  // packed upper triangle, (i<=j) at j(j+1)/2 + i
 };
 
 template <int D> TGP_HD Vec<D> vzero() { Vec<D> r;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) r.v[i] = 0.0; return r; }
 template <int D> TGP_HD Sym<D> szero() { Sym<D> r;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < Sym<D>::N; ++i) r.v[i] = 0.0; return r; }
 template <int D> TGP_HD Mat<D> meye() { Mat<D> r;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i < D; ++i) r(i, j) = (i == j) ? 1.0 : 0.0;
     return r; }
 
 template <int D> TGP_HD double dot(const Vec<D>& a, const Vec<D>& b) {
     double s = 0.0;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) s = fma(a[i], b[i], s);
     return s;
 }
 // A x
 template <int D> TGP_HD Vec<D> matvec(const Mat<D>& A, const Vec<D>& x) {
     Vec<D> r;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) {
         double s = 0.0;
-#pragma unroll
+TGP_UNROLL
         for (int j = 0; j < D; ++j) s = fma(A(i, j), x[j], s);
         r[i] = s;
     }
@@ -85,10 +102,10 @@ template <int D> TGP_HD Vec<D> matvec(const Mat<D>& A, const Vec<D>& x) {
 // A' x
 template <int D> TGP_HD Vec<D> matTvec(const Mat<D>& A, const Vec<D>& x) {
     Vec<D> r;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j) {
         double s = 0.0;
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i < D; ++i) s = fma(A(i, j), x[i], s);
         r[j] = s;
     }
@@ -96,10 +113,10 @@ template <int D> TGP_HD Vec<D> matTvec(const Mat<D>& A, const Vec<D>& x) {
 }
 template <int D> TGP_HD Vec<D> symvec(const Sym<D>& S, const Vec<D>& x) {
     Vec<D> r;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) {
         double s = 0.0;
-#pragma unroll
+TGP_UNROLL
         for (int j = 0; j < D; ++j) s = fma(S(i, j), x[j], s);
         r[i] = s;
     }
@@ -107,12 +124,12 @@ template <int D> TGP_HD Vec<D> symvec(const Sym<D>& S, const Vec<D>& x) {
 }
 template <int D> TGP_HD Mat<D> matmul(const Mat<D>& A, const Mat<D>& B) {
     Mat<D> C;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i < D; ++i) {
             double s = 0.0;
-#pragma unroll
+TGP_UNROLL
             for (int k = 0; k < D; ++k) s = fma(A(i, k), B(k, j), s);
             C(i, j) = s;
         }
@@ -121,12 +138,12 @@ template <int D> TGP_HD Mat<D> matmul(const Mat<D>& A, const Mat<D>& B) {
 // A * S (S symmetric packed) -> full
 template <int D> TGP_HD Mat<D> mat_sym(const Mat<D>& A, const Sym<D>& S) {
     Mat<D> C;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i < D; ++i) {
             double s = 0.0;
-#pragma unroll
+TGP_UNROLL
             for (int k = 0; k < D; ++k) s = fma(A(i, k), S(k, j), s);
             C(i, j) = s;
         }
@@ -135,12 +152,12 @@ template <int D> TGP_HD Mat<D> mat_sym(const Mat<D>& A, const Sym<D>& S) {
 // S * A (S symmetric packed) -> full
 template <int D> TGP_HD Mat<D> sym_mat(const Sym<D>& S, const Mat<D>& A) {
     Mat<D> C;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i < D; ++i) {
             double s = 0.0;
-#pragma unroll
+TGP_UNROLL
             for (int k = 0; k < D; ++k) s = fma(S(i, k), A(k, j), s);
             C(i, j) = s;
         }
@@ -149,12 +166,12 @@ template <int D> TGP_HD Mat<D> sym_mat(const Sym<D>& S, const Mat<D>& A) {
 // upper triangle of X * A' + C0 (result assumed symmetric)
 template <int D> TGP_HD Sym<D> mat_matT_sym(const Mat<D>& X, const Mat<D>& A, const Sym<D>& C0) {
     Sym<D> R;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i <= j; ++i) {
             double s = C0(i, j);
-#pragma unroll
+TGP_UNROLL
             for (int k = 0; k < D; ++k) s = fma(X(i, k), A(j, k), s);
             R(i, j) = s;
         }
@@ -163,12 +180,12 @@ template <int D> TGP_HD Sym<D> mat_matT_sym(const Mat<D>& X, const Mat<D>& A, co
 // upper triangle of X' * Y + C0 (result assumed symmetric)
 template <int D> TGP_HD Sym<D> matT_mat_sym(const Mat<D>& X, const Mat<D>& Y, const Sym<D>& C0) {
     Sym<D> R;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i <= j; ++i) {
             double s = C0(i, j);
-#pragma unroll
+TGP_UNROLL
             for (int k = 0; k < D; ++k) s = fma(X(k, i), Y(k, j), s);
             R(i, j) = s;
         }
@@ -186,7 +203,7 @@ template <int D> TGP_HD Sym<D> congruence(const Mat<D>& A, const Sym<D>& S, cons
 template <int D>
 TGP_HD void predict(Vec<D>& m, Sym<D>& P, const Mat<D>& A, const Vec<D>& a, const Sym<D>& Q) {
     Vec<D> mn = matvec(A, m);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) mn[i] += a[i];
     P = congruence(A, P, Q);
     m = mn;
@@ -202,13 +219,13 @@ TGP_HD double update_scalar(Vec<D>& m, Sym<D>& P, const Vec<D>& H, double h, dou
     const double is = 1.0 / sqrt(S);
     const double alpha = (y - (dot(H, m) + h)) * is;
     Vec<D> B;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) B[i] = V[i] * is;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) m[i] = fma(B[i], alpha, m[i]);
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i <= j; ++i) P(i, j) = fma(-B[i], B[j], P(i, j));
     *quad = alpha * alpha;
     return S;
@@ -268,15 +285,15 @@ TGP_HD StepConst<D> make_step_const(const Mat<D>& A, const Vec<D>& a, const Sym<
     sc.S = dot(qh, H) + R;
     sc.is = 1.0 / sqrt(sc.S);
     Vec<D> ath = matTvec(A, H);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) { sc.kq[i] = qh[i] * sc.is; sc.u[i] = ath[i] * sc.is; sc.a[i] = a[i]; }
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i < D; ++i) sc.Ak(i, j) = fma(-sc.kq[i], sc.u[j], A(i, j));
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i <= j; ++i) sc.Ck(i, j) = fma(-sc.kq[i], sc.kq[j], Q(i, j));
     sc.c0 = dot(H, a) + h;
     return sc;
@@ -292,40 +309,40 @@ TGP_HD void fold_step(Elem<D>& E, const StepConst<D>& sc, double y) {
     const Vec<D> v = matTvec(E.A, sc.u);  // A_i' u
     // M A_i = A_i - w v'/d
     Mat<D> MA;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j) {
         const double vj = v[j] * id;
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i < D; ++i) MA(i, j) = fma(-w[i], vj, E.A(i, j));
     }
     // t = b_i + C_i eta_k = b_i + w r;  M t = t - w (u.t)/d
     Vec<D> t;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) t[i] = fma(w[i], r, E.b[i]);
     const double ut = dot(sc.u, t) * id;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) t[i] = fma(-w[i], ut, t[i]);
     // eta, J use the *old* b_i, A_i (through v)
     const double s = (r - dot(sc.u, E.b)) * id;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) E.eta[i] = fma(v[i], s, E.eta[i]);
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j) {
         const double vj = v[j] * id;
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i <= j; ++i) E.J(i, j) = fma(v[i], vj, E.J(i, j));
     }
     // X = M C_i = C_i - w w'/d
     Sym<D> X;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j) {
         const double wj = w[j] * id;
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i <= j; ++i) X(i, j) = fma(-w[i], wj, E.C(i, j));
     }
     E.A = matmul(sc.Ak, MA);
     Vec<D> bn = matvec(sc.Ak, t);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) E.b[i] = bn[i] + fma(sc.kq[i], r, sc.a[i]);
     E.C = congruence(sc.Ak, X, sc.Ck);
 }
@@ -336,28 +353,28 @@ TGP_HD void fold_step(Elem<D>& E, const StepConst<D>& sc, double y) {
 template <int D, int NR>
 TGP_HD void solve_I_plus_CJ(const Sym<D>& C, const Sym<D>& J, double (&rhs)[D][NR]) {
     double a[D][D];
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i)
-#pragma unroll
+TGP_UNROLL
         for (int j = 0; j < D; ++j) {
             double s = (i == j) ? 1.0 : 0.0;
-#pragma unroll
+TGP_UNROLL
             for (int k = 0; k < D; ++k) s = fma(C(i, k), J(k, j), s);
             a[i][j] = s;
         }
-#pragma unroll
+TGP_UNROLL
     for (int k = 0; k < D; ++k) {
         // bring the largest |a[r][k]|, r >= k, to row k by a bubble pass of predicated swaps
-#pragma unroll
+TGP_UNROLL
         for (int r = k + 1; r < D; ++r) {
             const bool sw = fabs(a[r][k]) > fabs(a[k][k]);
-#pragma unroll
+TGP_UNROLL
             for (int j = k; j < D; ++j) {
                 const double x = a[k][j], z = a[r][j];
                 a[k][j] = sw ? z : x;
                 a[r][j] = sw ? x : z;
             }
-#pragma unroll
+TGP_UNROLL
             for (int j = 0; j < NR; ++j) {
                 const double x = rhs[k][j], z = rhs[r][j];
                 rhs[k][j] = sw ? z : x;
@@ -365,17 +382,17 @@ TGP_HD void solve_I_plus_CJ(const Sym<D>& C, const Sym<D>& J, double (&rhs)[D][N
             }
         }
         const double ip = 1.0 / a[k][k];
-#pragma unroll
+TGP_UNROLL
         for (int j = k + 1; j < D; ++j) a[k][j] *= ip;
-#pragma unroll
+TGP_UNROLL
         for (int j = 0; j < NR; ++j) rhs[k][j] *= ip;
-#pragma unroll
+TGP_UNROLL
         for (int r = 0; r < D; ++r) {
             if (r == k) continue;
             const double f = a[r][k];
-#pragma unroll
+TGP_UNROLL
             for (int j = k + 1; j < D; ++j) a[r][j] = fma(-f, a[k][j], a[r][j]);
-#pragma unroll
+TGP_UNROLL
             for (int j = 0; j < NR; ++j) rhs[r][j] = fma(-f, rhs[k][j], rhs[r][j]);
         }
     }
@@ -387,39 +404,39 @@ TGP_HD Elem<D> combine(const Elem<D>& Ei, const Elem<D>& Ej) {
     // RHS columns: [A_i (D) | b_i + C_i eta_j (1) | C_i (D)]
     double rhs[D][2 * D + 1];
     const Vec<D> ce = symvec(Ei.C, Ej.eta);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) {
-#pragma unroll
+TGP_UNROLL
         for (int j = 0; j < D; ++j) { rhs[i][j] = Ei.A(i, j); rhs[i][D + 1 + j] = Ei.C(i, j); }
         rhs[i][D] = Ei.b[i] + ce[i];
     }
     solve_I_plus_CJ<D, 2 * D + 1>(Ei.C, Ej.J, rhs);
     Mat<D> XA, XC;
     Vec<D> xt;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) {
-#pragma unroll
+TGP_UNROLL
         for (int j = 0; j < D; ++j) { XA(i, j) = rhs[i][j]; XC(i, j) = rhs[i][D + 1 + j]; }
         xt[i] = rhs[i][D];
     }
     Elem<D> E;
     E.A = matmul(Ej.A, XA);
     Vec<D> bn = matvec(Ej.A, xt);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) E.b[i] = bn[i] + Ej.b[i];
     // C = A_j (M C_i) A_j' + C_j ; M C_i is symmetric in exact arithmetic -> symmetrise
     Sym<D> XCs;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i <= j; ++i) XCs(i, j) = 0.5 * (XC(i, j) + XC(j, i));
     E.C = congruence(Ej.A, XCs, Ej.C);
     // eta = (M A_i)' (eta_j - J_j b_i) + eta_i ;  J = (M A_i)' (J_j A_i) + J_i
     Vec<D> z = symvec(Ej.J, Ei.b);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) z[i] = Ej.eta[i] - z[i];
     Vec<D> en = matTvec(XA, z);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) E.eta[i] = en[i] + Ei.eta[i];
     E.J = matT_mat_sym(XA, sym_mat(Ej.J, Ei.A), Ei.J);
     return E;
@@ -431,23 +448,23 @@ template <int D>
 TGP_HD void apply_elem(const Elem<D>& E, Vec<D>& m, Sym<D>& P) {
     double rhs[D][D + 1];
     const Vec<D> pe = symvec(P, E.eta);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) {
-#pragma unroll
+TGP_UNROLL
         for (int j = 0; j < D; ++j) rhs[i][1 + j] = P(i, j);
         rhs[i][0] = m[i] + pe[i];
     }
     solve_I_plus_CJ<D, D + 1>(P, E.J, rhs);
     Vec<D> xt;
     Sym<D> XP;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) xt[i] = rhs[i][0];
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i <= j; ++i) XP(i, j) = 0.5 * (rhs[i][1 + j] + rhs[j][1 + i]);
     Vec<D> mn = matvec(E.A, xt);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) m[i] = mn[i] + E.b[i];
     P = congruence(E.A, XP, E.C);
 }
@@ -471,14 +488,14 @@ template <int D> TGP_HD Aff<D> aff_combine(const Aff<D>& earlier, const Aff<D>& 
     Aff<D> e;
     e.A = matmul(later.A, earlier.A);
     Vec<D> t = matvec(later.A, earlier.b);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) e.b[i] = t[i] + later.b[i];
     e.C = congruence(later.A, earlier.C, later.C);
     return e;
 }
 template <int D> TGP_HD void aff_apply(const Aff<D>& e, Vec<D>& m, Sym<D>& P) {
     Vec<D> t = matvec(e.A, m);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) m[i] = t[i] + e.b[i];
     P = congruence(e.A, P, e.C);
 }
@@ -487,19 +504,19 @@ template <int D> TGP_HD void aff_apply(const Aff<D>& e, Vec<D>& m, Sym<D>& P) {
 // Returns false if a pivot is not positive.
 template <int D> TGP_HD bool chol_upper(const Sym<D>& S, Sym<D>& U) {
     bool ok = true;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j) {
         double d = S(j, j);
-#pragma unroll
+TGP_UNROLL
         for (int k = 0; k < j; ++k) d = fma(-U(k, j), U(k, j), d);
         ok = ok && (d > 0.0);
         const double sd = sqrt(d);
         const double isd = 1.0 / sd;
         U(j, j) = sd;
-#pragma unroll
+TGP_UNROLL
         for (int i = j + 1; i < D; ++i) {
             double s = S(j, i);
-#pragma unroll
+TGP_UNROLL
             for (int k = 0; k < j; ++k) s = fma(-U(k, j), U(k, i), s);
             U(j, i) = s * isd;
         }
@@ -513,43 +530,43 @@ template <int D>
 TGP_HD bool invert_dynamics(const Vec<D>& mf, const Sym<D>& Pf, const Vec<D>& mp, const Sym<D>& Pp,
                             const Mat<D>& A, Aff<D>& out) {
     Sym<D> Pj = Pp, U;
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) Pj(i, i) += kInvertJitter;
     const bool ok = chol_upper(Pj, U);
     // X = A Pf (D x D); B = U' \ X (forward substitution per column); Gt = U \ B
     Mat<D> X = mat_sym(A, Pf), B, Gt;
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i < D; ++i) {
             double s = X(i, j);
-#pragma unroll
+TGP_UNROLL
             for (int k = 0; k < i; ++k) s = fma(-U(k, i), B(k, j), s);
             B(i, j) = s / U(i, i);
         }
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = D - 1; i >= 0; --i) {
             double s = B(i, j);
-#pragma unroll
+TGP_UNROLL
             for (int k = i + 1; k < D; ++k) s = fma(-U(i, k), Gt(k, j), s);
             Gt(i, j) = s / U(i, i);
         }
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i < D; ++i) out.A(i, j) = Gt(j, i);
     Vec<D> gm = matvec(out.A, mp);
-#pragma unroll
+TGP_UNROLL
     for (int i = 0; i < D; ++i) out.b[i] = mf[i] - gm[i];
     // Sigma = Pf - B'B  (B == U Gt up to rounding; the reference recomputes U*Gt, lgssm.jl:237)
-#pragma unroll
+TGP_UNROLL
     for (int j = 0; j < D; ++j)
-#pragma unroll
+TGP_UNROLL
         for (int i = 0; i <= j; ++i) {
             double s = Pf(i, j);
-#pragma unroll
+TGP_UNROLL
             for (int k = 0; k < D; ++k) s = fma(-B(k, i), B(k, j), s);
             out.C(i, j) = s;
         }

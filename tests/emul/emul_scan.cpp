@@ -108,6 +108,8 @@ extern "C" int emul_filter_scan(const tgp_lgssm* md, const double* y, int L, int
         case 3: return filter_scan<3>(md, y, L, W, lml_steps, m_f, P_f);
         case 4: return filter_scan<4>(md, y, L, W, lml_steps, m_f, P_f);
         case 6: return filter_scan<6>(md, y, L, W, lml_steps, m_f, P_f);
+        case 8: return filter_scan<8>(md, y, L, W, lml_steps, m_f, P_f);
+        case 10: return filter_scan<10>(md, y, L, W, lml_steps, m_f, P_f);
         default: return TGP_EUNSUPPORTED;
     }
 }
@@ -119,6 +121,8 @@ extern "C" int emul_smooth_scan(const tgp_lgssm* md, const double* m_f, const do
         case 3: return smooth_scan<3>(md, m_f, P_f, Rn, sRn, L, mean, var);
         case 4: return smooth_scan<4>(md, m_f, P_f, Rn, sRn, L, mean, var);
         case 6: return smooth_scan<6>(md, m_f, P_f, Rn, sRn, L, mean, var);
+        case 8: return smooth_scan<8>(md, m_f, P_f, Rn, sRn, L, mean, var);
+        case 10: return smooth_scan<10>(md, m_f, P_f, Rn, sRn, L, mean, var);
         default: return TGP_EUNSUPPORTED;
     }
 }

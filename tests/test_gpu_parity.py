@@ -322,3 +322,41 @@ def test_steady_sharded_phases_single_device(pkg, world, T):
         np.testing.assert_allclose(x, ms[(r + 1) * T - 1], rtol=1e-6, atol=1e-8)
     for h in handles:
         h.close()
+
+
+@pytest.mark.parametrize("ordering", ["forward", "reverse"])
+@pytest.mark.parametrize("D", [5, 6, 8, 10])
+def test_filter_larger_state_dims(pkg, handle, D, ordering):
+    """D = 8 and 10 run the rolled-loop instantiations (state in thread-local memory)."""
+    rng = np.random.default_rng(D)
+    m = random_lgssm(rng, 700, D, ordering, True)
+    y = sample_y(rng, m)
+    _check_filter(pkg, handle, m, y)
+
+
+def cfg3_kernels(pkg):
+    """BASELINE config 3: D = 10 sum  Matern32 + 0.7 Matern52 + 0.5 Matern52∘ST(0.5) + 0.3 Matern32∘ST(2.0)
+    (the reference has no RQ kernel; this is a reference-expressible stand-in of the same state dimension)."""
+    TK = pkg.gp.TransformedKernel
+    kp = (1.0 * pkg.Matern32Kernel() + 0.7 * pkg.Matern52Kernel() + 0.5 * TK(pkg.Matern52Kernel(), 0.5)
+          + 0.3 * TK(pkg.Matern32Kernel(), 2.0))
+    ko = 1.0 * O.Matern32() + 0.7 * O.Matern52() + 0.5 * O.Matern52().stretch(0.5) + 0.3 * O.Matern32().stretch(2.0)
+    return kp, ko
+
+
+@pytest.mark.parametrize("T", [3000, 50_000])
+def test_cfg3_sum_kernel_d10_posterior_marginals(pkg, handle, T):
+    kp, ko = cfg3_kernels(pkg)
+    to = O.RegularSpacing(0.0, 0.01, T)
+    mo = O.build_lgssm(ko, to, 0.1)
+    assert mo.D == 10
+    rng = np.random.default_rng(20261017 + 3)
+    y = np.sin(np.arange(T) * 0.004) + 0.3 * np.cos(np.arange(T) * 0.05) + 0.35 * rng.standard_normal(T)
+    cm = c_oracle.Model.from_lgssm(mo)
+    mu_o, var_o, lml_o = c_oracle.posterior_marginals(cm, y, 1e-2)
+    fx = pkg.to_sde(pkg.GP(kp))(pkg.RegularSpacing(0.0, 0.01, T), 0.1)
+    lml = pkg.gp.logpdf(fx, y)
+    assert abs(lml - lml_o) <= LML_RTOL * abs(lml_o)
+    mu, var = pkg.gp.marginals(pkg.gp.posterior(fx, y)(pkg.RegularSpacing(0.0, 0.01, T), 1e-2))
+    np.testing.assert_allclose(mu, mu_o, rtol=MV_RTOL, atol=1e-7)
+    np.testing.assert_allclose(var, var_o, rtol=MV_RTOL)
