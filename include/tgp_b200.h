@@ -45,7 +45,7 @@ extern "C" {
 #define TGP_R_DIAG   1       /* R is the M diagonal entries per step                           */
 #define TGP_R_DENSE  2       /* R is a dense M x M matrix per step                             */
 
-#define TGP_MAX_D 32         /* latent dimension supported by the small-state kernels          */
+#define TGP_MAX_D 4096       /* largest latent / observation dimension accepted (dense path)    */
 
 /* algorithm selection for tgp_set_option(h, TGP_OPT_ALGO, v) */
 #define TGP_OPT_ALGO         1
@@ -100,6 +100,9 @@ int         tgp_set_stream(tgp_handle h, void* cuda_stream);
  * tgp_logpdf   replaces logpdf(::LGSSM, y)            src/models/lgssm.jl:147-165
  *              (scan_emit + step_logpdf: predict LGC:46-52, posterior_and_lml LGC:247-257 /
  *              129-141). lml_per_step (T doubles, may be NULL) receives the emitted `lmls`.
+ *              Scalar observations with D in {1..6, 8, 10} run the parallel-in-time scan kernels; every other
+ *              shape (vector observations M > 1 = SmallOutputLGC, any R_kind; larger D) runs the dense
+ *              step-by-step path (tgp_dense.cu), y then being T x M (M fastest).
  */
 int tgp_logpdf(tgp_handle h, const tgp_lgssm* model, const double* y,
                double* lml_out, double* lml_per_step);

@@ -10,7 +10,8 @@ from . import _lib, gp, lgssm
 from ._lib import (DimensionMismatch, Handle, PosDefException, TGPError, default_handle, TGP_ALGO_AUTO, TGP_ALGO_SCAN)
 from .build import build
 from .gp import (GP, ApproxPeriodicKernel, ArrayStorage, B200Storage, ConstantKernel, FiniteLTISDE, Matern12Kernel,
-                 Matern32Kernel, Matern52Kernel, RegularSpacing, SArrayStorage, to_sde, with_lengthscale)
-from .lgssm import LGSSM, Fill, Forward, Gaussian, GaussMarkovModel, Reverse, ScalarEmissions
+                 Matern32Kernel, Matern52Kernel, RectilinearGrid, RegularSpacing, SArrayStorage, SEKernel, Separable, to_sde,
+                 with_lengthscale)
+from .lgssm import LGSSM, Fill, Forward, Gaussian, GaussMarkovModel, Reverse, ScalarEmissions, SmallOutputEmissions
 
 __all__ = [n for n in dir() if not n.startswith("_")]

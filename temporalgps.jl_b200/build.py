@@ -67,12 +67,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == tag:
         return LIB
     jobs = [(os.path.join(CSRC, "tgp_api.cu"), os.path.join(BUILD, "tgp_api.o"), [], os.path.join(BUILD, "tgp_api.log"))]
+    jobs.append((os.path.join(CSRC, "tgp_dense.cu"), os.path.join(BUILD, "tgp_dense.o"), [], os.path.join(BUILD, "tgp_dense.log")))
     for d in TGP_DIMS:
         jobs.append((os.path.join(CSRC, "tgp_inst.cu"), os.path.join(BUILD, f"tgp_inst_d{d}.o"), [f"-DTGP_D={d}"],
                      os.path.join(BUILD, f"tgp_inst_d{d}.log")))
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(_compile, jobs))
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart"]
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "lib64")
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart", "-lcublas", "-L" + cuda_lib, "-Xlinker", "-rpath=" + cuda_lib]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("link failed:\n" + p.stderr[-4000:])

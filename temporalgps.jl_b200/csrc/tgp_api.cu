@@ -19,6 +19,7 @@ int validate(tgp_ctx* h, const tgp_lgssm* m, bool need_y, const void* y) {
     if (!h) return TGP_EINVAL;
     if (!m) return fail(h, TGP_EINVAL, "model descriptor is NULL");
     if (m->D < 1 || m->D > TGP_MAX_D) return fail(h, TGP_EUNSUPPORTED, "latent dimension D=%d outside 1..%d", m->D, TGP_MAX_D);
+    if (m->M > TGP_MAX_D) return fail(h, TGP_EUNSUPPORTED, "observation dimension M=%d outside 1..%d", m->M, TGP_MAX_D);
     if (m->M < 1) return fail(h, TGP_EINVAL, "observation dimension M=%d must be >= 1", m->M);
     if (m->T < 1) return fail(h, TGP_EINVAL, "Dimension mismatch. length(prior) is %lld", (long long)m->T);
     if (m->ordering != TGP_FORWARD && m->ordering != TGP_REVERSE) return fail(h, TGP_EINVAL, "ordering must be TGP_FORWARD or TGP_REVERSE");
@@ -33,6 +34,18 @@ int validate(tgp_ctx* h, const tgp_lgssm* m, bool need_y, const void* y) {
         if (c.s != 0 && c.s < c.inner) return fail(h, TGP_EINVAL, "stride %s=%lld must be 0 or >= %lld", c.name, (long long)c.s, (long long)c.inner);
     if (need_y && !y) return fail(h, TGP_EINVAL, "Dimension mismatch. y is NULL but length(prior) is %lld", (long long)m->T);
     return TGP_OK;
+}
+
+// Shapes the small-state scan kernels are instantiated for; everything else takes the dense sequential path.
+bool scan_shape(const tgp_lgssm* m) {
+    if (m->M != 1 || m->R_kind != TGP_R_SCALAR) return false;
+    switch (m->D) {
+#define TGP_SHAPE_CASE(Dv) case Dv:
+        TGP_FOR_EACH_D(TGP_SHAPE_CASE)
+#undef TGP_SHAPE_CASE
+        return true;
+        default: return false;
+    }
 }
 
 int require_scalar_obs(tgp_ctx* h, const tgp_lgssm* m) {
@@ -201,8 +214,8 @@ int tgp_set_stream(tgp_handle h, void* cuda_stream) {
 
 int tgp_logpdf(tgp_handle h, const tgp_lgssm* model, const double* y, double* lml_out, double* lml_per_step) {
     TGP_TRY(validate(h, model, true, y));
-    TGP_TRY(require_scalar_obs(h, model));
     TGP_TRY(begin_call(h));
+    if (!scan_shape(model)) return dense_filter(h, model, y, lml_out, lml_per_step, nullptr, 0, nullptr, 0);
 #define CALL(Dv) do_filter<Dv>(h, model, y, nullptr, 0, nullptr, 0, lml_out, lml_per_step)
     TGP_DISPATCH_D(h, model->D)
 #undef CALL
@@ -211,10 +224,10 @@ int tgp_logpdf(tgp_handle h, const tgp_lgssm* model, const double* y, double* lm
 int tgp_filter(tgp_handle h, const tgp_lgssm* model, const double* y, double* m_f, int64_t s_m, double* P_f, int64_t s_P,
                double* lml_out) {
     TGP_TRY(validate(h, model, true, y));
-    TGP_TRY(require_scalar_obs(h, model));
     if (m_f && s_m < model->D) return fail(h, TGP_EINVAL, "s_m=%lld must be >= D", (long long)s_m);
     if (P_f && s_P < (int64_t)model->D * model->D) return fail(h, TGP_EINVAL, "s_P=%lld must be >= D*D", (long long)s_P);
     TGP_TRY(begin_call(h));
+    if (!scan_shape(model)) return dense_filter(h, model, y, lml_out, nullptr, m_f, s_m, P_f, s_P);
 #define CALL(Dv) do_filter<Dv>(h, model, y, m_f, s_m, P_f, s_P, lml_out, nullptr)
     TGP_DISPATCH_D(h, model->D)
 #undef CALL

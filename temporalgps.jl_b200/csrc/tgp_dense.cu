@@ -1,0 +1,280 @@
+// tgp_dense.cu — large-state / vector-observation path (SmallOutputLGC, LGC:129-141; BASELINE config 5: separable
+// space-time GPs, D = 768, M = 256). The state is too large for a register-resident scan element, and every step is
+// a genuine dense contraction, so the recursion runs step by step on ONE stream exactly as the reference executes it:
+//     predict   m <- A m + a;  P <- (A * Symmetric(P)) * A' + Q                                  (LGC:46-52)
+//     update    V = H P;  S = chol(Symmetric(V H' + R));  B = U' \ V;  alpha = U' \ (y - H m - h)
+//               lml = -(M log 2pi + logdet S + alpha'alpha)/2;  m += B' alpha;  P -= B'B          (LGC:129-141)
+// In this round the GEMM-shaped pieces are LIBRARY calls (cuBLAS D/Sgemm, symm, trsm): this is the measured baseline
+// that the hand-written tcgen05 step kernel of the next round has to beat; the Cholesky, the residual / likelihood
+// and the bookkeeping kernels are ours. For time-invariant models one step is captured into a CUDA graph (a device-side
+// step counter indexes y / outputs) and replayed T times, so the host issues one launch per step instead of ~14.
+#include <cublas_v2.h>
+
+#include <algorithm>
+
+#include "tgp_ctx.cuh"
+
+namespace tgp {
+
+#define TGP_CUBLAS(h, call)                                                                                        \
+    do {                                                                                                           \
+        cublasStatus_t s_ = (call);                                                                                \
+        if (s_ != CUBLAS_STATUS_SUCCESS) return fail(h, TGP_ECUDA, "%s failed: cuBLAS status %d (%s:%d)", #call, (int)s_, __FILE__, __LINE__); \
+    } while (0)
+
+constexpr double kLog2PiD = 1.8378770664093454835606594728112;
+
+// S (M x M, column-major, upper triangle valid) <- upper Cholesky factor U, S = U'U; lower triangle zeroed.
+// One CTA; right-looking, column by column in global / L2 memory (M <= a few hundred). fail[0] gets the step on error.
+__global__ void __launch_bounds__(1024) k_chol_upper(double* __restrict__ S, int M, const long long* __restrict__ step,
+                                                      unsigned long long* __restrict__ err) {
+    __shared__ double s_d;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = 0; j < M; ++j) {
+        if (tid == 0) {
+            const double d = S[j + (size_t)M * j];
+            if (!(d > 0.0)) { atomicMin(err, (unsigned long long)*step); s_d = 1.0; }
+            else s_d = sqrt(d);
+            S[j + (size_t)M * j] = s_d;
+        }
+        __syncthreads();
+        const double inv = 1.0 / s_d;
+        for (int i = j + 1 + tid; i < M; i += nt) S[j + (size_t)M * i] *= inv;   // row j of U
+        __syncthreads();
+        // trailing update of the upper triangle: S[r, c] -= U[j, r] U[j, c], j < r <= c
+        const int n = M - 1 - j;
+        for (long long e = tid; e < (long long)n * n; e += nt) {
+            const int r = j + 1 + (int)(e % n), c = j + 1 + (int)(e / n);
+            if (r <= c) S[r + (size_t)M * c] = fma(-S[j + (size_t)M * r], S[j + (size_t)M * c], S[r + (size_t)M * c]);
+        }
+        __syncthreads();
+    }
+    for (long long e = tid; e < (long long)M * M; e += nt) {
+        const int r = (int)(e % M), c = (int)(e / M);
+        if (r > c) S[e] = 0.0;
+    }
+}
+
+// S <- R_t expanded to a dense M x M matrix (R_kind: 0 scalar, 1 diag, 2 dense).
+__global__ void k_expand_R(double* __restrict__ S, int M, const double* __restrict__ R, long long sR, int R_kind,
+                           const long long* __restrict__ step) {
+    const double* Rt = R + *step * sR;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)M * M; e += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(e % M), c = (int)(e / M);
+        double v = 0.0;
+        if (R_kind == 2) v = Rt[e];
+        else if (r == c) v = R_kind == 1 ? Rt[r] : Rt[0];
+        S[e] = v;
+    }
+}
+
+// r <- y_t - h_t   (H m is subtracted by a gemv afterwards)
+__global__ void k_residual0(double* __restrict__ r, int M, const double* __restrict__ y, const double* __restrict__ hh, long long sh,
+                            const long long* __restrict__ step) {
+    const long long t = *step;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) r[i] = y[t * M + i] - hh[t * sh + i];
+}
+
+// lml_t = -(M log 2pi + 2 sum log U_ii + alpha'alpha)/2 ; accumulates the total; advances nothing.
+__global__ void __launch_bounds__(256) k_lml(const double* __restrict__ U, const double* __restrict__ alpha, int M, double* __restrict__ lml_steps,
+                                             double* __restrict__ lml_total, const long long* __restrict__ step) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < M; i += 256) s += 2.0 * log(U[i + (size_t)M * i]) + alpha[i] * alpha[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double l = -0.5 * (M * kLog2PiD + sh[0]);
+        if (lml_steps) lml_steps[*step] = l;
+        *lml_total += l;
+    }
+}
+
+// per-step transition vector: mt <- a_t (before the gemv accumulates A m into it); Pn <- Q_t
+__global__ void k_load_aQ(double* __restrict__ mt, double* __restrict__ Pn, int D, const double* __restrict__ a, long long sa,
+                          const double* __restrict__ Q, long long sQ, const long long* __restrict__ step) {
+    const long long t = *step;
+    const long long n = (long long)D * D;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n + D; e += (long long)gridDim.x * blockDim.x) {
+        if (e < n) Pn[e] = Q[t * sQ + e];
+        else mt[e - n] = a[t * sa + (e - n)];
+    }
+}
+
+__global__ void k_emit_state(const double* __restrict__ m, const double* __restrict__ P, int D, double* __restrict__ m_f, long long s_m,
+                             double* __restrict__ P_f, long long s_P, const long long* __restrict__ step) {
+    const long long t = *step;
+    const long long n = (long long)D * D;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n + D; e += (long long)gridDim.x * blockDim.x) {
+        if (e < n) { if (P_f) P_f[t * s_P + e] = P[e]; }
+        else if (m_f) m_f[t * s_m + (e - n)] = m[e - n];
+    }
+}
+
+__global__ void k_advance(long long* step, long long delta) { *step += delta; }
+
+struct DenseWs {
+    double *m, *mt, *P, *Pn, *T1, *V, *S, *B, *r;
+    long long* step;
+    double* lml;
+    unsigned long long* err;
+};
+
+static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const double* dy, const DenseWs& w, long long t /* host index or -1: use device counter */,
+                      bool graph_mode, double* lml_steps, double* m_f, int64_t s_m, double* P_f, int64_t s_P) {
+    const int D = d.D, M = d.M;
+    cudaStream_t st = h->stream;
+    const double one = 1.0, zero = 0.0, mone = -1.0;
+    // In graph mode the model is time-invariant (all strides 0), so parameter pointers are fixed and only y / outputs
+    // are indexed through the device counter; otherwise t is known on the host.
+    const long long tt = graph_mode ? 0 : t;
+    const double* A = d.A + tt * d.sA;
+    const double* H = d.H + tt * d.sH;
+    const bool rev = d.ordering == TGP_REVERSE;
+    const int nb = (int)std::min<long long>(((long long)D * D + D + 255) / 256, 1184);
+
+    auto predict = [&]() -> int {
+        TGP_K(h, "dense:k_load_aQ");
+        k_load_aQ<<<nb, 256, 0, st>>>(w.mt, w.Pn, D, d.a, d.sa, d.Q, d.sQ, w.step);
+        TGP_LAUNCH_CHECK(h);
+        TGP_CUBLAS(h, cublasDgemv(cb, CUBLAS_OP_N, D, D, &one, A, D, w.m, 1, &one, w.mt, 1));                 // mt = A m + a
+        TGP_CUBLAS(h, cublasDsymm(cb, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, D, D, &one, w.P, D, A, D, &zero, w.T1, D));  // A * Symmetric(P)
+        TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, D, D, D, &one, w.T1, D, A, D, &one, w.Pn, D)); // Pn = T1 A' + Q
+        TGP_CUDA(h, cudaMemcpyAsync(w.m, w.mt, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
+        TGP_CUDA(h, cudaMemcpyAsync(w.P, w.Pn, sizeof(double) * D * D, cudaMemcpyDeviceToDevice, st));
+        h->launches += 5;
+        return TGP_OK;
+    };
+    auto update = [&]() -> int {
+        TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_N, M, D, D, &one, H, M, w.P, D, &zero, w.V, M));   // V = H P
+        TGP_K(h, "dense:k_expand_R");
+        k_expand_R<<<std::min((M * M + 255) / 256, 1184), 256, 0, st>>>(w.S, M, d.R, d.sR, d.R_kind, w.step);
+        TGP_LAUNCH_CHECK(h);
+        TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, M, M, D, &one, w.V, M, H, M, &one, w.S, M));    // S = V H' + R
+        TGP_K(h, "dense:k_chol_upper");
+        k_chol_upper<<<1, 1024, 0, st>>>(w.S, M, w.step, w.err);
+        TGP_LAUNCH_CHECK(h);
+        TGP_CUDA(h, cudaMemcpyAsync(w.B, w.V, sizeof(double) * M * D, cudaMemcpyDeviceToDevice, st));
+        TGP_CUBLAS(h, cublasDtrsm(cb, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, D, &one, w.S, M, w.B, M));  // B = U' \ V
+        TGP_K(h, "dense:k_residual0");
+        k_residual0<<<(M + 255) / 256, 256, 0, st>>>(w.r, M, dy, d.h, d.sh, w.step);
+        TGP_LAUNCH_CHECK(h);
+        TGP_CUBLAS(h, cublasDgemv(cb, CUBLAS_OP_N, M, D, &mone, H, M, w.m, 1, &one, w.r, 1));                    // r = y - h - H m
+        TGP_CUBLAS(h, cublasDtrsv(cb, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, w.S, M, w.r, 1));   // alpha = U' \ r
+        TGP_K(h, "dense:k_lml");
+        k_lml<<<1, 256, 0, st>>>(w.S, w.r, M, lml_steps, w.lml, w.step);
+        TGP_LAUNCH_CHECK(h);
+        TGP_CUBLAS(h, cublasDgemv(cb, CUBLAS_OP_T, M, D, &one, w.B, M, w.r, 1, &one, w.m, 1));                    // m += B' alpha
+        TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, D, D, M, &mone, w.B, M, w.B, M, &one, w.P, D));  // P -= B'B
+        if (m_f || P_f) {
+            TGP_K(h, "dense:k_emit_state");
+            k_emit_state<<<nb, 256, 0, st>>>(w.m, w.P, D, m_f, s_m, P_f, s_P, w.step);
+            TGP_LAUNCH_CHECK(h);
+        }
+        h->launches += 8;
+        return TGP_OK;
+    };
+    if (!rev) { TGP_TRY(predict()); TGP_TRY(update()); }
+    else      { TGP_TRY(update()); TGP_TRY(predict()); }
+    TGP_K(h, "dense:k_advance");
+    k_advance<<<1, 1, 0, st>>>(w.step, rev ? -1 : 1);
+    TGP_LAUNCH_CHECK(h);
+    return TGP_OK;
+}
+
+// Entry point used by tgp_logpdf / tgp_filter for shapes outside the small-state scan kernels.
+int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out, double* lml_steps_user, double* m_f_user, int64_t s_m,
+                 double* P_f_user, int64_t s_P) {
+    const int D = m->D, M = m->M;
+    const int64_t T = m->T;
+    cudaStream_t st = h->stream;
+    static cublasHandle_t cb = nullptr;
+    if (!cb) TGP_CUBLAS(h, cublasCreate(&cb));
+    TGP_CUBLAS(h, cublasSetStream(cb, st));
+    TGP_CUBLAS(h, cublasSetPointerMode(cb, CUBLAS_POINTER_MODE_HOST));
+    TGP_CUBLAS(h, cublasSetMathMode(cb, CUBLAS_PEDANTIC_MATH));   // plain FP64: no down-conversion anywhere
+
+    // stage the model
+    tgp_lgssm d = *m;
+    const size_t rin = m->R_kind == TGP_R_SCALAR ? 1 : (m->R_kind == TGP_R_DIAG ? (size_t)M : (size_t)M * M);
+    TGP_TRY(stage_steps(h, m->A, m->sA, T, (size_t)D * D, &d.A));
+    TGP_TRY(stage_steps(h, m->a, m->sa, T, D, &d.a));
+    TGP_TRY(stage_steps(h, m->Q, m->sQ, T, (size_t)D * D, &d.Q));
+    TGP_TRY(stage_steps(h, m->H, m->sH, T, (size_t)M * D, &d.H));
+    TGP_TRY(stage_steps(h, m->h, m->sh, T, M, &d.h));
+    TGP_TRY(stage_steps(h, m->R, m->sR, T, rin, &d.R));
+    TGP_TRY(stage_in(h, m->m0, D, &d.m0));
+    TGP_TRY(stage_in(h, m->P0, (size_t)D * D, &d.P0));
+    const double* dy;
+    TGP_TRY(stage_in(h, y, (size_t)T * M, &dy));
+    double *lml_steps, *m_f, *P_f;
+    int64_t ds, dsm, dsP;
+    TGP_TRY(stage_out(h, lml_steps_user, 1, 1, T, &lml_steps, &ds));
+    TGP_TRY(stage_out(h, m_f_user, D, s_m, T, &m_f, &dsm));
+    TGP_TRY(stage_out(h, P_f_user, (size_t)D * D, s_P, T, &P_f, &dsP));
+
+    DenseWs w;
+    TGP_TRY(dalloc(h, D, &w.m));
+    TGP_TRY(dalloc(h, D, &w.mt));
+    TGP_TRY(dalloc(h, (size_t)D * D, &w.P));
+    TGP_TRY(dalloc(h, (size_t)D * D, &w.Pn));
+    TGP_TRY(dalloc(h, (size_t)D * D, &w.T1));
+    TGP_TRY(dalloc(h, (size_t)M * D, &w.V));
+    TGP_TRY(dalloc(h, (size_t)M * M, &w.S));
+    TGP_TRY(dalloc(h, (size_t)M * D, &w.B));
+    TGP_TRY(dalloc(h, M, &w.r));
+    TGP_TRY(dalloc(h, 1, &w.step));
+    TGP_TRY(dalloc(h, 1, &w.lml));
+    TGP_TRY(dalloc(h, 1, &w.err));
+    void* cbws;
+    const size_t cbws_bytes = size_t(32) << 20;
+    TGP_TRY(dalloc(h, cbws_bytes / 8, (double**)&cbws));
+    TGP_CUBLAS(h, cublasSetWorkspace(cb, cbws, cbws_bytes));
+    TGP_CUDA(h, cudaMemcpyAsync(w.m, d.m0, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
+    TGP_CUDA(h, cudaMemcpyAsync(w.P, d.P0, sizeof(double) * D * D, cudaMemcpyDeviceToDevice, st));
+    TGP_CUDA(h, cudaMemsetAsync(w.lml, 0, sizeof(double), st));
+    TGP_CUDA(h, cudaMemsetAsync(w.err, 0xFF, sizeof(unsigned long long), st));
+    const bool rev = m->ordering == TGP_REVERSE;
+    const long long t0 = rev ? T - 1 : 0;
+    TGP_CUDA(h, cudaMemcpyAsync(w.step, &t0, sizeof(long long), cudaMemcpyHostToDevice, st));
+    TGP_CUDA(h, cudaStreamSynchronize(st));   // t0 is a stack variable
+
+    const bool ti = !(m->sA | m->sa | m->sQ | m->sH | m->sh | m->sR);
+    if (ti && T >= 8 && !h->timing) {
+        // capture ONE step, replay it T times
+        cudaGraph_t graph;
+        cudaGraphExec_t exec;
+        TGP_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = dense_step(h, cb, d, dy, w, -1, true, lml_steps, m_f, dsm, P_f, dsP);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc != TGP_OK) return rc;
+        TGP_CUDA(h, ce);
+        TGP_CUDA(h, cudaGraphInstantiate(&exec, graph, 0));
+        for (int64_t t = 0; t < T; ++t) TGP_CUDA(h, cudaGraphLaunch(exec, st));
+        TGP_CUDA(h, cudaStreamSynchronize(st));
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+    } else {
+        // time-varying parameters: pointers depend on t, issue the step's launches directly. The custom kernels index
+        // through the device counter, the cuBLAS calls through host-computed pointers.
+        for (int64_t n = 0; n < T; ++n) {
+            const long long t = rev ? T - 1 - n : n;
+            TGP_TRY(dense_step(h, cb, d, dy, w, t, false, lml_steps, m_f, dsm, P_f, dsP));
+        }
+    }
+    // results
+    unsigned long long* perr = (unsigned long long*)h->pinned;
+    TGP_CUDA(h, cudaMemcpyAsync(perr, w.err, 8, cudaMemcpyDeviceToHost, st));
+    h->d2h += 8;
+    TGP_TRY(deliver_scalar(h, w.lml, lml_out));
+    TGP_TRY(flush_outputs(h));
+    TGP_CUDA(h, cudaStreamSynchronize(st));
+    if (*perr != ~0ull) return fail(h, TGP_ENOTPD, "innovation covariance not positive definite at time index %lld (0-based)", (long long)*perr);
+    return TGP_OK;
+}
+
+}  // namespace tgp

@@ -18,6 +18,10 @@ template <int D> int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double*
 template <int D> int do_shard_prefix(int n, const double* elems, const double* m0, const double* P0, double* m_in,
                                      double* P_in);
 
+// Large-state / vector-observation path (tgp_dense.cu): any D, M; sequential in time.
+int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out, double* lml_steps, double* m_f, int64_t s_m,
+                 double* P_f, int64_t s_P);
+
 #define TGP_DECL_D(Dv)                                                                                               \
     extern template int do_filter<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, double*, int64_t, double*, int64_t, \
                                       double*, double*);                                                             \

@@ -16,7 +16,7 @@ from scipy.linalg import expm
 from scipy.special import ive
 
 from . import lgssm as L
-from .lgssm import Fill, Forward, Gaussian, GaussMarkovModel, LGSSM, ScalarEmissions
+from .lgssm import Fill, Forward, Gaussian, GaussMarkovModel, LGSSM, ScalarEmissions, SmallOutputEmissions
 
 
 # ---- storage tags (storage_types.jl) -------------------------------------------------------------
@@ -228,6 +228,63 @@ def _dense(v, T):
     return np.asarray(v)
 
 
+# ---- separable space-time kernels on rectilinear grids (src/space_time/) -------------------------------
+class SEKernel(Kernel):
+    """exp(-tau^2 / 2): spatial factor only (no SDE form)."""
+    def matrix(self, r):
+        r = np.asarray(r, dtype=np.float64)
+        return np.exp(-0.5 * (r[:, None] - r[None, :]) ** 2)
+
+
+@dataclass
+class Separable(Kernel):
+    """separable_kernel.jl:9 — k((r, t), (r', t')) = space(r, r') * time(t, t')."""
+    space: Kernel
+    time: Kernel
+
+
+@dataclass
+class RectilinearGrid:
+    """rectilinear_grid.jl:11 — xl (space) varies fastest, xr (time) slowest."""
+    xl: object
+    xr: object
+
+    def __len__(self):
+        return len(self.xl) * len(self.xr)
+
+
+def _space_matrix(k, r):
+    if hasattr(k, "matrix"):
+        return k.matrix(r)
+    if isinstance(k, ScaledKernel):
+        return k.s2 * _space_matrix(k.kernel, r)
+    if isinstance(k, TransformedKernel):
+        return _space_matrix(k.kernel, k.s * np.asarray(r, dtype=np.float64))
+    raise TypeError(f"no kernel matrix for spatial kernel {k!r}")
+
+
+def lgssm_components_separable(k: Separable, x: RectilinearGrid):
+    """lgssm_components(k::Separable, x::SpaceTimeGrid, storage) — to_gauss_markov.jl:1-24: dense Kronecker assembly,
+    A = I (x) A_t, Q = (K_r + 1e-12 I) (x) Q_t, H = I (x) H_t, x0.P = K_r (x) P_t."""
+    r = np.asarray(x.xl, dtype=np.float64)
+    Nr = len(r)
+    Kr = _space_matrix(k.space, r)
+    As_t, as_t, Qs_t, Hs_t, hs_t, x0_t = lgssm_components(k.time, x.xr)
+    T = len(x.xr)
+    I = np.eye(Nr)
+
+    def lift(v, f):
+        return Fill(f(v.value), T) if isinstance(v, Fill) else np.stack([f(m) for m in np.asarray(v)])
+
+    As = lift(As_t, lambda A: np.kron(I, A))
+    as_ = lift(as_t, lambda a: np.tile(a, Nr))
+    Qs = lift(Qs_t, lambda Q: np.kron(Kr + 1e-12 * I, Q))
+    Hs = lift(Hs_t, lambda H: np.kron(I, np.atleast_2d(H)))
+    hs = lift(hs_t, lambda h: np.full(Nr, float(h)))
+    x0 = Gaussian(np.tile(x0_t.m, Nr), np.kron(Kr, x0_t.P))
+    return As, as_, Qs, Hs, hs, x0
+
+
 # ---- GP objects (AbstractGPs surface) ------------------------------------------------------------
 @dataclass
 class GP:
@@ -277,6 +334,16 @@ def _noise_to_time_form(x, noise):
 
 def build_lgssm(f: LTISDE, x, noise) -> LGSSM:
     """build_lgssm — lti_sde.jl:71-80 (+ mean handling :112-131)."""
+    if isinstance(f.f.kernel, Separable):
+        if f.f.mean is not None:
+            raise TypeError("mean functions on space-time grids are not mirrored")
+        As, as_, Qs, Hs, hs, x0 = lgssm_components_separable(f.f.kernel, x)
+        Nr, T = len(x.xl), len(x.xr)
+        if np.ndim(noise) == 0:     # noise_var_to_time_form(::RectilinearGrid, ::Diagonal) (rectilinear_grid.jl:90-93)
+            Rs = Fill(np.full(Nr, float(noise)), T)
+        else:
+            Rs = np.asarray(noise, dtype=np.float64).reshape(T, Nr)
+        return LGSSM(GaussMarkovModel(Forward, As, as_, Qs, x0), SmallOutputEmissions(Hs, hs, Rs))
     As, as_, Qs, Hs, hs, x0 = lgssm_components(f.f.kernel, x)
     mean = f.f.mean
     if mean is not None and not callable(mean) and isinstance(hs, Fill):
@@ -304,6 +371,8 @@ def logpdf(fx, y):
     """logpdf(ft::FiniteLTISDE, y) — lti_sde.jl:60-68; posterior variant posterior_lti_sde.jl:62-78."""
     if isinstance(fx, FinitePosteriorLTISDE):
         return _posterior_logpdf(fx, y)
+    if isinstance(fx.x, RectilinearGrid):     # observations_to_time_form: space fastest (rectilinear_grid.jl:78-80)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(len(fx.x.xr), len(fx.x.xl)))
     return L.logpdf(fx.build_lgssm(), y, fx._handle())
 
 

@@ -74,10 +74,29 @@ class ScalarEmissions:
 
 
 @dataclass
+class SmallOutputEmissions:
+    """StructArray{SmallOutputLGC} (lti_sde.jl:103-109): y[t] = H[t] x[t] + h[t] + N(0, R[t]), y[t] in R^M.
+    Rs: (T, M) | Fill((M,)) = diagonal (the space-time path's `Diagonal`), or (T, M, M) | Fill((M, M)) = dense."""
+    Hs: object   # Fill | (T, M, D)
+    hs: object   # Fill | (T, M)
+    Rs: object
+
+    @property
+    def M(self):
+        H = self.Hs.value if isinstance(self.Hs, Fill) else np.asarray(self.Hs)[0]
+        return int(np.asarray(H).shape[0])
+
+    @property
+    def r_dense(self):
+        R = self.Rs.value if isinstance(self.Rs, Fill) else np.asarray(self.Rs)[0]
+        return np.ndim(R) == 2
+
+
+@dataclass
 class LGSSM:
     """lgssm.jl:9-12."""
     transitions: GaussMarkovModel
-    emissions: ScalarEmissions
+    emissions: object   # ScalarEmissions | SmallOutputEmissions
 
     def __len__(self):
         return len(self.transitions)
@@ -120,12 +139,17 @@ class _Marshalled:
         T = len(model)
         D = model.D
         d = tgp_lgssm()
-        d.D, d.M, d.T = D, 1, T
+        vector = isinstance(em, SmallOutputEmissions)
+        M = em.M if vector else 1
+        d.D, d.M, d.T = D, M, T
         d.ordering = _lib.TGP_FORWARD if tr.ordering == Forward else _lib.TGP_REVERSE
-        d.R_kind = _lib.TGP_R_SCALAR
+        d.R_kind = (_lib.TGP_R_DENSE if em.r_dense else _lib.TGP_R_DIAG) if vector else _lib.TGP_R_SCALAR
         self.keep = []
-        for name, sname, arr, nd, cm in (("A", "sA", tr.As, 2, True), ("a", "sa", tr.as_, 1, False), ("Q", "sQ", tr.Qs, 2, True),
-                                         ("H", "sH", em.Hs, 1, False), ("h", "sh", em.hs, 0, False), ("R", "sR", em.Rs, 0, False)):
+        if vector:   # H is M x D column-major per step; y is (T, M) with M fastest
+            emis = (("H", "sH", em.Hs, 2, True), ("h", "sh", em.hs, 1, False), ("R", "sR", em.Rs, 2 if em.r_dense else 1, em.r_dense))
+        else:
+            emis = (("H", "sH", em.Hs, 1, False), ("h", "sh", em.hs, 0, False), ("R", "sR", em.Rs, 0, False))
+        for name, sname, arr, nd, cm in (("A", "sA", tr.As, 2, True), ("a", "sa", tr.as_, 1, False), ("Q", "sQ", tr.Qs, 2, True)) + emis:
             a, s = _per_step(arr, T, nd, cm)
             self.keep.append(a)
             setattr(d, name, a.ctypes.data)
@@ -137,7 +161,7 @@ class _Marshalled:
         self.keep += [m0, P0]
         d.m0, d.P0 = m0.ctypes.data, P0.ctypes.data
         self.desc = d
-        self.T, self.D = T, D
+        self.T, self.D, self.M = T, D, M
 
 
 def _check_inputs(model: LGSSM, y):
@@ -169,6 +193,8 @@ def transform_model_and_obs(model: LGSSM, y):
 
 def _maybe_missing(model, y):
     if isinstance(y, np.ma.MaskedArray):          # dispatch on type, as missings.jl:8-23 does
+        if isinstance(model.emissions, SmallOutputEmissions):
+            raise TGPError(_lib.TGP_EUNSUPPORTED, "missing data with vector observations is not built yet")
         return transform_model_and_obs(model, y)
     return model, y, 0
 

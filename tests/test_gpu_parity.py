@@ -203,9 +203,11 @@ def test_errors(pkg, handle):
     bad = O.LGSSM("forward", m.As, m.as_, m.Qs, m.m0, m.P0, m.Hs, m.hs, np.full(20, -1e6))
     with pytest.raises(pkg.PosDefException):
         pkg.lgssm.logpdf(to_pkg_model(pkg, bad), np.zeros(20), handle)
-    big = random_lgssm(rng, 5, 7, "forward", True)
-    with pytest.raises(pkg.TGPError):
-        pkg.lgssm.logpdf(to_pkg_model(pkg, big), np.zeros(5), handle)
+    big = random_lgssm(rng, 5, 7, "forward", True)     # D = 7 has no scan instantiation: runs the dense path, still correct
+    yb = sample_y(rng, big)
+    assert abs(pkg.lgssm.logpdf(to_pkg_model(pkg, big), yb, handle) - O.logpdf(big, yb)) <= 1e-9 * abs(O.logpdf(big, yb))
+    with pytest.raises(pkg.TGPError):                  # the smoother entry points are scan-only for now
+        pkg.lgssm.posterior_marginals(to_pkg_model(pkg, big), yb, 0.1, handle)
 
 
 def test_shard_reduce_prefix(pkg, handle):
@@ -360,3 +362,68 @@ def test_cfg3_sum_kernel_d10_posterior_marginals(pkg, handle, T):
     mu, var = pkg.gp.marginals(pkg.gp.posterior(fx, y)(pkg.RegularSpacing(0.0, 0.01, T), 1e-2))
     np.testing.assert_allclose(mu, mu_o, rtol=MV_RTOL, atol=1e-7)
     np.testing.assert_allclose(var, var_o, rtol=MV_RTOL)
+
+
+# ---- vector observations / large state: the dense step-by-step path (tgp_dense.cu) ----------------------------------
+def _random_vector_lgssm(rng, T, D, M, ordering, r_dense):
+    from tests.util import random_psd, _stable
+    As = np.stack([_stable(0.9 * np.eye(D) + 0.1 * rng.standard_normal((D, D))) for _ in range(T)])
+    as_ = rng.standard_normal((T, D)) * 0.3
+    Qs = np.stack([random_psd(rng, D) for _ in range(T)])
+    Hs = rng.standard_normal((T, M, D))
+    hs = rng.standard_normal((T, M)) * 0.2
+    Rs = np.stack([random_psd(rng, M, 0.1, 1.0) if r_dense else np.diag(rng.uniform(0.1, 1.0, M)) for _ in range(T)])
+    return O.LGSSM(ordering, As, as_, Qs, rng.standard_normal(D), random_psd(rng, D, 0.5, 2.0), Hs, hs, Rs)
+
+
+def _pkg_vector_model(pkg, m, r_dense):
+    L = pkg.lgssm
+    tr = L.GaussMarkovModel(m.ordering, np.array(m.As), np.array(m.as_), np.array(m.Qs), L.Gaussian(np.array(m.m0), np.array(m.P0)))
+    Rs = np.array(m.Rs) if r_dense else np.array([np.diag(R) for R in m.Rs])
+    return L.LGSSM(tr, L.SmallOutputEmissions(np.array(m.Hs), np.array(m.hs), Rs))
+
+
+@pytest.mark.parametrize("r_dense", [False, True])
+@pytest.mark.parametrize("ordering", ["forward", "reverse"])
+@pytest.mark.parametrize("D,M", [(1, 1), (3, 2), (3, 1), (7, 3), (12, 5)])
+def test_small_output_lgc_vector_observations(pkg, handle, D, M, ordering, r_dense):
+    """posterior_and_lml(::SmallOutputLGC) (LGC:129-141) through tgp_logpdf / tgp_filter: Dlat/Dobs of the reference's
+    unit tests (test/models/lgssm.jl: Dlat in {1,3}, Dobs in {1,2}) and larger; time-varying, both orderings."""
+    rng = np.random.default_rng(100 * D + M)
+    T = 49
+    m = _random_vector_lgssm(rng, T, D, M, ordering, r_dense)
+    y = O.sample_prior(O.LGSSM("forward", m.As, m.as_, m.Qs, m.m0, m.P0, m.Hs, m.hs, m.Rs), rng)
+    ms_o, Ps_o, lmls_o = O.filter_(m, y)
+    pm = _pkg_vector_model(pkg, m, r_dense)
+    lml, steps = pkg.lgssm.logpdf(pm, y, handle, per_step=True)
+    np.testing.assert_allclose(steps, lmls_o, rtol=1e-9, atol=1e-10)
+    assert abs(lml - lmls_o.sum()) <= LML_RTOL * abs(lmls_o.sum())
+    ms, Ps = pkg.lgssm._filter(pm, y, handle)
+    np.testing.assert_allclose(ms, ms_o, rtol=MV_RTOL, atol=1e-9)
+    np.testing.assert_allclose(Ps, Ps_o, rtol=MV_RTOL, atol=1e-10)
+
+
+@pytest.mark.parametrize("regular", [True, False])
+def test_space_time_separable_logpdf(pkg, regular):
+    """test/space_time/to_gauss_markov.jl:36-66: Separable(SE, Matern32) on RectilinearGrid(Nr = 3, Nt = 5): SDE path ==
+    dense GP; plus a larger grid against the oracle (time-invariant -> the CUDA-graph replay)."""
+    rng = np.random.default_rng(123456)
+    r = rng.standard_normal(3)
+    tp = pkg.RegularSpacing(0.0, 0.3, 5) if regular else np.sort(rng.uniform(0, 2, 5))
+    to = O.RegularSpacing(0.0, 0.3, 5) if regular else np.array(tp)
+    mo = O.build_lgssm_separable(O.SqExp(), O.Matern32(), r, to, 0.1)
+    y = O.sample_prior(mo, rng)
+    fx = pkg.to_sde(pkg.GP(pkg.Separable(pkg.SEKernel(), pkg.Matern32Kernel())))(pkg.RectilinearGrid(r, tp), 0.1)
+    lml = pkg.gp.logpdf(fx, y.reshape(-1))
+    lp_d = O.dense_separable_logpdf(O.SqExp(), O.Matern32(), r, to, 0.1, y.reshape(-1))
+    assert abs(lml - lp_d) <= 1e-6 * abs(lp_d)
+    assert abs(lml - O.logpdf(mo, y)) <= LML_RTOL * abs(lml)
+    # config-5 shape, scaled down: Separable(SE, Matern52), 24 spatial points x 300 times (D = 72, M = 24)
+    r2 = np.linspace(-3, 3, 24)
+    T = 300
+    mo2 = O.build_lgssm_separable(O.SqExp(), O.Matern52(), r2, O.RegularSpacing(0.0, 0.01, T), 0.1)
+    y2 = O.sample_prior(mo2, rng)
+    fx2 = pkg.to_sde(pkg.GP(pkg.Separable(pkg.SEKernel(), pkg.Matern52Kernel())))(pkg.RectilinearGrid(r2, pkg.RegularSpacing(0.0, 0.01, T)), 0.1)
+    lml2 = pkg.gp.logpdf(fx2, y2.reshape(-1))
+    ref2 = O.logpdf(mo2, y2)
+    assert abs(lml2 - ref2) <= LML_RTOL * abs(ref2)
