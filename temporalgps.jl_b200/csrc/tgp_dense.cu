@@ -24,32 +24,66 @@ namespace tgp {
 
 constexpr double kLog2PiD = 1.8378770664093454835606594728112;
 
-// S (M x M, column-major, upper triangle valid) <- upper Cholesky factor U, S = U'U; lower triangle zeroed.
-// One CTA; right-looking, column by column in global / L2 memory (M <= a few hundred). fail[0] gets the step on error.
-__global__ void __launch_bounds__(1024) k_chol_upper(double* __restrict__ S, int M, const long long* __restrict__ step,
-                                                      unsigned long long* __restrict__ err) {
-    __shared__ double s_d;
+// Upper Cholesky factor in place (S = U'U, column-major, upper triangle read), blocked right-looking with NB = 32:
+//   k_chol_panel  (1 CTA)    block row [k0, k0+nb) x [k0, M): into shared memory, factor the diagonal block column by
+//                            column, apply U_kk^-T to the rest of the row, write the rows of U back;
+//   k_chol_trail  (many CTAs) S[i, c] -= sum_r U[k0+r, i] U[k0+r, c] for k0+nb <= i <= c < M.
+// 2*ceil(M/32) - 1 launches per factorisation (inside the captured step graph). err gets the time step on failure.
+constexpr int kCholNB = 32;
+
+__global__ void __launch_bounds__(1024) k_chol_panel(double* __restrict__ S, int M, int k0, const long long* __restrict__ step,
+                                                     unsigned long long* __restrict__ err) {
+    extern __shared__ double pan[];          // pan[r * W + (c - k0)], r < nb, k0 <= c < M
+    __shared__ double s_inv;
+    const int nb = min(kCholNB, M - k0), W = M - k0;
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int j = 0; j < M; ++j) {
+    for (int e = tid; e < nb * W; e += nt) {
+        const int r = e % nb, c = e / nb;
+        pan[r * W + c] = S[(size_t)(k0 + r) + (size_t)M * (k0 + c)];
+    }
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
         if (tid == 0) {
-            const double d = S[j + (size_t)M * j];
-            if (!(d > 0.0)) { atomicMin(err, (unsigned long long)*step); s_d = 1.0; }
-            else s_d = sqrt(d);
-            S[j + (size_t)M * j] = s_d;
+            const double d = pan[j * W + j];
+            if (!(d > 0.0)) { atomicMin(err, (unsigned long long)*step); s_inv = 1.0; pan[j * W + j] = 1.0; }
+            else { const double sd = sqrt(d); pan[j * W + j] = sd; s_inv = 1.0 / sd; }
         }
         __syncthreads();
-        const double inv = 1.0 / s_d;
-        for (int i = j + 1 + tid; i < M; i += nt) S[j + (size_t)M * i] *= inv;   // row j of U
+        const double inv = s_inv;
+        for (int c = j + 1 + tid; c < W; c += nt) pan[j * W + c] *= inv;          // row j of U
         __syncthreads();
-        // trailing update of the upper triangle: S[r, c] -= U[j, r] U[j, c], j < r <= c
-        const int n = M - 1 - j;
-        for (long long e = tid; e < (long long)n * n; e += nt) {
-            const int r = j + 1 + (int)(e % n), c = j + 1 + (int)(e / n);
-            if (r <= c) S[r + (size_t)M * c] = fma(-S[j + (size_t)M * r], S[j + (size_t)M * c], S[r + (size_t)M * c]);
+        // rows j+1 .. nb-1 of the panel: pan[r][c] -= U[j][r] * U[j][c], c >= r
+        const int nr = nb - 1 - j;
+        for (int e = tid; e < nr * W; e += nt) {
+            const int r = j + 1 + e / W, c = e % W;
+            if (c >= r) pan[r * W + c] = fma(-pan[j * W + r], pan[j * W + c], pan[r * W + c]);
         }
         __syncthreads();
     }
-    for (long long e = tid; e < (long long)M * M; e += nt) {
+    for (int e = tid; e < nb * W; e += nt) {
+        const int r = e % nb, c = e / nb;
+        S[(size_t)(k0 + r) + (size_t)M * (k0 + c)] = (c >= r) ? pan[r * W + c] : 0.0;
+    }
+    // below-diagonal part of these columns (rows > k0 + nb) is cleared by k_chol_trail's final pass
+}
+
+__global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ S, int M, int k0, int nb) {
+    const int n = M - k0 - nb;                 // trailing size
+    const int base = k0 + nb;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)n * n; e += (long long)gridDim.x * blockDim.x) {
+        const int i = base + (int)(e % n), c = base + (int)(e / n);
+        if (i > c) { continue; }
+        const double* ui = S + (size_t)k0 + (size_t)M * i;
+        const double* uc = S + (size_t)k0 + (size_t)M * c;
+        double acc = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < nb; ++r) acc = fma(ui[r], uc[r], acc);
+        S[(size_t)i + (size_t)M * c] -= acc;
+    }
+}
+
+__global__ void k_clear_lower(double* __restrict__ S, int M) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)M * M; e += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(e % M), c = (int)(e / M);
         if (r > c) S[e] = 0.0;
     }
@@ -155,8 +189,20 @@ static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const d
         k_expand_R<<<std::min((M * M + 255) / 256, 1184), 256, 0, st>>>(w.S, M, d.R, d.sR, d.R_kind, w.step);
         TGP_LAUNCH_CHECK(h);
         TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, M, M, D, &one, w.V, M, H, M, &one, w.S, M));    // S = V H' + R
-        TGP_K(h, "dense:k_chol_upper");
-        k_chol_upper<<<1, 1024, 0, st>>>(w.S, M, w.step, w.err);
+        for (int k0 = 0; k0 < M; k0 += kCholNB) {
+            const int nbk = std::min(kCholNB, M - k0);
+            TGP_K(h, "dense:k_chol_panel");
+            k_chol_panel<<<1, 1024, sizeof(double) * nbk * (M - k0), st>>>(w.S, M, k0, w.step, w.err);
+            TGP_LAUNCH_CHECK(h);
+            const int n = M - k0 - nbk;
+            if (n > 0) {
+                TGP_K(h, "dense:k_chol_trail");
+                k_chol_trail<<<(int)std::min<long long>(((long long)n * n + 255) / 256, 1184), 256, 0, st>>>(w.S, M, k0, nbk);
+                TGP_LAUNCH_CHECK(h);
+            }
+        }
+        TGP_K(h, "dense:k_clear_lower");
+        k_clear_lower<<<std::min((M * M + 255) / 256, 1184), 256, 0, st>>>(w.S, M);
         TGP_LAUNCH_CHECK(h);
         TGP_CUDA(h, cudaMemcpyAsync(w.B, w.V, sizeof(double) * M * D, cudaMemcpyDeviceToDevice, st));
         TGP_CUBLAS(h, cublasDtrsm(cb, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, D, &one, w.S, M, w.B, M));  // B = U' \ V
@@ -243,6 +289,9 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
     TGP_CUDA(h, cudaMemcpyAsync(w.step, &t0, sizeof(long long), cudaMemcpyHostToDevice, st));
     TGP_CUDA(h, cudaStreamSynchronize(st));   // t0 is a stack variable
 
+    const size_t pan_bytes = sizeof(double) * kCholNB * (size_t)M;
+    if (pan_bytes > 200 * 1024) return fail(h, TGP_EUNSUPPORTED, "observation dimension M=%d too large for the Cholesky panel kernel", M);
+    if (pan_bytes > 48 * 1024) TGP_CUDA(h, cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pan_bytes));
     const bool ti = !(m->sA | m->sa | m->sQ | m->sH | m->sh | m->sR);
     if (ti && T >= 8 && !h->timing) {
         // capture ONE step, replay it T times

@@ -61,9 +61,33 @@ def cfg3(T):
             "kernels_ms_per_call": {n: ms / c for n, ms, c in tim}}
 
 
+def cfg5(Nr, T, T_cpu):
+    """Separable(SE, Matern52) on RectilinearGrid(range(-3, 3, Nr), RegularSpacing(0, 0.01, T)): D = 3 Nr, M = Nr. FP64, dense
+    as the reference executes it (2.57 GFLOP/step at Nr = 256). The CPU side is the NumPy oracle (multi-threaded BLAS) on T_cpu steps."""
+    r = np.linspace(-3.0, 3.0, Nr)
+    rng = np.random.default_rng(20261017 + 5)
+    y = rng.standard_normal((T, Nr))
+    fx = pkg.to_sde(pkg.GP(pkg.Separable(pkg.SEKernel(), pkg.Matern52Kernel())))(pkg.RectilinearGrid(r, pkg.RegularSpacing(0.0, 0.01, T)), 0.1)
+    model = fx.build_lgssm()
+    t_gpu, lml = timeit(lambda: pkg.lgssm.logpdf(model, y, h), 2, 1)
+    mo = O.build_lgssm_separable(O.SqExp(), O.Matern52(), r, O.RegularSpacing(0.0, 0.01, T_cpu), 0.1)
+    t0 = time.perf_counter()
+    ref = O.logpdf_steps(mo, y[:T_cpu])
+    t_cpu = (time.perf_counter() - t0) / T_cpu
+    lml_c, steps = pkg.lgssm.logpdf(pkg.to_sde(pkg.GP(pkg.Separable(pkg.SEKernel(), pkg.Matern52Kernel())))(
+        pkg.RectilinearGrid(r, pkg.RegularSpacing(0.0, 0.01, T_cpu)), 0.1).build_lgssm(), y[:T_cpu], h, per_step=True)
+    D, M = 3 * Nr, Nr
+    flops = 4.0 * D ** 3 + 2.0 * M * D * D + 2.0 * M * M * D + M ** 3 / 3.0 + 1.0 * M * M * D + 2.0 * D * D * M
+    return {"config": f"cfg5 Separable(SE, Matern52) Nr={Nr} (D={D}, M={M}) T={T} logpdf, FP64, dense (library GEMMs + own Cholesky), CUDA-graph replay",
+            "gpu_ms_per_step": t_gpu / T * 1e3, "gpu_steps_per_s": T / t_gpu, "gpu_tflops_dense_equiv": flops * T / t_gpu / 1e12,
+            "cpu_oracle_ms_per_step": t_cpu * 1e3, "cpu_sample_steps": T_cpu, "lml_step_max_rel_err": float(np.max(np.abs(steps - ref) / np.abs(ref)))}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--T3", type=int, default=1_000_000)
     a = ap.parse_args()
     print(json.dumps(cfg1()))
     print(json.dumps(cfg3(a.T3)))
+    print(json.dumps(cfg5(64, 500, 20)))
+    print(json.dumps(cfg5(256, 300, 6)))
