@@ -246,8 +246,14 @@ def run_ours(args):
     bytes_per_step = 8.0  # logpdf: y read once, 8 B per Kalman step
     top_ms = top[1] / top[2]
     achieved = bytes_per_step * T / (top_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        rec = json.load(open(tp)).get(top[0].split("(")[0])
+        if rec and rec.get("T") == T:
+            traffic = rec["dram_bytes_per_launch"]
     roof = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-            "traffic": None, "peak_source": peak_src, "kernel_ms": top_ms, "kernel_share_of_step": top[1] / tot,
+            "traffic": traffic, "peak_source": peak_src, "kernel_ms": top_ms, "kernel_share_of_step": top[1] / tot,
             "algorithmic_bytes_per_step": bytes_per_step,
             "kernels": [{"name": n, "ms_per_launch": ms / c, "launches_per_step": c / K} for n, ms, c in tim]}
 
