@@ -55,6 +55,11 @@ extern "C" {
 #define TGP_OPT_SS_TOL       3  /* (double bits) relative tolerance for steady-state detection  */
 #define TGP_OPT_TIMING       4  /* 1: bracket every kernel launch with CUDA events (tgp_get_timing) */
 #define TGP_OPT_SS_PREFIX    5  /* steps filtered by the general scan before the steady-state test */
+#define TGP_OPT_DENSE_MATH   6  /* arithmetic of the large-state / vector-observation path (tgp_dense.cu)      */
+#define TGP_DENSE_F64        0  /* FP64 throughout (reference ArrayStorage(Float64)); library GEMMs              */
+#define TGP_DENSE_TF32X3     1  /* FP32 storage (reference ArrayStorage(Float32)): covariance algebra on the tcgen05
+                                 * tensor cores as 3xTF32 split products with FP32 accumulation in TMEM; innovation
+                                 * Cholesky, means and the log-likelihood stay FP64                               */
 
 typedef struct tgp_ctx* tgp_handle;
 
@@ -140,6 +145,10 @@ int tgp_marginals(tgp_handle h, const tgp_lgssm* model, double* mean_out, double
 int tgp_posterior_marginals(tgp_handle h, const tgp_lgssm* model, const double* y,
                             const double* R_new, int64_t sRnew,
                             double* mean_out, double* var_out, double* lml_out);
+
+/* Test hook (no reference analogue): C (Mx x N) = X' Y for HOST column-major float matrices X (K x Mx), Y (K x N),
+ * computed by the tcgen05 3xTF32 contraction kernel alone; symmetric != 0 exercises the mirrored upper-triangle epilogue. */
+int tgp_debug_tc_gemm(tgp_handle h, int K, int Mx, int N, const float* X, const float* Y, float* C, int symmetric);
 
 /* ---- time-sharded multi-GPU path (no reference analogue) -------------------
  * A scan element is (A, b, C, eta, J): 3*D*D + 2*D doubles, matrices column-major, in that

@@ -19,6 +19,8 @@ TGP_FORWARD, TGP_REVERSE = 0, 1
 TGP_R_SCALAR, TGP_R_DIAG, TGP_R_DENSE = 0, 1, 2
 TGP_OPT_ALGO, TGP_OPT_CHUNK, TGP_OPT_SS_TOL, TGP_OPT_TIMING, TGP_OPT_SS_PREFIX = 1, 2, 3, 4, 5
 TGP_ALGO_AUTO, TGP_ALGO_SCAN = 0, 1
+TGP_OPT_DENSE_MATH = 6
+TGP_DENSE_F64, TGP_DENSE_TF32X3 = 0, 1
 
 
 class TGPError(RuntimeError):
@@ -68,6 +70,7 @@ _SIGS = {
     "tgp_marginals": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p]),
     "tgp_posterior_marginals": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "tgp_debug_tc_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "tgp_elem_size": (C.c_int, [C.c_int]),
     "tgp_shard_reduce": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p]),
     "tgp_shard_xchg_size": (C.c_int, [C.c_int]),
@@ -159,6 +162,19 @@ class Handle:
 
     def set_ss_tol(self, tol):
         self.set_option(TGP_OPT_SS_TOL, int(np.float64(tol).view(np.int64)))
+
+    def set_dense_math(self, mode):
+        self.set_option(TGP_OPT_DENSE_MATH, mode)
+
+    def tc_gemm(self, X, Y, symmetric=False):
+        """Test hook: X' Y through the tcgen05 3xTF32 kernel. X (K, Mx), Y (K, N) float32; returns (Mx, N) float32."""
+        Xf = np.asfortranarray(X, dtype=np.float32)
+        Yf = np.asfortranarray(Y, dtype=np.float32)
+        K, Mx = Xf.shape
+        N = Yf.shape[1]
+        Cm = np.zeros((Mx, N), dtype=np.float32, order="F")
+        self.check(lib().tgp_debug_tc_gemm(self._h, K, Mx, N, Xf.ctypes.data, Yf.ctypes.data, Cm.ctypes.data, 1 if symmetric else 0))
+        return Cm
 
     def set_timing(self, on: bool):
         self.set_option(TGP_OPT_TIMING, 1 if on else 0)

@@ -171,6 +171,10 @@ int tgp_set_option(tgp_handle h, int option, int64_t value) {
             if (value < 0 || value > (int64_t(1) << 24)) return fail(h, TGP_EINVAL, "steady-state prefix must be in 0..2^24");
             h->ss_prefix = value;
             return TGP_OK;
+        case TGP_OPT_DENSE_MATH:
+            if (value != TGP_DENSE_F64 && value != TGP_DENSE_TF32X3) return fail(h, TGP_EINVAL, "unknown dense arithmetic %lld", (long long)value);
+            h->dense_math = (int)value;
+            return TGP_OK;
         default: return fail(h, TGP_EINVAL, "unknown option %d", option);
     }
 }
@@ -263,6 +267,12 @@ int tgp_posterior_marginals(tgp_handle h, const tgp_lgssm* model, const double* 
 #define CALL(Dv) do_posterior_marginals<Dv>(h, model, y, R_new, sRnew, mean_out, var_out, lml_out)
     TGP_DISPATCH_D(h, model->D)
 #undef CALL
+}
+
+int tgp_debug_tc_gemm(tgp_handle h, int K, int Mx, int N, const float* X, const float* Y, float* C, int symmetric) {
+    if (!h || !X || !Y || !C || K < 1 || Mx < 1 || N < 1) return TGP_EINVAL;
+    TGP_TRY(begin_call(h));
+    return tc_gemm_selftest(h, K, Mx, N, X, Y, C, symmetric);
 }
 
 int tgp_elem_size(int D) { return 3 * D * D + 2 * D; }

@@ -74,6 +74,7 @@ struct tgp_ctx {
     int64_t launches = 0, h2d = 0, d2h = 0;
     int algo = TGP_ALGO_AUTO;
     int chunk = 0;
+    int dense_math = TGP_DENSE_F64;   // arithmetic of the large-state path (TGP_OPT_DENSE_MATH)
     double ss_tol = 1e-13;
     int64_t ss_prefix = 0;   // 0 = auto
     int sm_count = 148;

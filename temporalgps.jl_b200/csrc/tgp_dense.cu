@@ -232,9 +232,13 @@ static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const d
     return TGP_OK;
 }
 
+int dense_filter_tc(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out, double* lml_steps_user, double* m_f_user, int64_t s_m,
+                    double* P_f_user, int64_t s_P);
+
 // Entry point used by tgp_logpdf / tgp_filter for shapes outside the small-state scan kernels.
 int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out, double* lml_steps_user, double* m_f_user, int64_t s_m,
                  double* P_f_user, int64_t s_P) {
+    if (h->dense_math == TGP_DENSE_TF32X3) return dense_filter_tc(h, m, y, lml_out, lml_steps_user, m_f_user, s_m, P_f_user, s_P);
     const int D = m->D, M = m->M;
     const int64_t T = m->T;
     cudaStream_t st = h->stream;
@@ -327,3 +331,5 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
 }
 
 }  // namespace tgp
+
+#include "tgp_dense_tc.cuh"

@@ -22,6 +22,9 @@ template <int D> int do_shard_prefix(int n, const double* elems, const double* m
 int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out, double* lml_steps, double* m_f, int64_t s_m,
                  double* P_f, int64_t s_P);
 
+// Test hook for the tcgen05 contraction kernel alone (tgp_dense_tc.cuh).
+int tc_gemm_selftest(tgp_ctx* h, int K, int Mx, int N, const float* X, const float* Y, float* C, int symmetric);
+
 #define TGP_DECL_D(Dv)                                                                                               \
     extern template int do_filter<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, double*, int64_t, double*, int64_t, \
                                       double*, double*);                                                             \

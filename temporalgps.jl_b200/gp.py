@@ -22,16 +22,24 @@ from .lgssm import Fill, Forward, Gaussian, GaussMarkovModel, LGSSM, ScalarEmiss
 # ---- storage tags (storage_types.jl) -------------------------------------------------------------
 @dataclass(frozen=True)
 class B200Storage:
-    """Selects the B200 library for the LGSSM recursions. dtype is always float64 on this path."""
+    """Selects the B200 library for the LGSSM recursions. The small-state scan kernels are FP64 whatever `dtype` says;
+    on the large-state / vector-observation path float32 selects the FP32-storage tcgen05 kernels (3xTF32 products,
+    TGP_DENSE_TF32X3), float64 the FP64 step."""
     device: int = 0
+    dtype: type = np.float64
+
+    def handle(self):
+        h = L.default_handle(self.device)
+        h.set_option(L.TGP_OPT_DENSE_MATH, L.TGP_DENSE_TF32X3 if np.dtype(self.dtype) == np.float32 else L.TGP_DENSE_F64)
+        return h
 
 
 def SArrayStorage(dtype=np.float64):   # accepted for source compatibility; same path
-    return B200Storage()
+    return B200Storage(0, dtype)
 
 
 def ArrayStorage(dtype=np.float64):
-    return B200Storage()
+    return B200Storage(0, dtype)
 
 
 # ---- inputs --------------------------------------------------------------------------------------
@@ -361,7 +369,7 @@ class FiniteLTISDE:
     noise: object
 
     def _handle(self):
-        return L.default_handle(self.f.storage.device)
+        return self.f.storage.handle()
 
     def build_lgssm(self):
         return build_lgssm(self.f, self.x, self.noise)
@@ -447,7 +455,7 @@ def merge_datasets(x1, x2, S1, S2, y1, y2):
 
 def _posterior_marginals(fx: FinitePosteriorLTISDE):
     post = fx.f
-    h = L.default_handle(post.prior.storage.device)
+    h = post.prior.storage.handle()
     if _same_inputs(fx.x, post.x):                       # posterior_lti_sde.jl:27-36
         model = build_lgssm(post.prior, post.x, post.noise)
         return L.posterior_marginals(model, post.y, _noise_to_time_form(fx.x, fx.noise), h)
@@ -464,7 +472,7 @@ def _posterior_marginals(fx: FinitePosteriorLTISDE):
 def _posterior_logpdf(fx: FinitePosteriorLTISDE, y_pr):
     """posterior_lti_sde.jl:62-78."""
     post = fx.f
-    h = L.default_handle(post.prior.storage.device)
+    h = post.prior.storage.handle()
     n_pr = len(fx.x)
     S_pr = _noise_to_time_form(fx.x, fx.noise)
     x, S, ys, tr, pr = merge_datasets(post.x, fx.x, _noise_to_time_form(post.x, post.noise), S_pr, post.y, np.full(n_pr, np.nan))

@@ -19,7 +19,8 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import DimensionMismatch, Handle, PosDefException, TGPError, default_handle, tgp_lgssm
+from ._lib import (TGP_DENSE_F64, TGP_DENSE_TF32X3, TGP_OPT_DENSE_MATH, DimensionMismatch, Handle, PosDefException, TGPError,
+                   default_handle, tgp_lgssm)
 
 Forward = "forward"   # gauss_markov_model.jl:1
 Reverse = "reverse"   # gauss_markov_model.jl:3
