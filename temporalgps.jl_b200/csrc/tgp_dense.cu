@@ -11,6 +11,7 @@
 #include <cublas_v2.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "tgp_ctx.cuh"
 
@@ -134,7 +135,7 @@ __global__ void k_load_aQ(double* __restrict__ mt, double* __restrict__ Pn, int 
     const long long t = *step;
     const long long n = (long long)D * D;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n + D; e += (long long)gridDim.x * blockDim.x) {
-        if (e < n) Pn[e] = Q[t * sQ + e];
+        if (e < n) { if (Pn) Pn[e] = Q[t * sQ + e]; }
         else mt[e - n] = a[t * sa + (e - n)];
     }
 }
@@ -151,15 +152,52 @@ __global__ void k_emit_state(const double* __restrict__ m, const double* __restr
 
 __global__ void k_advance(long long* step, long long delta) { *step += delta; }
 
+// Steady-state detection for time-invariant models: conv[0] = max |P - Pprev|, conv[1] = max |P| (bit patterns of
+// non-negative doubles order like integers), and Pprev <- P for the next step.
+__global__ void k_conv_check(const double* __restrict__ P, double* __restrict__ Pprev, long long n, unsigned long long* __restrict__ conv) {
+    double md = 0.0, ma = 0.0;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const double x = P[e];
+        md = fmax(md, fabs(x - Pprev[e]));
+        ma = fmax(ma, fabs(x));
+        Pprev[e] = x;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        md = fmax(md, __shfl_xor_sync(0xffffffffu, md, off));
+        ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(conv, (unsigned long long)__double_as_longlong(md));
+        atomicMax(conv + 1, (unsigned long long)__double_as_longlong(ma));
+    }
+}
+
+__global__ void k_advance_conv64(long long* step, long long delta, unsigned long long* conv, double tol, long long* ss_at) {
+    if (conv) {
+        const double d = __longlong_as_double((long long)conv[0]), a = __longlong_as_double((long long)conv[1]);
+        conv[2] = conv[0];   // kept for diagnostics (TGP_DEBUG): the last measured |dP|, |P|
+        conv[3] = conv[1];
+        if (*ss_at < 0 && a > 0.0 && d <= tol * a) *ss_at = *step;
+        conv[0] = 0ull;
+        conv[1] = 0ull;
+    }
+    *step += delta;
+}
+
 struct DenseWs {
     double *m, *mt, *P, *Pn, *T1, *V, *S, *B, *r;
     long long* step;
     double* lml;
     unsigned long long* err;
+    double* Pprev = nullptr;             // steady-state detection (time-invariant models only)
+    unsigned long long* conv = nullptr;
+    long long* ss_at = nullptr;
 };
 
+// frozen: the covariance recursion has reached its fixed point; only the mean / likelihood part of the step runs.
 static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const double* dy, const DenseWs& w, long long t /* host index or -1: use device counter */,
-                      bool graph_mode, double* lml_steps, double* m_f, int64_t s_m, double* P_f, int64_t s_P) {
+                      bool graph_mode, double* lml_steps, double* m_f, int64_t s_m, double* P_f, int64_t s_P, bool frozen = false) {
     const int D = d.D, M = d.M;
     cudaStream_t st = h->stream;
     const double one = 1.0, zero = 0.0, mone = -1.0;
@@ -173,9 +211,14 @@ static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const d
 
     auto predict = [&]() -> int {
         TGP_K(h, "dense:k_load_aQ");
-        k_load_aQ<<<nb, 256, 0, st>>>(w.mt, w.Pn, D, d.a, d.sa, d.Q, d.sQ, w.step);
+        k_load_aQ<<<nb, 256, 0, st>>>(w.mt, frozen ? nullptr : w.Pn, D, d.a, d.sa, d.Q, d.sQ, w.step);
         TGP_LAUNCH_CHECK(h);
         TGP_CUBLAS(h, cublasDgemv(cb, CUBLAS_OP_N, D, D, &one, A, D, w.m, 1, &one, w.mt, 1));                 // mt = A m + a
+        if (frozen) {
+            TGP_CUDA(h, cudaMemcpyAsync(w.m, w.mt, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
+            h->launches += 2;
+            return TGP_OK;
+        }
         TGP_CUBLAS(h, cublasDsymm(cb, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, D, D, &one, w.P, D, A, D, &zero, w.T1, D));  // A * Symmetric(P)
         TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, D, D, D, &one, w.T1, D, A, D, &one, w.Pn, D)); // Pn = T1 A' + Q
         TGP_CUDA(h, cudaMemcpyAsync(w.m, w.mt, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
@@ -184,6 +227,7 @@ static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const d
         return TGP_OK;
     };
     auto update = [&]() -> int {
+      if (!frozen) {
         TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_N, M, D, D, &one, H, M, w.P, D, &zero, w.V, M));   // V = H P
         TGP_K(h, "dense:k_expand_R");
         k_expand_R<<<std::min((M * M + 255) / 256, 1184), 256, 0, st>>>(w.S, M, d.R, d.sR, d.R_kind, w.step);
@@ -206,6 +250,7 @@ static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const d
         TGP_LAUNCH_CHECK(h);
         TGP_CUDA(h, cudaMemcpyAsync(w.B, w.V, sizeof(double) * M * D, cudaMemcpyDeviceToDevice, st));
         TGP_CUBLAS(h, cublasDtrsm(cb, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, D, &one, w.S, M, w.B, M));  // B = U' \ V
+      }
         TGP_K(h, "dense:k_residual0");
         k_residual0<<<(M + 255) / 256, 256, 0, st>>>(w.r, M, dy, d.h, d.sh, w.step);
         TGP_LAUNCH_CHECK(h);
@@ -215,19 +260,26 @@ static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const d
         k_lml<<<1, 256, 0, st>>>(w.S, w.r, M, lml_steps, w.lml, w.step);
         TGP_LAUNCH_CHECK(h);
         TGP_CUBLAS(h, cublasDgemv(cb, CUBLAS_OP_T, M, D, &one, w.B, M, w.r, 1, &one, w.m, 1));                    // m += B' alpha
-        TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, D, D, M, &mone, w.B, M, w.B, M, &one, w.P, D));  // P -= B'B
+        if (!frozen) {
+            TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, D, D, M, &mone, w.B, M, w.B, M, &one, w.P, D));  // P -= B'B
+            if (w.conv) {
+                TGP_K(h, "dense:k_conv_check");
+                k_conv_check<<<nb, 256, 0, st>>>(w.P, w.Pprev, (long long)D * D, w.conv);
+                TGP_LAUNCH_CHECK(h);
+            }
+        }
         if (m_f || P_f) {
             TGP_K(h, "dense:k_emit_state");
             k_emit_state<<<nb, 256, 0, st>>>(w.m, w.P, D, m_f, s_m, P_f, s_P, w.step);
             TGP_LAUNCH_CHECK(h);
         }
-        h->launches += 8;
+        h->launches += frozen ? 3 : 8;
         return TGP_OK;
     };
     if (!rev) { TGP_TRY(predict()); TGP_TRY(update()); }
     else      { TGP_TRY(update()); TGP_TRY(predict()); }
     TGP_K(h, "dense:k_advance");
-    k_advance<<<1, 1, 0, st>>>(w.step, rev ? -1 : 1);
+    k_advance_conv64<<<1, 1, 0, st>>>(w.step, rev ? -1 : 1, frozen ? nullptr : w.conv, h->ss_tol, w.ss_at);
     TGP_LAUNCH_CHECK(h);
     return TGP_OK;
 }
@@ -280,6 +332,15 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
     TGP_TRY(dalloc(h, 1, &w.step));
     TGP_TRY(dalloc(h, 1, &w.lml));
     TGP_TRY(dalloc(h, 1, &w.err));
+    const bool ti = !(m->sA | m->sa | m->sQ | m->sH | m->sh | m->sR);
+    if (ti && h->algo == TGP_ALGO_AUTO) {
+        TGP_TRY(dalloc(h, (size_t)D * D, &w.Pprev));
+        TGP_TRY(dalloc(h, 4, &w.conv));
+        TGP_TRY(dalloc(h, 1, &w.ss_at));
+        TGP_CUDA(h, cudaMemcpyAsync(w.Pprev, d.P0, sizeof(double) * D * D, cudaMemcpyDeviceToDevice, st));
+        TGP_CUDA(h, cudaMemsetAsync(w.conv, 0, 4 * sizeof(unsigned long long), st));
+        TGP_CUDA(h, cudaMemsetAsync(w.ss_at, 0xFF, sizeof(long long), st));
+    }
     void* cbws;
     const size_t cbws_bytes = size_t(32) << 20;
     TGP_TRY(dalloc(h, cbws_bytes / 8, (double**)&cbws));
@@ -296,21 +357,43 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
     const size_t pan_bytes = sizeof(double) * kCholNB * (size_t)M;
     if (pan_bytes > 200 * 1024) return fail(h, TGP_EUNSUPPORTED, "observation dimension M=%d too large for the Cholesky panel kernel", M);
     if (pan_bytes > 48 * 1024) TGP_CUDA(h, cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pan_bytes));
-    const bool ti = !(m->sA | m->sa | m->sQ | m->sH | m->sh | m->sR);
     if (ti && T >= 8 && !h->timing) {
-        // capture ONE step, replay it T times
-        cudaGraph_t graph;
-        cudaGraphExec_t exec;
-        TGP_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int rc = dense_step(h, cb, d, dy, w, -1, true, lml_steps, m_f, dsm, P_f, dsP);
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (rc != TGP_OK) return rc;
-        TGP_CUDA(h, ce);
-        TGP_CUDA(h, cudaGraphInstantiate(&exec, graph, 0));
-        for (int64_t t = 0; t < T; ++t) TGP_CUDA(h, cudaGraphLaunch(exec, st));
+        // Capture ONE step, replay it. Every kPoll steps the host looks at the steady-state word; once the covariance
+        // recursion has converged (max |P_t - P_{t-1}| <= ss_tol max |P_t|, tested on the device) the remaining steps replay
+        // the mean-only graph: same arithmetic with P, S, U, B frozen at their limit.
+        cudaGraph_t graph[2] = {nullptr, nullptr};
+        cudaGraphExec_t exec[2] = {nullptr, nullptr};
+        int64_t per_replay[2] = {0, 0};
+        for (int fz = 0; fz < (w.conv ? 2 : 1); ++fz) {
+            TGP_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int64_t l0 = h->launches;
+            int rc = dense_step(h, cb, d, dy, w, -1, true, lml_steps, m_f, dsm, P_f, dsP, fz == 1);
+            per_replay[fz] = h->launches - l0;    // kernels of one replay; nothing ran during the capture itself
+            h->launches = l0;
+            cudaError_t ce = cudaStreamEndCapture(st, &graph[fz]);
+            if (rc != TGP_OK) return rc;
+            TGP_CUDA(h, ce);
+            TGP_CUDA(h, cudaGraphInstantiate(&exec[fz], graph[fz], 0));
+        }
+        constexpr int64_t kPoll = 16;
+        long long* pss = (long long*)(h->pinned + 16);
+        *pss = -1;
+        bool frozen = false;
+        for (int64_t t = 0; t < T; ++t) {
+            TGP_CUDA(h, cudaGraphLaunch(exec[frozen ? 1 : 0], st));
+            h->launches += per_replay[frozen ? 1 : 0];
+            if (w.conv && !frozen && (t + 1) % kPoll == 0) {
+                TGP_CUDA(h, cudaMemcpyAsync(pss, w.ss_at, sizeof(long long), cudaMemcpyDeviceToHost, st));
+                TGP_CUDA(h, cudaStreamSynchronize(st));
+                h->d2h += 8;
+                frozen = *pss >= 0;
+            }
+        }
         TGP_CUDA(h, cudaStreamSynchronize(st));
-        cudaGraphExecDestroy(exec);
-        cudaGraphDestroy(graph);
+        for (int fz = 0; fz < 2; ++fz) {
+            if (exec[fz]) cudaGraphExecDestroy(exec[fz]);
+            if (graph[fz]) cudaGraphDestroy(graph[fz]);
+        }
     } else {
         // time-varying parameters: pointers depend on t, issue the step's launches directly. The custom kernels index
         // through the device counter, the cuBLAS calls through host-computed pointers.
@@ -318,6 +401,14 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
             const long long t = rev ? T - 1 - n : n;
             TGP_TRY(dense_step(h, cb, d, dy, w, t, false, lml_steps, m_f, dsm, P_f, dsP));
         }
+    }
+    if (w.conv && getenv("TGP_DEBUG")) {
+        double cv[4];
+        long long ss;
+        cudaMemcpy(cv, w.conv, sizeof cv, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&ss, w.ss_at, sizeof ss, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[tgp] dense f64: last max|dP| = %.3e, max|P| = %.3e, ratio %.3e, tol %.1e, converged at step %lld\n", cv[2], cv[3],
+                cv[3] > 0 ? cv[2] / cv[3] : 0.0, h->ss_tol, ss);
     }
     // results
     unsigned long long* perr = (unsigned long long*)h->pinned;

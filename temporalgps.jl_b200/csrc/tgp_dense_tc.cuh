@@ -148,16 +148,32 @@ __global__ void k_emit_state_pair(const double* __restrict__ m, Pair P, int D, d
     }
 }
 
+// End of a step: steady-state test on what the covariance epilogue measured (conv[0] = max |P_t - P_{t-1}|, conv[1] = max |P_t|),
+// then advance the device-side step counter. ss_at: -1 until the covariance recursion has converged, then the step index.
+__global__ void k_advance_conv(long long* step, long long delta, unsigned* conv, float tol, long long* ss_at) {
+    if (conv) {
+        const float d = __uint_as_float(conv[0]), a = __uint_as_float(conv[1]);
+        if (*ss_at < 0 && a > 0.f && d <= tol * a) *ss_at = *step;
+        conv[0] = 0u;
+        conv[1] = 0u;
+    }
+    *step += delta;
+}
+
 struct TcWs {
     TcOp At, Ht, Pa, Pb, W, Vt, V, B, Winv;
     double *S, *m, *mp, *r, *alpha, *lml;
     long long* step;
     unsigned long long* err;
+    unsigned* conv = nullptr;      // steady-state detection (time-invariant models only)
+    long long* ss_at = nullptr;
 };
 
 // One step. cur / nxt: covariance ping-pong (Pa, Pb); on return *cur holds the filtering covariance.
+// frozen: the covariance recursion has reached its fixed point (time-invariant model): P, S, U, Winv, B stay as the
+// last full step left them and only the mean / likelihood part of the step runs (same arithmetic, frozen gain).
 static int tc_step(tgp_ctx* h, const tgp_lgssm& d, const double* dy, TcWs& w, long long t, bool graph_mode, double* lml_steps, double* m_f,
-                   int64_t s_m, double* P_f, int64_t s_P) {
+                   int64_t s_m, double* P_f, int64_t s_P, bool frozen = false) {
     const int D = d.D, M = d.M;
     cudaStream_t st = h->stream;
     const long long tt = graph_mode ? 0 : t;
@@ -179,6 +195,7 @@ static int tc_step(tgp_ctx* h, const tgp_lgssm& d, const double* dy, TcWs& w, lo
     auto predict = [&]() -> int {
         TGP_TRY(gemv("tc:k_gemv_pair(predict mean)", w.At.pr, D, D, w.m, d.a, d.sa, nullptr, 0, 1.0, w.mp));
         TGP_CUDA(h, cudaMemcpyAsync(w.m, w.mp, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
+        if (frozen) return TGP_OK;
         tc::Epi e1;
         e1.Mx = D; e1.N = D; e1.out_hi = w.W.pr.hi(); e1.out_lo = w.W.pr.lo(); e1.ld_out = w.W.pr.ld;
         TGP_TRY(tc_gemm(h, "tc:gemm W=P'At", *P, w.At, D, e1));
@@ -189,7 +206,24 @@ static int tc_step(tgp_ctx* h, const tgp_lgssm& d, const double* dy, TcWs& w, lo
         std::swap(P, Pn);
         return TGP_OK;
     };
+    auto update_mean = [&]() -> int {   // residual, whitened residual, likelihood, mean
+        TGP_TRY(gemv("tc:k_gemv_pair(residual)", w.Ht.pr, D, M, w.m, dy, M, d.h, d.sh, -1.0, w.r));
+        TGP_TRY(gemv("tc:k_gemv_pair(alpha)", w.Winv.pr, M, M, w.r, nullptr, 0, nullptr, 0, 1.0, w.alpha));
+        TGP_K(h, "dense:k_lml");
+        k_lml<<<1, 256, 0, st>>>(w.S, w.alpha, M, lml_steps, w.lml, w.step);
+        TGP_LAUNCH_CHECK(h);
+        TGP_TRY(gemv("tc:k_gemv_pair(mean)", w.B.pr, M, D, w.alpha, w.m, 0, nullptr, 0, 1.0, w.mp));
+        TGP_CUDA(h, cudaMemcpyAsync(w.m, w.mp, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
+        if (m_f || P_f) {
+            const int nb = (int)std::min<long long>(((long long)D * D + D + 255) / 256, 1184);
+            TGP_K(h, "tc:k_emit_state_pair");
+            k_emit_state_pair<<<nb, 256, 0, st>>>(w.m, (rev ? w.Pb : w.Pa).pr, D, m_f, s_m, P_f, s_P, w.step);
+            TGP_LAUNCH_CHECK(h);
+        }
+        return TGP_OK;
+    };
     auto update = [&]() -> int {
+        if (frozen) return update_mean();
         tc::Epi e3;
         e3.Mx = D; e3.N = M; e3.out_hi = w.Vt.pr.hi(); e3.out_lo = w.Vt.pr.lo(); e3.ld_out = w.Vt.pr.ld;
         e3.outT_hi = w.V.pr.hi(); e3.outT_lo = w.V.pr.lo(); e3.ld_outT = w.V.pr.ld;
@@ -220,29 +254,16 @@ static int tc_step(tgp_ctx* h, const tgp_lgssm& d, const double* dy, TcWs& w, lo
         tc::Epi e6;
         e6.Mx = D; e6.N = D; e6.symmetric = 1; e6.alpha = -1.f; e6.cin_hi = P->pr.hi(); e6.cin_lo = P->pr.lo(); e6.ld_cin = P->pr.ld;
         e6.out_hi = Pn->pr.hi(); e6.out_lo = Pn->pr.lo(); e6.ld_out = Pn->pr.ld;
+        e6.conv = w.conv;
         TGP_TRY(tc_gemm(h, "tc:gemm P=Pp-B'B", w.B, w.B, M, e6));
         std::swap(P, Pn);
-        // residual, whitened residual, likelihood, mean
-        TGP_TRY(gemv("tc:k_gemv_pair(residual)", w.Ht.pr, D, M, w.m, dy, M, d.h, d.sh, -1.0, w.r));
-        TGP_TRY(gemv("tc:k_gemv_pair(alpha)", w.Winv.pr, M, M, w.r, nullptr, 0, nullptr, 0, 1.0, w.alpha));
-        TGP_K(h, "dense:k_lml");
-        k_lml<<<1, 256, 0, st>>>(w.S, w.alpha, M, lml_steps, w.lml, w.step);
-        TGP_LAUNCH_CHECK(h);
-        TGP_TRY(gemv("tc:k_gemv_pair(mean)", w.B.pr, M, D, w.alpha, w.m, 0, nullptr, 0, 1.0, w.mp));
-        TGP_CUDA(h, cudaMemcpyAsync(w.m, w.mp, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
-        if (m_f || P_f) {
-            const int nb = (int)std::min<long long>(((long long)D * D + D + 255) / 256, 1184);
-            TGP_K(h, "tc:k_emit_state_pair");
-            k_emit_state_pair<<<nb, 256, 0, st>>>(w.m, P->pr, D, m_f, s_m, P_f, s_P, w.step);
-            TGP_LAUNCH_CHECK(h);
-        }
-        return TGP_OK;
+        return update_mean();
     };
     if (!rev) { TGP_TRY(predict()); TGP_TRY(update()); }
     else      { TGP_TRY(update()); TGP_TRY(predict()); }
     // two swaps per step: the filtering / predicted covariance is back in w.Pa
     TGP_K(h, "dense:k_advance");
-    k_advance<<<1, 1, 0, st>>>(w.step, rev ? -1 : 1);
+    k_advance_conv<<<1, 1, 0, st>>>(w.step, rev ? -1 : 1, frozen ? nullptr : w.conv, fmaxf((float)h->ss_tol, 2e-6f), w.ss_at);
     TGP_LAUNCH_CHECK(h);
     return TGP_OK;
 }
@@ -289,6 +310,13 @@ int dense_filter_tc(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml
     TGP_TRY(dalloc(h, 1, &w.lml));
     TGP_TRY(dalloc(h, 1, &w.step));
     TGP_TRY(dalloc(h, 1, &w.err));
+    const bool ti = !(m->sA | m->sa | m->sQ | m->sH | m->sh | m->sR);
+    if (ti && h->algo == TGP_ALGO_AUTO) {
+        TGP_TRY(dalloc(h, 2, &w.conv));
+        TGP_TRY(dalloc(h, 1, &w.ss_at));
+        TGP_CUDA(h, cudaMemsetAsync(w.conv, 0, 2 * sizeof(unsigned), st));
+        TGP_CUDA(h, cudaMemsetAsync(w.ss_at, 0xFF, sizeof(long long), st));
+    }
     const int nb = (int)std::min<long long>(((long long)D * D + 255) / 256, 1184);
     TGP_K(h, "tc:k_to_pair");
     k_to_pair<<<nb, 256, 0, st>>>(d.A, D, D, 1, w.At.pr);
@@ -311,21 +339,43 @@ int dense_filter_tc(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml
     if (pan_bytes > 200 * 1024) return fail(h, TGP_EUNSUPPORTED, "observation dimension M=%d too large for the Cholesky panel kernel", M);
     if (pan_bytes > 48 * 1024) TGP_CUDA(h, cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pan_bytes));
     if (sizeof(double) * 8 * M > 48 * 1024) TGP_CUDA(h, cudaFuncSetAttribute(k_tri_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 8 * M)));
-    const bool ti = !(m->sA | m->sa | m->sQ | m->sH | m->sh | m->sR);
     if (ti && T >= 8 && !h->timing) {
-        cudaGraph_t graph;
-        cudaGraphExec_t exec;
+        // One step captured into a CUDA graph and replayed. Every kPoll steps the host looks at the steady-state word;
+        // once the covariance recursion has converged the remaining steps replay the mean-only graph.
+        cudaGraph_t graph[2] = {nullptr, nullptr};
+        cudaGraphExec_t exec[2] = {nullptr, nullptr};
+        int64_t per_replay[2] = {0, 0};
         TGP_CUDA(h, cudaStreamSynchronize(st));
-        TGP_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int rc = tc_step(h, d, dy, w, -1, true, lml_steps, m_f, dsm, P_f, dsP);
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (rc != TGP_OK) return rc;
-        TGP_CUDA(h, ce);
-        TGP_CUDA(h, cudaGraphInstantiate(&exec, graph, 0));
-        for (int64_t t = 0; t < T; ++t) TGP_CUDA(h, cudaGraphLaunch(exec, st));
+        for (int fz = 0; fz < (w.conv ? 2 : 1); ++fz) {
+            TGP_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int64_t l0 = h->launches;
+            int rc = tc_step(h, d, dy, w, -1, true, lml_steps, m_f, dsm, P_f, dsP, fz == 1);
+            per_replay[fz] = h->launches - l0;    // kernels of one replay; nothing ran during the capture itself
+            h->launches = l0;
+            cudaError_t ce = cudaStreamEndCapture(st, &graph[fz]);
+            if (rc != TGP_OK) return rc;
+            TGP_CUDA(h, ce);
+            TGP_CUDA(h, cudaGraphInstantiate(&exec[fz], graph[fz], 0));
+        }
+        constexpr int64_t kPoll = 16;
+        long long* pss = (long long*)(h->pinned + 16);
+        *pss = -1;
+        bool frozen = false;
+        for (int64_t t = 0; t < T; ++t) {
+            TGP_CUDA(h, cudaGraphLaunch(exec[frozen ? 1 : 0], st));
+            h->launches += per_replay[frozen ? 1 : 0];
+            if (w.conv && !frozen && (t + 1) % kPoll == 0) {
+                TGP_CUDA(h, cudaMemcpyAsync(pss, w.ss_at, sizeof(long long), cudaMemcpyDeviceToHost, st));
+                TGP_CUDA(h, cudaStreamSynchronize(st));
+                h->d2h += 8;
+                frozen = *pss >= 0;
+            }
+        }
         TGP_CUDA(h, cudaStreamSynchronize(st));
-        cudaGraphExecDestroy(exec);
-        cudaGraphDestroy(graph);
+        for (int fz = 0; fz < 2; ++fz) {
+            if (exec[fz]) cudaGraphExecDestroy(exec[fz]);
+            if (graph[fz]) cudaGraphDestroy(graph[fz]);
+        }
     } else {
         for (int64_t n = 0; n < T; ++n) {
             const long long t = rev ? T - 1 - n : n;

@@ -48,6 +48,9 @@ struct Epi {
     float* outT_hi = nullptr; float* outT_lo = nullptr; int ld_outT = 0;   // C' as a pair
     double* out_d = nullptr; int ld_outd = 0;                              // C in double
     int symmetric = 0;          // C is symmetric: only tiles touching the upper triangle are computed, (m <= n) is mirrored
+    // steady-state detection (nullable): conv[0] = max |C_new - C_old| and conv[1] = max |C_new| as float bits (atomicMax),
+    // C_old being what the pair output buffer held before this launch overwrote it (the previous step's covariance)
+    unsigned* conv = nullptr;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -193,6 +196,7 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int m = m0 + warp * 32 + lane;
         const bool row_ok = m < e.Mx;
+        float cmax_d = 0.f, cmax_a = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -229,6 +233,11 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     const float h = tf32_hi(x), l = x - h;
                     hi[c] = h; lo[c] = l;
                     if (e.out_hi) {
+                        if (e.conv) {
+                            const float old = e.out_hi[(size_t)m + (size_t)e.ld_out * n] + e.out_lo[(size_t)m + (size_t)e.ld_out * n];
+                            cmax_d = fmaxf(cmax_d, fabsf(x - old));
+                            cmax_a = fmaxf(cmax_a, fabsf(x));
+                        }
                         e.out_hi[(size_t)m + (size_t)e.ld_out * n] = h;      // lanes = consecutive m: coalesced
                         e.out_lo[(size_t)m + (size_t)e.ld_out * n] = l;
                     }
@@ -250,6 +259,14 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     }
                 }
             }
+        }
+        if (e.conv) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                cmax_d = fmaxf(cmax_d, __shfl_xor_sync(0xffffffffu, cmax_d, off));
+                cmax_a = fmaxf(cmax_a, __shfl_xor_sync(0xffffffffu, cmax_a, off));
+            }
+            if (lane == 0) { atomicMax(e.conv, __float_as_uint(cmax_d)); atomicMax(e.conv + 1, __float_as_uint(cmax_a)); }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

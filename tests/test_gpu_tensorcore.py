@@ -18,9 +18,11 @@ def test_tc_gemm_matches_numpy(handle, K, Mx, N):
     Y = rng.standard_normal((K, N)).astype(np.float32)
     C = handle.tc_gemm(X, Y)
     ref = X.astype(np.float64).T @ Y.astype(np.float64)
-    scale = np.sqrt(K)
-    err = np.max(np.abs(C - ref)) / scale
-    assert err < 5e-6, f"max abs err / sqrt(K) = {err:.3e}"      # one TF32 pass would give ~5e-4
+    # The tensor core truncates every partial product to the accumulator's precision, so the error of a 3xTF32 product grows
+    # linearly in K (measured on B200: 5e-7 K .. 1.2e-6 K for N(0,1) operands); a single TF32 pass would sit near 5e-4 sqrt(K).
+    err = np.max(np.abs(C - ref))
+    assert err < 2.5e-6 * K, f"max abs err = {err:.3e} (K = {K})"
+    assert err < 1e-4 * np.sqrt(K)
 
 
 @pytest.mark.parametrize("K,M", [(256, 768), (96, 200)])
@@ -31,7 +33,7 @@ def test_tc_gemm_symmetric_epilogue(handle, K, M):
     C = handle.tc_gemm(X, X, symmetric=True)
     assert np.array_equal(C, C.T)
     ref = X.astype(np.float64).T @ X.astype(np.float64)
-    assert np.max(np.abs(C - ref)) / np.sqrt(K) < 5e-6
+    assert np.max(np.abs(C - ref)) < 2.5e-6 * K
 
 
 def _separable(pkg, Nr, T, dtype):
@@ -83,3 +85,31 @@ def test_tc_path_time_varying_filter(pkg, handle, ordering):
     assert abs(lml - lmls_o.sum()) <= 1e-3 * abs(lmls_o.sum())
     np.testing.assert_allclose(ms, ms_o, rtol=1e-3, atol=1e-3)
     np.testing.assert_allclose(Ps, Ps_o, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(np.float64, 1e-9), (np.float32, 1e-3)])
+def test_dense_steady_state_switch(pkg, dtype, rtol):
+    """Time-invariant large-state model, long series: after the covariance recursion has converged (device-side test) the
+    library replays the mean-only step. Per-step lml must still match the sequential oracle, and the launch counter must
+    show that the covariance kernels stopped running."""
+    Nr, T = 16, 1800
+    fx, mo = _separable(pkg, Nr, T, dtype)
+    rng = np.random.default_rng(11)
+    y = O.sample_prior(mo, rng)
+    h = fx._handle()
+    c0 = h.counters()["launches"]
+    try:
+        lml, steps = pkg.lgssm.logpdf(fx.build_lgssm(), y, h, per_step=True)
+        c1 = h.counters()["launches"]
+        h.set_algo(pkg.TGP_ALGO_SCAN)          # disables the steady-state switch: every step runs the full update
+        lml_full, steps_full = pkg.lgssm.logpdf(fx.build_lgssm(), y, h, per_step=True)
+        c2 = h.counters()["launches"]
+    finally:
+        h.set_algo(pkg.TGP_ALGO_AUTO)
+        h.set_dense_math(pkg.lgssm.TGP_DENSE_F64)
+    ref_steps = O.logpdf_steps(mo, y)
+    atol = rtol * np.max(np.abs(ref_steps))        # lml_t crosses zero at this M: judge per-step values on the series' scale
+    np.testing.assert_allclose(steps_full, ref_steps, rtol=rtol, atol=atol)
+    np.testing.assert_allclose(steps, ref_steps, rtol=rtol, atol=atol)
+    assert abs(lml - ref_steps.sum()) <= max(rtol, 1e-6) * abs(ref_steps.sum())
+    assert (c1 - c0) < 0.8 * (c2 - c1), (c1 - c0, c2 - c1)
