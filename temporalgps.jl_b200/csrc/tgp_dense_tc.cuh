@@ -40,25 +40,31 @@ struct TcOp {             // a pair buffer and its TMA descriptors (box = 32 flo
     CUtensorMap m128, m64;
 };
 
-static int tc_make_op(tgp_ctx* h, int rows, int cols, TcOp* op) {
+// 2-D FP32 tensor map: `rows` contiguous elements per column, `ncols` columns `col_stride_bytes` apart, box 32 x box_cols, 128-byte swizzle.
+static int tc_encode_map(tgp_ctx* h, const float* base, int rows, long long ncols, size_t col_stride_bytes, unsigned box_cols, CUtensorMap* out) {
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return fail(h, TGP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)ncols};
+    const cuuint64_t strides[1] = {(cuuint64_t)col_stride_bytes};
+    const cuuint32_t es[2] = {1, 1};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, box_cols};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, TGP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows %d cols %lld)", (int)r, rows, ncols);
+    return TGP_OK;
+}
+
+// Zero-initialised pair buffer + its maps. extra_cols: additional zero columns behind each plane (a shifted read of the lo
+// plane at a negative column then lands in the zero padding of the hi plane).
+static int tc_make_op(tgp_ctx* h, int rows, int cols, TcOp* op, int extra_cols = 0) {
     Pair& p = op->pr;
     p.rows = rows; p.cols = cols;
     p.ld = (rows + 31) / 32 * 32;
-    p.cpad = (cols + 127) / 128 * 128;
+    p.cpad = (cols + extra_cols + 127) / 128 * 128;
     TGP_TRY(dalloc(h, p.floats(), &p.p));
     TGP_CUDA(h, cudaMemsetAsync(p.p, 0, p.floats() * sizeof(float), h->stream));
-    PFN_tmapEncodeTiled enc = tmap_encoder();
-    if (!enc) return fail(h, TGP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)(2 * p.cpad)};
-    const cuuint64_t strides[1] = {(cuuint64_t)p.ld * sizeof(float)};
-    const cuuint32_t es[2] = {1, 1};
-    for (int which = 0; which < 2; ++which) {
-        const cuuint32_t box[2] = {(cuuint32_t)tc::BK, which == 0 ? 128u : 64u};
-        CUresult r = enc(which == 0 ? &op->m128 : &op->m64, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.p, dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(h, TGP_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows %d cols %d)", (int)r, rows, cols);
-    }
+    TGP_TRY(tc_encode_map(h, p.p, rows, 2LL * p.cpad, (size_t)p.ld * sizeof(float), 128u, &op->m128));
+    TGP_TRY(tc_encode_map(h, p.p, rows, 2LL * p.cpad, (size_t)p.ld * sizeof(float), 64u, &op->m64));
     return TGP_OK;
 }
 
@@ -68,12 +74,16 @@ static int tc_prepare(tgp_ctx* h) {
     return TGP_OK;
 }
 
-// C = alpha X' Y (+ additive term), tile 128 x 64.
-static int tc_gemm(tgp_ctx* h, const char* name, const TcOp& X, const TcOp& Y, int K, const tc::Epi& e) {
+// C = alpha X' Y (+ additive terms), tile 128 x 64. Y may continue into a second tensor Y2 from contraction index k_switch on.
+static int tc_gemm(tgp_ctx* h, const char* name, const TcOp& X, const TcOp& Y, int K, const tc::Epi& e, const TcOp* Y2 = nullptr, int k_switch_elems = 0,
+                   int y_col_shift = 0) {
     constexpr int BN = 64;
     dim3 grid((e.Mx + tc::BM - 1) / tc::BM, (e.N + BN - 1) / BN);
+    tc::Src src;
+    src.K = K; src.lo_col_x = X.pr.cpad; src.lo_col_y = Y.pr.cpad; src.y_col_shift = y_col_shift;
+    if (Y2) { src.lo_col_y2 = Y2->pr.cpad; src.k_switch = k_switch_elems / tc::BK; }
     TGP_K(h, name);
-    tc::k_tc_gemm_tn<BN><<<grid, tc::kThreads, tc::Cfg<BN>::kSmem, h->stream>>>(X.m128, Y.m64, K, X.pr.cpad, Y.pr.cpad, e);
+    tc::k_tc_gemm_tn<BN><<<grid, tc::kThreads, tc::Cfg<BN>::kSmem, h->stream>>>(X.m128, Y.m64, Y2 ? Y2->m64 : Y.m64, src, e);
     TGP_LAUNCH_CHECK(h);
     return TGP_OK;
 }
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(256) k_gemv_pair(Pair X, int K, int N, const d
 
 // Winv = U^-1 for the upper Cholesky factor U (M x M, double, column-major, upper triangle read). One warp per ROW j of
 // Winv: z' U = e_j'  <=>  z_i = (delta_ij - sum_{j <= k < i} U[k, i] z_k) / U[i, i], i = j..M-1 (column i of U is contiguous).
-__global__ void __launch_bounds__(256) k_tri_inv(const double* __restrict__ U, int M, Pair Winv) {
+__global__ void __launch_bounds__(256) k_tri_inv(const double* __restrict__ U, int M, Pair Winv, Pair WinvT) {
     extern __shared__ double zbuf[];                 // 8 warps x M
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * 8 + warp;
@@ -134,6 +144,8 @@ __global__ void __launch_bounds__(256) k_tri_inv(const double* __restrict__ U, i
         const float hi = tc::tf32_hi(x);
         Winv.hi()[(size_t)j + (size_t)Winv.ld * i] = hi;
         Winv.lo()[(size_t)j + (size_t)Winv.ld * i] = x - hi;
+        WinvT.hi()[(size_t)i + (size_t)WinvT.ld * j] = hi;      // the transpose (lower triangular), used by the time-blocked phase
+        WinvT.lo()[(size_t)i + (size_t)WinvT.ld * j] = x - hi;
     }
 }
 
@@ -161,7 +173,7 @@ __global__ void k_advance_conv(long long* step, long long delta, unsigned* conv,
 }
 
 struct TcWs {
-    TcOp At, Ht, Pa, Pb, W, Vt, V, B, Winv;
+    TcOp At, Ht, Pa, Pb, W, Vt, V, B, Winv, WinvT;
     double *S, *m, *mp, *r, *alpha, *lml;
     long long* step;
     unsigned long long* err;
@@ -246,7 +258,7 @@ static int tc_step(tgp_ctx* h, const tgp_lgssm& d, const double* dy, TcWs& w, lo
             }
         }
         TGP_K(h, "tc:k_tri_inv");
-        k_tri_inv<<<(M + 7) / 8, 256, sizeof(double) * 8 * M, st>>>(w.S, M, w.Winv.pr);
+        k_tri_inv<<<(M + 7) / 8, 256, sizeof(double) * 8 * M, st>>>(w.S, M, w.Winv.pr, w.WinvT.pr);
         TGP_LAUNCH_CHECK(h);
         tc::Epi e5;
         e5.Mx = M; e5.N = D; e5.out_hi = w.B.pr.hi(); e5.out_lo = w.B.pr.lo(); e5.ld_out = w.B.pr.ld;
@@ -264,6 +276,237 @@ static int tc_step(tgp_ctx* h, const tgp_lgssm& d, const double* dy, TcWs& w, lo
     // two swaps per step: the filtering / predicted covariance is back in w.Pa
     TGP_K(h, "dense:k_advance");
     k_advance_conv<<<1, 1, 0, st>>>(w.step, rev ? -1 : 1, frozen ? nullptr : w.conv, fmaxf((float)h->ss_tol, 2e-6f), w.ss_at);
+    TGP_LAUNCH_CHECK(h);
+    return TGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Time-blocked steady phase (Forward ordering, log-likelihood only). Once P, S, U, B are frozen the step is the constant
+// affine map of z_t = [m_t; alpha_t]:
+//     [m_t; alpha_t] = G [m_{t-1}; y_t] + g,    G = [[Abar, Kbar], [W1, W2]],
+//     W2 = Winv', W1 = -Winv' H A, Kbar = B' Winv', Abar = A + B' W1, g = [a + B' w0; w0], w0 = -Winv'(h + H a)
+// (the same arithmetic as the mean part of the step, lml_t = -(M log 2pi + logdet S + alpha_t'alpha_t)/2). The n remaining
+// steps are cut into nb blocks of kTbL consecutive steps and ALL blocks advance together, one position j per launch:
+//     pass 1   S_{j+1} = [Abar Kbar] [S_j; Y_j] + c      S: D x nb (one column per block), Y_j: M x nb (a strided view of y)
+//              from zero states -> the zero-state response of every block;
+//     prefix   X_b = Abar^L X_{b-1} + Z_b by recursive doubling over the blocks (log2 nb products with Abar^(L 2^k));
+//     pass 2   the same recursion from the true block-initial states, the alpha rows going straight into per-step sums of squares.
+// Every product is a (D + M) x (D + M) x nb contraction on the tensor cores (k_tc_gemm_tn): the sequential chain of T GEMVs
+// becomes ~2 kTbL + 2 log2(nb) large GEMMs.
+constexpr int kTbL = 64;
+
+__global__ void k_y_to_pair(const double* __restrict__ y, long long n, int M, Pair Y) {   // column t of Y = y_t (t < n)
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n * M; e += (long long)gridDim.x * blockDim.x) {
+        const long long t = e / M;
+        const int i = (int)(e % M);
+        const float x = (float)y[e];
+        const float hi = tc::tf32_hi(x);
+        Y.hi()[(size_t)i + (size_t)Y.ld * t] = hi;
+        Y.lo()[(size_t)i + (size_t)Y.ld * t] = x - hi;
+    }
+}
+// dst[r0 + i, c0 + j] = src[i, j]
+__global__ void k_copy_pair_block(Pair src, int rows, int cols, Pair dst, int r0, int c0) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)rows * cols; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % rows), j = (int)(e / rows);
+        const size_t so = (size_t)i + (size_t)src.ld * j, dn = (size_t)(r0 + i) + (size_t)dst.ld * (c0 + j);
+        dst.hi()[dn] = src.hi()[so];
+        dst.lo()[dn] = src.lo()[so];
+    }
+}
+// dst[:, 0] = v (double vector), dst[:, b] = src[:, b - 1] for 1 <= b < nb (src nullable: only column 0 is set)
+__global__ void k_block_states(const double* __restrict__ v, Pair src, int D, long long nb, Pair dst) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)D * nb; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e % D);
+        const long long b = e / D;
+        float x;
+        if (b == 0) x = (float)v[i];
+        else if (src.p) x = src.hi()[(size_t)i + (size_t)src.ld * (b - 1)] + src.lo()[(size_t)i + (size_t)src.ld * (b - 1)];
+        else continue;
+        const float hi = tc::tf32_hi(x);
+        dst.hi()[(size_t)i + (size_t)dst.ld * b] = hi;
+        dst.lo()[(size_t)i + (size_t)dst.ld * b] = x - hi;
+    }
+}
+__global__ void k_make_bias(const double* __restrict__ c, int D, const double* __restrict__ w0, int M, float* __restrict__ bias) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D + M; i += gridDim.x * blockDim.x) bias[i] = (float)(i < D ? c[i] : w0[i - D]);
+}
+// lml_t = -(M log 2pi + 2 sum log U_ii + csq_t)/2 for the n blocked steps; total added to *lml_total. One CTA.
+__global__ void __launch_bounds__(1024) k_lml_blocked(const double* __restrict__ U, int M, const double* __restrict__ csq, long long n,
+                                                      double* __restrict__ lml_steps, double* __restrict__ lml_total) {
+    __shared__ double sh[1024];
+    __shared__ double s_ld;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < M; i += 1024) s += 2.0 * log(U[i + (size_t)M * i]);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) { if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off]; __syncthreads(); }
+    if (threadIdx.x == 0) s_ld = sh[0];
+    __syncthreads();
+    const double c0 = M * kLog2PiD + s_ld;
+    double acc = 0.0;
+    for (long long t = threadIdx.x; t < n; t += 1024) {
+        const double l = -0.5 * (c0 + csq[t]);
+        if (lml_steps) lml_steps[t] = l;
+        acc += l;
+    }
+    __syncthreads();
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) { if (threadIdx.x < off) sh[threadIdx.x] += sh[threadIdx.x + off]; __syncthreads(); }
+    if (threadIdx.x == 0) *lml_total += sh[0];
+}
+
+static tc::Epi epi_out(int Mx, int N, const TcOp& out) {
+    tc::Epi e;
+    e.Mx = Mx; e.N = N; e.out_hi = out.pr.hi(); e.out_lo = out.pr.lo(); e.ld_out = out.pr.ld;
+    return e;
+}
+
+// t0: index of the first blocked step, n: number of steps. w.m holds the filtered mean of step t0 - 1; w.S, w.B, w.Winv(T) are frozen.
+static int tc_steady_blocked(tgp_ctx* h, const tgp_lgssm& d, const double* dy, TcWs& w, int64_t t0, int64_t n, double* lml_steps) {
+    const int D = d.D, M = d.M, L = kTbL;
+    const int Dp = (D + 31) / 32 * 32;                    // the state part of the stacked contraction index, padded to whole k-blocks
+    const long long nb = (n + L - 1) / L;
+    cudaStream_t st = h->stream;
+    auto grid1d = [](long long work) { return (int)std::min<long long>((work + 255) / 256, 2368); };
+
+    // ---- constants ---------------------------------------------------------------------------------------------------------
+    TcOp Ap, HA, W1, Ab, Abt, Kb, Gt, P2, Pt2;
+    TGP_TRY(tc_make_op(h, D, D, &Ap));
+    TGP_TRY(tc_make_op(h, M, D, &HA));
+    TGP_TRY(tc_make_op(h, M, D, &W1));
+    TGP_TRY(tc_make_op(h, D, D, &Ab));
+    TGP_TRY(tc_make_op(h, D, D, &Abt));
+    TGP_TRY(tc_make_op(h, D, M, &Kb));
+    TGP_TRY(tc_make_op(h, Dp + M, D + M, &Gt));
+    TGP_TRY(tc_make_op(h, D, D, &P2));
+    TGP_TRY(tc_make_op(h, D, D, &Pt2));
+    TGP_K(h, "tc:k_to_pair");
+    k_to_pair<<<grid1d((long long)D * D), 256, 0, st>>>(d.A, D, D, 0, Ap.pr);
+    TGP_LAUNCH_CHECK(h);
+    TGP_TRY(tc_gemm(h, "tc:gemm HA=Ht'A", w.Ht, Ap, D, epi_out(M, D, HA)));
+    {   // W1 = -Winv' HA, and W1' into G' (rows = state in, columns D.. = alpha out)
+        tc::Epi e = epi_out(M, D, W1);
+        e.alpha = -1.f;
+        e.outT_hi = Gt.pr.hi() + (size_t)Gt.pr.ld * D; e.outT_lo = Gt.pr.lo() + (size_t)Gt.pr.ld * D; e.ld_outT = Gt.pr.ld;
+        TGP_TRY(tc_gemm(h, "tc:gemm W1=-Winv'HA", w.Winv, HA, M, e));
+    }
+    {   // Abar = A + B' W1 (and its transpose)
+        tc::Epi e = epi_out(D, D, Ab);
+        e.cin_hi = Ap.pr.hi(); e.cin_lo = Ap.pr.lo(); e.ld_cin = Ap.pr.ld;
+        e.outT_hi = Abt.pr.hi(); e.outT_lo = Abt.pr.lo(); e.ld_outT = Abt.pr.ld;
+        TGP_TRY(tc_gemm(h, "tc:gemm Abar=A+B'W1", w.B, W1, M, e));
+    }
+    {   // Kbar = B' Winv', and Kbar' into G' (rows Dp.. = observation in, columns 0..D = state out)
+        tc::Epi e = epi_out(D, M, Kb);
+        e.outT_hi = Gt.pr.hi() + Dp; e.outT_lo = Gt.pr.lo() + Dp; e.ld_outT = Gt.pr.ld;
+        TGP_TRY(tc_gemm(h, "tc:gemm Kbar=B'Winv'", w.B, w.WinvT, M, e));
+    }
+    TGP_K(h, "tc:k_copy_pair_block");
+    k_copy_pair_block<<<grid1d((long long)D * D), 256, 0, st>>>(Abt.pr, D, D, Gt.pr, 0, 0);
+    TGP_LAUNCH_CHECK(h);
+    TGP_K(h, "tc:k_copy_pair_block");
+    k_copy_pair_block<<<grid1d((long long)M * M), 256, 0, st>>>(w.Winv.pr, M, M, Gt.pr, Dp, D);
+    TGP_LAUNCH_CHECK(h);
+    double *t1, *w0, *cbar, *csq;
+    float* bias;
+    TGP_TRY(dalloc(h, M, &t1));
+    TGP_TRY(dalloc(h, M, &w0));
+    TGP_TRY(dalloc(h, D, &cbar));
+    TGP_TRY(dalloc(h, D + M, &bias));
+    TGP_TRY(dalloc(h, (size_t)nb * L, &csq));
+    TGP_CUDA(h, cudaMemsetAsync(csq, 0, sizeof(double) * nb * L, st));
+    auto gemv = [&](const Pair& X, int K, int N, const double* v, const double* b1, double sign, double* out) -> int {
+        TGP_K(h, "tc:k_gemv_pair(setup)");
+        k_gemv_pair<<<(N * 32 + 255) / 256, 256, 0, st>>>(X, K, N, v, b1, 0, nullptr, 0, sign, out, w.step);
+        TGP_LAUNCH_CHECK(h);
+        return TGP_OK;
+    };
+    TGP_TRY(gemv(w.Ht.pr, D, M, d.a, d.h, 1.0, t1));          // t1 = h + H a
+    TGP_TRY(gemv(w.Winv.pr, M, M, t1, nullptr, -1.0, w0));    // w0 = -Winv' t1
+    TGP_TRY(gemv(w.B.pr, M, D, w0, d.a, 1.0, cbar));          // c = a + B' w0
+    TGP_K(h, "tc:k_make_bias");
+    k_make_bias<<<(D + M + 255) / 256, 256, 0, st>>>(cbar, D, w0, M, bias);
+    TGP_LAUNCH_CHECK(h);
+
+    // ---- observations as a pair tensor and its kTbL strided views (position j of every block) ------------------------------
+    const long long nbp = (nb + 127) / 128 * 128;
+    Pair Yp;
+    Yp.rows = M; Yp.cols = (int)std::min<long long>(nbp * L, 0x7fffffff); Yp.ld = (M + 31) / 32 * 32; Yp.cpad = (int)(nbp * L);
+    if (nbp * L > 0x7fffffffLL) return fail(h, TGP_EUNSUPPORTED, "series too long for the time-blocked steady phase");
+    TGP_TRY(dalloc(h, Yp.floats(), &Yp.p));
+    TGP_CUDA(h, cudaMemsetAsync(Yp.p, 0, Yp.floats() * sizeof(float), st));
+    TGP_K(h, "tc:k_y_to_pair");
+    k_y_to_pair<<<grid1d(n * M), 256, 0, st>>>(dy + t0 * M, n, M, Yp);
+    TGP_LAUNCH_CHECK(h);
+    std::vector<TcOp> yv(L);
+    for (int j = 0; j < L; ++j) {
+        yv[j].pr = Yp;
+        yv[j].pr.cpad = (int)nbp;        // lo plane of the view: nbp view-columns behind the hi plane
+        TGP_TRY(tc_encode_map(h, Yp.p + (size_t)Yp.ld * j, M, 2 * nbp, (size_t)Yp.ld * L * sizeof(float), 64u, &yv[j].m64));
+    }
+
+    // ---- pass 1: zero-state response of every block (block 0 starts from the current mean) ---------------------------------
+    TcOp Sa, Sb, Xa, Xb;
+    TGP_TRY(tc_make_op(h, D, (int)nb, &Sa));
+    TGP_TRY(tc_make_op(h, D, (int)nb, &Sb));
+    TGP_TRY(tc_make_op(h, D, (int)nb, &Xa, (int)nb));
+    TGP_TRY(tc_make_op(h, D, (int)nb, &Xb, (int)nb));
+    Pair none;
+    TGP_K(h, "tc:k_block_states");
+    k_block_states<<<grid1d(D), 256, 0, st>>>(w.m, none, D, 1, Sa.pr);
+    TGP_LAUNCH_CHECK(h);
+    TcOp* Sc = &Sa;
+    TcOp* Sn = &Sb;
+    for (int j = 0; j < L; ++j) {
+        tc::Epi e = epi_out(D, (int)nb, j == L - 1 ? Xa : *Sn);
+        e.row_bias = bias;
+        TGP_TRY(tc_gemm(h, "tc:gemm blocked pass 1", Gt, *Sc, Dp + M, e, &yv[j], Dp));
+        std::swap(Sc, Sn);
+    }
+    // ---- prefix over blocks by recursive doubling: X_b += P_k X_{b - 2^k}, P_0 = Abar^L, P_{k+1} = P_k^2 -------------------------
+    TcOp* P = &Ab;      // (P, Pt) -> (P^2, (P^2)')
+    TcOp* Pt = &Abt;
+    TcOp* Q = &P2;
+    TcOp* Qt = &Pt2;
+    auto square = [&]() -> int {
+        tc::Epi e = epi_out(D, D, *Qt);
+        e.outT_hi = Q->pr.hi(); e.outT_lo = Q->pr.lo(); e.ld_outT = Q->pr.ld;
+        TGP_TRY(tc_gemm(h, "tc:gemm power", *P, *Pt, D, e));
+        std::swap(P, Q);
+        std::swap(Pt, Qt);
+        return TGP_OK;
+    };
+    // (Abar / Abar' may be overwritten by the squarings: G' holds its own copy)
+    for (int s2 = 1; s2 < L; s2 <<= 1) TGP_TRY(square());
+    TcOp* Xc = &Xa;
+    TcOp* Xn = &Xb;
+    for (long long sh = 1; sh < nb; sh <<= 1) {
+        tc::Epi e = epi_out(D, (int)nb, *Xn);
+        e.cin_hi = Xc->pr.hi(); e.cin_lo = Xc->pr.lo(); e.ld_cin = Xc->pr.ld;
+        TGP_TRY(tc_gemm(h, "tc:gemm blocked prefix", *Pt, *Xc, D, e, nullptr, 0, (int)-sh));
+        std::swap(Xc, Xn);
+        if ((sh << 1) < nb) TGP_TRY(square());
+    }
+    // ---- pass 2: from the true block-initial states; alpha rows -> per-step sums of squares ---------------------------------
+    TGP_K(h, "tc:k_block_states");
+    k_block_states<<<grid1d((long long)D * nb), 256, 0, st>>>(w.m, Xc->pr, D, nb, Sa.pr);
+    TGP_LAUNCH_CHECK(h);
+    Sc = &Sa;
+    Sn = &Sb;
+    for (int j = 0; j < L && j < n; ++j) {
+        const long long nvalid = (n - j + L - 1) / L;      // blocks that have a step at position j
+        tc::Epi e = epi_out(D + M, (int)nvalid, *Sn);
+        e.row_bias = bias;
+        e.split_row = D;
+        e.colsq = csq + j;
+        e.colsq_stride = L;
+        TGP_TRY(tc_gemm(h, "tc:gemm blocked pass 2", Gt, *Sc, Dp + M, e, &yv[j], Dp));
+        std::swap(Sc, Sn);
+    }
+    TGP_K(h, "tc:k_lml_blocked");
+    k_lml_blocked<<<1, 1024, 0, st>>>(w.S, M, csq, n, lml_steps ? lml_steps + t0 : nullptr, w.lml);
     TGP_LAUNCH_CHECK(h);
     return TGP_OK;
 }
@@ -302,6 +545,7 @@ int dense_filter_tc(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml
     TGP_TRY(tc_make_op(h, M, D, &w.V));
     TGP_TRY(tc_make_op(h, M, D, &w.B));
     TGP_TRY(tc_make_op(h, M, M, &w.Winv));
+    TGP_TRY(tc_make_op(h, M, M, &w.WinvT));
     TGP_TRY(dalloc(h, (size_t)M * M, &w.S));
     TGP_TRY(dalloc(h, D, &w.m));
     TGP_TRY(dalloc(h, D, &w.mp));
@@ -369,6 +613,11 @@ int dense_filter_tc(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml
                 TGP_CUDA(h, cudaStreamSynchronize(st));
                 h->d2h += 8;
                 frozen = *pss >= 0;
+                // log-likelihood only, Forward ordering, enough steps left: the rest of the series advances block-parallel
+                if (frozen && !rev && !m_f && !P_f && T - (t + 1) >= 8 * kTbL && h->chunk != 1) {
+                    TGP_TRY(tc_steady_blocked(h, d, dy, w, t + 1, T - (t + 1), lml_steps));
+                    break;
+                }
             }
         }
         TGP_CUDA(h, cudaStreamSynchronize(st));

@@ -51,6 +51,12 @@ struct Epi {
     // steady-state detection (nullable): conv[0] = max |C_new - C_old| and conv[1] = max |C_new| as float bits (atomicMax),
     // C_old being what the pair output buffer held before this launch overwrote it (the previous step's covariance)
     unsigned* conv = nullptr;
+    // time-blocked mean recursion (nullable): per-row additive constant; rows >= split_row are not stored but their squares
+    // are summed per column into colsq[n * colsq_stride] (double atomics)
+    const float* row_bias = nullptr;
+    int split_row = 1 << 30;
+    double* colsq = nullptr;
+    long long colsq_stride = 0;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,9 +127,19 @@ struct Cfg {
     static_assert((kSplit + 1) * BN <= kTmemCols, "accumulators exceed TMEM");
 };
 
+// Operand sources of one launch. The Y operand may be the CONCATENATION along K of two tensors (k-blocks < k_switch from tmY,
+// the rest from tmY2): the time-blocked mean recursion multiplies [state; observations] without materialising the stack.
+struct Src {
+    int K = 0;
+    int lo_col_x = 0, lo_col_y = 0, lo_col_y2 = 0;   // column offset of the lo plane inside each pair tensor
+    int k_switch = 1 << 30;                           // first k-block read from tmY2 (at K coordinate (kb - k_switch) * BK)
+    int y_col_shift = 0;                              // added to the column coordinate of tmY (negative columns read as zero)
+};
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, int K, int lo_col_x, int lo_col_y, Epi e) {
+k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmY2,
+             const Src src, const Epi e) {
     using C = Cfg<BN>;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     if (e.symmetric && m0 >= n0 + BN) return;   // tile strictly below the diagonal: produced by its mirror
@@ -134,7 +150,7 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     uint64_t* accum = empty + C::kStages;
     uint32_t* tmem_slot = (uint32_t*)(accum + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nk = (K + BK - 1) / BK;
+    const int nk = (src.K + BK - 1) / BK;
 
     if (warp == 4 && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -159,9 +175,14 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 uint8_t* st = smem + s * C::kStageBytes;
                 mbar_expect_tx(&full[s], C::kStageBytes);
                 tma_load_2d(st, &tmX, &full[s], kb * BK, m0);
-                tma_load_2d(st + C::kXBytes, &tmX, &full[s], kb * BK, lo_col_x + m0);
-                tma_load_2d(st + 2 * C::kXBytes, &tmY, &full[s], kb * BK, n0);
-                tma_load_2d(st + 2 * C::kXBytes + C::kYBytes, &tmY, &full[s], kb * BK, lo_col_y + n0);
+                tma_load_2d(st + C::kXBytes, &tmX, &full[s], kb * BK, src.lo_col_x + m0);
+                if (kb < src.k_switch) {
+                    tma_load_2d(st + 2 * C::kXBytes, &tmY, &full[s], kb * BK, n0 + src.y_col_shift);
+                    tma_load_2d(st + 2 * C::kXBytes + C::kYBytes, &tmY, &full[s], kb * BK, src.lo_col_y + n0 + src.y_col_shift);
+                } else {
+                    tma_load_2d(st + 2 * C::kXBytes, &tmY2, &full[s], (kb - src.k_switch) * BK, n0);
+                    tma_load_2d(st + 2 * C::kXBytes + C::kYBytes, &tmY2, &full[s], (kb - src.k_switch) * BK, src.lo_col_y2 + n0);
+                }
             }
         }
     } else if (warp == 5) {
@@ -196,6 +217,8 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int m = m0 + warp * 32 + lane;
         const bool row_ok = m < e.Mx;
+        const bool row_sq = row_ok && m >= e.split_row;       // rows whose squares are summed per column instead of being stored
+        const float bias = (row_ok && e.row_bias) ? e.row_bias[m] : 0.f;
         float cmax_d = 0.f, cmax_a = 0.f;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -212,39 +235,78 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 #pragma unroll
                 for (int c = 0; c < 32; ++c) acc[c] += __uint_as_float(v[c]);
             }
-            if (!row_ok) continue;
+            const int nb0 = n0 + c0;
+            if (nb0 >= e.N) break;                               // uniform: the whole chunk is outside C
+            // ---- phase A: every global LOAD of the chunk (independent, so they overlap) --------------------------------
+            float add[32], old[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { add[c] = 0.f; old[c] = 0.f; }
+            const bool store_row = row_ok && !row_sq;
+            if (store_row && e.cin_hi) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int n = nb0 + c;
+                    if (n < e.N && (!e.symmetric || m <= n))
+                        add[c] = e.cin_hi[(size_t)m + (size_t)e.ld_cin * n] + e.cin_lo[(size_t)m + (size_t)e.ld_cin * n];
+                }
+            }
+            if (store_row && e.conv && e.out_hi) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int n = nb0 + c;
+                    if (n < e.N && (!e.symmetric || m <= n))
+                        old[c] = e.out_hi[(size_t)m + (size_t)e.ld_out * n] + e.out_lo[(size_t)m + (size_t)e.ld_out * n];
+                }
+            }
+            // ---- phase B: values ------------------------------------------------------------------------------------------
             float hi[32], lo[32];
-            bool any = false;
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                const int n = n0 + c0 + c;
-                float x = e.alpha * acc[c];
-                const bool ok = n < e.N && (!e.symmetric || m <= n);
-                if (ok) {
-                    if (e.cin_hi) x += e.cin_hi[(size_t)m + (size_t)e.ld_cin * n] + e.cin_lo[(size_t)m + (size_t)e.ld_cin * n];
+                const int n = nb0 + c;
+                float x = fmaf(e.alpha, acc[c], add[c]) + bias;
+                if (row_ok && (e.cin_d || e.cin_diag) && n < e.N) {
                     double xd = (double)x;
                     if (e.cin_d) xd += e.cin_d[(size_t)m + (size_t)e.ld_cind * n];
                     if (e.cin_diag && m == n) xd += e.cin_diag[(size_t)e.diag_stride * m];
-                    if (e.cin_d || e.cin_diag) x = (float)xd;
-                    if (e.out_d) {
+                    if (e.out_d && (!e.symmetric || m <= n)) {
                         e.out_d[(size_t)m + (size_t)e.ld_outd * n] = xd;
                         if (e.symmetric) e.out_d[(size_t)n + (size_t)e.ld_outd * m] = xd;
                     }
-                    const float h = tf32_hi(x), l = x - h;
-                    hi[c] = h; lo[c] = l;
-                    if (e.out_hi) {
-                        if (e.conv) {
-                            const float old = e.out_hi[(size_t)m + (size_t)e.ld_out * n] + e.out_lo[(size_t)m + (size_t)e.ld_out * n];
-                            cmax_d = fmaxf(cmax_d, fabsf(x - old));
-                            cmax_a = fmaxf(cmax_a, fabsf(x));
-                        }
-                        e.out_hi[(size_t)m + (size_t)e.ld_out * n] = h;      // lanes = consecutive m: coalesced
-                        e.out_lo[(size_t)m + (size_t)e.ld_out * n] = l;
-                    }
-                    any = true;
-                } else { hi[c] = 0.f; lo[c] = 0.f; }
+                    x = (float)xd;
+                } else if (row_ok && e.out_d && n < e.N && (!e.symmetric || m <= n)) {
+                    e.out_d[(size_t)m + (size_t)e.ld_outd * n] = (double)x;
+                    if (e.symmetric) e.out_d[(size_t)n + (size_t)e.ld_outd * m] = (double)x;
+                }
+                acc[c] = x;
+                hi[c] = tf32_hi(x);
+                lo[c] = x - hi[c];
             }
-            if (!any) continue;
+            // ---- column sums of squares of the rows >= split_row (whitened residuals of the time-blocked recursion) -------
+            if (e.colsq) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    float q = (row_sq && nb0 + c < e.N) ? acc[c] * acc[c] : 0.f;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+                    if (lane == 0 && nb0 + c < e.N && m0 + warp * 32 + 31 >= e.split_row) atomicAdd(e.colsq + (size_t)(nb0 + c) * e.colsq_stride, (double)q);
+                }
+            }
+            if (!store_row) continue;
+            // ---- phase C: stores ------------------------------------------------------------------------------------------
+            if (e.out_hi) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int n = nb0 + c;
+                    if (n < e.N && (!e.symmetric || m <= n)) {
+                        if (e.conv) {
+                            cmax_d = fmaxf(cmax_d, fabsf(acc[c] - old[c]));
+                            cmax_a = fmaxf(cmax_a, fabsf(acc[c]));
+                        }
+                        e.out_hi[(size_t)m + (size_t)e.ld_out * n] = hi[c];      // lanes = consecutive m: coalesced
+                        e.out_lo[(size_t)m + (size_t)e.ld_out * n] = lo[c];
+                    }
+                }
+            }
             // transposed copy (C'), or the mirror image of a symmetric C: this thread's 32 values are contiguous there
             float* th = e.symmetric ? e.out_hi : e.outT_hi;
             float* tl = e.symmetric ? e.out_lo : e.outT_lo;
@@ -252,7 +314,7 @@ k_tc_gemm_tn(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             if (th) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
-                    const int n = n0 + c0 + c;
+                    const int n = nb0 + c;
                     if (n < e.N && (!e.symmetric || m < n)) {
                         th[(size_t)n + (size_t)ldt * m] = hi[c];
                         tl[(size_t)n + (size_t)ldt * m] = lo[c];

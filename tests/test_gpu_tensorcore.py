@@ -113,3 +113,30 @@ def test_dense_steady_state_switch(pkg, dtype, rtol):
     np.testing.assert_allclose(steps, ref_steps, rtol=rtol, atol=atol)
     assert abs(lml - ref_steps.sum()) <= max(rtol, 1e-6) * abs(ref_steps.sum())
     assert (c1 - c0) < 0.8 * (c2 - c1), (c1 - c0, c2 - c1)
+
+
+def test_tc_time_blocked_steady_phase(pkg):
+    """FP32-storage path, log-likelihood only: after the switch the remaining steps advance block-parallel on the tensor cores
+    (tc_steady_blocked: 64-step blocks, two passes + a doubling prefix over blocks). Per-step lml must agree with the
+    sequential frozen replay of the same library (TGP_OPT_CHUNK = 1 disables the blocking) and with the FP64 oracle."""
+    Nr, T = 20, 3000        # D = 60 (not a multiple of 32: exercises the padded stack), M = 20; ragged last block
+    fx, mo = _separable(pkg, Nr, T, np.float32)
+    rng = np.random.default_rng(12)
+    y = O.sample_prior(mo, rng)
+    h = fx._handle()
+    try:
+        c0 = h.counters()["launches"]
+        lml_b, steps_b = pkg.lgssm.logpdf(fx.build_lgssm(), y, h, per_step=True)
+        c1 = h.counters()["launches"]
+        h.set_chunk(1)
+        lml_s, steps_s = pkg.lgssm.logpdf(fx.build_lgssm(), y, h, per_step=True)
+        c2 = h.counters()["launches"]
+    finally:
+        h.set_chunk(0)
+        h.set_dense_math(pkg.lgssm.TGP_DENSE_F64)
+    ref_steps = O.logpdf_steps(mo, y)
+    scale = np.max(np.abs(ref_steps))
+    np.testing.assert_allclose(steps_b, steps_s, rtol=2e-4, atol=2e-4 * scale)
+    np.testing.assert_allclose(steps_b, ref_steps, rtol=1e-3, atol=1e-3 * scale)
+    assert abs(lml_b - ref_steps.sum()) <= 1e-4 * abs(ref_steps.sum())
+    assert (c1 - c0) < 0.5 * (c2 - c1), (c1 - c0, c2 - c1)     # ~200 big launches instead of ~6 per step
