@@ -26,46 +26,99 @@ namespace tgp {
 constexpr double kLog2PiD = 1.8378770664093454835606594728112;
 
 // Upper Cholesky factor in place (S = U'U, column-major, upper triangle read), blocked right-looking with NB = 32:
-//   k_chol_panel  (1 CTA)    block row [k0, k0+nb) x [k0, M): into shared memory, factor the diagonal block column by
-//                            column, apply U_kk^-T to the rest of the row, write the rows of U back;
+//   k_chol_panel2 (1 CTA)    diagonal block factored by one warp, its inverse, then U_kk^-T applied to the block row;
 //   k_chol_trail  (many CTAs) S[i, c] -= sum_r U[k0+r, i] U[k0+r, c] for k0+nb <= i <= c < M.
 // 2*ceil(M/32) - 1 launches per factorisation (inside the captured step graph). err gets the time step on failure.
 constexpr int kCholNB = 32;
 
-__global__ void __launch_bounds__(1024) k_chol_panel(double* __restrict__ S, int M, int k0, const long long* __restrict__ step,
-                                                     unsigned long long* __restrict__ err) {
-    extern __shared__ double pan[];          // pan[r * W + (c - k0)], r < nb, k0 <= c < M
-    __shared__ double s_inv;
-    const int nb = min(kCholNB, M - k0), W = M - k0;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int e = tid; e < nb * W; e += nt) {
-        const int r = e % nb, c = e / nb;
-        pan[r * W + c] = S[(size_t)(k0 + r) + (size_t)M * (k0 + c)];
+// ---- faster panel: the only serial part is the 32 x 32 diagonal block ------------------------------------------------------
+// k_chol_panel2 (1 CTA): diagonal block S_kk -> U_kk by ONE warp (lane = column, matrix in shared memory, warp-synchronous),
+// its inverse X = U_kk^-1 by the same warp (lane = column, back substitution), then every warp applies X' to the block row:
+// U[k-block, c] = X' S[k-block, c] for the columns right of the block (a 32-long dot per entry, no serial dependency).
+// X is also stored (Dinv, 32 x 32 per block): k_tri_inv2 builds U^-1 from these.
+__global__ void __launch_bounds__(256) k_chol_panel2(double* __restrict__ S, int M, int k0, const long long* __restrict__ step,
+                                                      unsigned long long* __restrict__ err, double* __restrict__ Dinv) {
+    __shared__ double A[32][33];
+    __shared__ double X[32][33];
+    __shared__ double rinv[32];
+    __shared__ double colbuf[8][4][32];
+    const int nb = min(32, M - k0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < 1024; e += 256) {
+        const int r = e & 31, c = e >> 5;
+        A[r][c] = (r < nb && c < nb) ? S[(size_t)(k0 + r) + (size_t)M * (k0 + c)] : (r == c ? 1.0 : 0.0);
     }
     __syncthreads();
-    for (int j = 0; j < nb; ++j) {
-        if (tid == 0) {
-            const double d = pan[j * W + j];
-            if (!(d > 0.0)) { atomicMin(err, (unsigned long long)*step); s_inv = 1.0; pan[j * W + j] = 1.0; }
-            else { const double sd = sqrt(d); pan[j * W + j] = sd; s_inv = 1.0 / sd; }
+    if (warp == 0) {
+        // lane c keeps column c of the block in REGISTERS (all indices compile-time after unrolling); only row j of U is
+        // exchanged through shared memory at step j. No shared-memory read-modify-write in the inner loop.
+        const int c = lane;
+        double col[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) col[r] = A[r][c];
+        double* rowbuf = colbuf[0][0];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            double d = __shfl_sync(0xffffffffu, col[j], j);           // pivot S_jj - sum_k U_kj^2, held by lane j
+            if (!(d > 0.0)) { if (lane == 0) atomicMin(err, (unsigned long long)*step); d = 1.0; }
+            const double inv = rsqrt(d);
+            const double ujc = c == j ? d * inv : col[j] * inv;       // U[j][c] for c >= j
+            col[j] = ujc;
+            rowbuf[c] = ujc;
+            if (c == j) rinv[j] = inv;
+            __syncwarp();
+#pragma unroll
+            for (int r = j + 1; r < 32; ++r)
+                if (r <= c) col[r] = fma(-rowbuf[r], ujc, col[r]);    // S[r][c] -= U[j][r] U[j][c]
+            __syncwarp();
         }
-        __syncthreads();
-        const double inv = s_inv;
-        for (int c = j + 1 + tid; c < W; c += nt) pan[j * W + c] *= inv;          // row j of U
-        __syncthreads();
-        // rows j+1 .. nb-1 of the panel: pan[r][c] -= U[j][r] * U[j][c], c >= r
-        const int nr = nb - 1 - j;
-        for (int e = tid; e < nr * W; e += nt) {
-            const int r = j + 1 + e / W, c = e % W;
-            if (c >= r) pan[r * W + c] = fma(-pan[j * W + r], pan[j * W + c], pan[r * W + c]);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) A[r][c] = r <= c ? col[r] : 0.0;  // U_kk (upper)
+        __syncwarp();
+        // X = U^-1, column c in registers: X[c][c] = 1/U[c][c]; X[i][c] = -(sum_{i < l <= c} U[i][l] X[l][c]) / U[i][i]
+        double xc[32];
+#pragma unroll
+        for (int i = 31; i >= 0; --i) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int l = i + 1; l < 32; ++l) {
+                const double u = A[i][l];                              // same address for every lane: broadcast
+                if (l <= c) { if (l & 1) s1 = fma(u, xc[l], s1); else s0 = fma(u, xc[l], s0); }
+            }
+            xc[i] = i == c ? rinv[i] : (i < c ? -(s0 + s1) * rinv[i] : 0.0);
         }
-        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) X[i][c] = xc[i];
     }
-    for (int e = tid; e < nb * W; e += nt) {
-        const int r = e % nb, c = e / nb;
-        S[(size_t)(k0 + r) + (size_t)M * (k0 + c)] = (c >= r) ? pan[r * W + c] : 0.0;
+    __syncthreads();
+    for (int e = tid; e < 1024; e += 256) {
+        const int r = e & 31, c = e >> 5;
+        if (r < nb && c < nb) S[(size_t)(k0 + r) + (size_t)M * (k0 + c)] = (c >= r) ? A[r][c] : 0.0;
+        Dinv[(size_t)(k0 / 32) * 1024 + r + 32 * c] = X[r][c];
     }
-    // below-diagonal part of these columns (rows > k0 + nb) is cleared by k_chol_trail's final pass
+    // block row: a warp takes 4 columns at a time (4 independent FMA chains), lane = row i of the block:
+    // U[k0 + i, col] = sum_{r <= i} X[r][i] S[k0 + r, col]
+    const int W = M - k0 - nb;
+    for (int c4 = warp * 4; c4 < W; c4 += 32) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int cc = c4 + q;
+            colbuf[warp][q][lane] = (cc < W && lane < nb) ? S[(size_t)(k0 + lane) + (size_t)M * (k0 + nb + cc)] : 0.0;
+        }
+        __syncwarp();
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r = 0; r <= lane; ++r) {
+            const double xr = X[r][lane];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] = fma(xr, colbuf[warp][q][r], s[q]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int cc = c4 + q;
+            if (cc < W && lane < nb) S[(size_t)(k0 + lane) + (size_t)M * (k0 + nb + cc)] = s[q];
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_chol_trail(double* __restrict__ S, int M, int k0, int nb) {
@@ -190,6 +243,7 @@ struct DenseWs {
     long long* step;
     double* lml;
     unsigned long long* err;
+    double* Dinv = nullptr;              // inverses of the 32 x 32 diagonal blocks of U (k_chol_panel2)
     double* Pprev = nullptr;             // steady-state detection (time-invariant models only)
     unsigned long long* conv = nullptr;
     long long* ss_at = nullptr;
@@ -235,8 +289,8 @@ static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const d
         TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, M, M, D, &one, w.V, M, H, M, &one, w.S, M));    // S = V H' + R
         for (int k0 = 0; k0 < M; k0 += kCholNB) {
             const int nbk = std::min(kCholNB, M - k0);
-            TGP_K(h, "dense:k_chol_panel");
-            k_chol_panel<<<1, 1024, sizeof(double) * nbk * (M - k0), st>>>(w.S, M, k0, w.step, w.err);
+            TGP_K(h, "dense:k_chol_panel2");
+            k_chol_panel2<<<1, 256, 0, st>>>(w.S, M, k0, w.step, w.err, w.Dinv);
             TGP_LAUNCH_CHECK(h);
             const int n = M - k0 - nbk;
             if (n > 0) {
@@ -332,6 +386,7 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
     TGP_TRY(dalloc(h, 1, &w.step));
     TGP_TRY(dalloc(h, 1, &w.lml));
     TGP_TRY(dalloc(h, 1, &w.err));
+    TGP_TRY(dalloc(h, (size_t)((M + 31) / 32) * 1024, &w.Dinv));
     const bool ti = !(m->sA | m->sa | m->sQ | m->sH | m->sh | m->sR);
     if (ti && h->algo == TGP_ALGO_AUTO) {
         TGP_TRY(dalloc(h, (size_t)D * D, &w.Pprev));
@@ -354,9 +409,6 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
     TGP_CUDA(h, cudaMemcpyAsync(w.step, &t0, sizeof(long long), cudaMemcpyHostToDevice, st));
     TGP_CUDA(h, cudaStreamSynchronize(st));   // t0 is a stack variable
 
-    const size_t pan_bytes = sizeof(double) * kCholNB * (size_t)M;
-    if (pan_bytes > 200 * 1024) return fail(h, TGP_EUNSUPPORTED, "observation dimension M=%d too large for the Cholesky panel kernel", M);
-    if (pan_bytes > 48 * 1024) TGP_CUDA(h, cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pan_bytes));
     if (ti && T >= 8 && !h->timing) {
         // Capture ONE step, replay it. Every kPoll steps the host looks at the steady-state word; once the covariance
         // recursion has converged (max |P_t - P_{t-1}| <= ss_tol max |P_t|, tested on the device) the remaining steps replay

@@ -9,7 +9,7 @@
 //                              Pp = W' At + Q        (= A P A' + Q)        D x D   symmetric
 //     update (LGC:129-141)     Vt = Pp' Ht           (= (H Pp)')           D x M   (+ its transpose V, M x D)
 //                              S  = Vt' Ht + R       (= H Pp H' + R)       M x M   symmetric, emitted in FP64
-//                              U  = chol(S) in FP64 (k_chol_panel / k_chol_trail),  Winv = U^-1  (k_tri_inv)
+//                              U  = chol(S) in FP64 (k_chol_panel2 / k_chol_trail),  Winv = U^-1  (k_tri_inv2)
 //                              B  = Winv' V          (= U' \ V)            M x D
 //                              P  = Pp - B' B                              D x D   symmetric
 // Means / residual / likelihood are FP64 GEMVs over the FP32 matrices (k_gemv_pair), lml_t in FP64.
@@ -71,19 +71,24 @@ static int tc_make_op(tgp_ctx* h, int rows, int cols, TcOp* op, int extra_cols =
 // once per process and device, outside any stream capture
 static int tc_prepare(tgp_ctx* h) {
     TGP_CUDA(h, cudaFuncSetAttribute(tc::k_tc_gemm_tn<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<64>::kSmem));
+    TGP_CUDA(h, cudaFuncSetAttribute(tc::k_tc_gemm_tn<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<128>::kSmem));
     return TGP_OK;
 }
 
-// C = alpha X' Y (+ additive terms), tile 128 x 64. Y may continue into a second tensor Y2 from contraction index k_switch on.
+// C = alpha X' Y (+ additive terms). Y may continue into a second tensor Y2 from contraction index k_switch on.
+// Tile 128 x 64 for the D x D / D x M products of one step (more CTAs); 128 x 128 when C is wide (the time-blocked phase):
+// the operand stream from L2 is what bounds these kernels, and the wider tile does 1.5x the MMAs per byte loaded.
 static int tc_gemm(tgp_ctx* h, const char* name, const TcOp& X, const TcOp& Y, int K, const tc::Epi& e, const TcOp* Y2 = nullptr, int k_switch_elems = 0,
                    int y_col_shift = 0) {
-    constexpr int BN = 64;
-    dim3 grid((e.Mx + tc::BM - 1) / tc::BM, (e.N + BN - 1) / BN);
     tc::Src src;
     src.K = K; src.lo_col_x = X.pr.cpad; src.lo_col_y = Y.pr.cpad; src.y_col_shift = y_col_shift;
     if (Y2) { src.lo_col_y2 = Y2->pr.cpad; src.k_switch = k_switch_elems / tc::BK; }
+    const bool wide = e.N >= 1024 && !e.symmetric;
+    const int BN = wide ? 128 : 64;
+    dim3 grid((e.Mx + tc::BM - 1) / tc::BM, (e.N + BN - 1) / BN);
     TGP_K(h, name);
-    tc::k_tc_gemm_tn<BN><<<grid, tc::kThreads, tc::Cfg<BN>::kSmem, h->stream>>>(X.m128, Y.m64, Y2 ? Y2->m64 : Y.m64, src, e);
+    if (wide) tc::k_tc_gemm_tn<128><<<grid, tc::kThreads, tc::Cfg<128>::kSmem, h->stream>>>(X.m128, Y.m128, Y2 ? Y2->m128 : Y.m128, src, e);
+    else      tc::k_tc_gemm_tn<64><<<grid, tc::kThreads, tc::Cfg<64>::kSmem, h->stream>>>(X.m128, Y.m64, Y2 ? Y2->m64 : Y.m64, src, e);
     TGP_LAUNCH_CHECK(h);
     return TGP_OK;
 }
@@ -122,30 +127,55 @@ __global__ void __launch_bounds__(256) k_gemv_pair(Pair X, int K, int N, const d
     }
 }
 
-// Winv = U^-1 for the upper Cholesky factor U (M x M, double, column-major, upper triangle read). One warp per ROW j of
-// Winv: z' U = e_j'  <=>  z_i = (delta_ij - sum_{j <= k < i} U[k, i] z_k) / U[i, i], i = j..M-1 (column i of U is contiguous).
-__global__ void __launch_bounds__(256) k_tri_inv(const double* __restrict__ U, int M, Pair Winv, Pair WinvT) {
-    extern __shared__ double zbuf[];                 // 8 warps x M
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j = blockIdx.x * 8 + warp;
-    if (j >= M) return;
-    double* z = zbuf + (size_t)warp * M;
-    for (int i = j; i < M; ++i) {
-        const double* col = U + (size_t)M * i;
-        double acc = 0.0;
-        for (int k = j + lane; k < i; k += 32) acc = fma(col[k], z[k], acc);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (lane == 0) z[i] = ((i == j ? 1.0 : 0.0) - acc) / col[i];
-        __syncwarp();
+// Winv = U^-1 from the inverses of the 32 x 32 diagonal blocks (Dinv, written by k_chol_panel2): blocked back substitution,
+// one warp per COLUMN c of Winv, lane = row inside the current block row I:
+//     x_J = Dinv_J[:, c - 32 J];    x_I = -Dinv_I (sum_{l > 32 I + 31}^{c} U[32 I + lane, l] x_l),  I = J-1 .. 0.
+// Rows of U are read coalesced across the lanes; 8 block steps at M = 256 instead of 256 scalar ones.
+__global__ void __launch_bounds__(256) k_tri_inv2(const double* __restrict__ U, int M, const double* __restrict__ Dinv, Pair Winv, Pair WinvT) {
+    extern __shared__ double xbuf[];                 // 8 warps x (Mp + 32), then the staged block row of U: 32 x Mp
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = blockIdx.x * 8 + warp;             // the 8 columns of a CTA lie in the same block column J
+    const bool live = c < M;
+    const int Mp = (M + 31) / 32 * 32;
+    double* x = xbuf + (size_t)warp * (Mp + 32);
+    double* tb = x + Mp;
+    double* tile = xbuf + (size_t)8 * (Mp + 32);
+    const int J = (blockIdx.x * 8) / 32;
+    const int cmax = min(blockIdx.x * 8 + 7, M - 1);
+    if (live) x[32 * J + lane] = Dinv[(size_t)J * 1024 + lane + 32 * (c - 32 * J)];
+    __syncwarp();
+    for (int I = J - 1; I >= 0; --I) {
+        const int l0 = 32 * (I + 1), nl = cmax - l0 + 1;
+        __syncthreads();                              // the previous tile has been consumed
+        for (int e = tid; e < 32 * nl; e += 256) tile[e] = __ldg(U + (size_t)(32 * I + (e & 31)) + (size_t)M * (l0 + (e >> 5)));
+        __syncthreads();
+        if (live) {
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            int l = l0;
+            for (; l + 3 <= c; l += 4) {
+                const double* tp = tile + (size_t)(l - l0) * 32 + lane;
+                t0 = fma(tp[0], x[l], t0);      t1 = fma(tp[32], x[l + 1], t1);
+                t2 = fma(tp[64], x[l + 2], t2); t3 = fma(tp[96], x[l + 3], t3);
+            }
+            for (; l <= c; ++l) t0 = fma(tile[(size_t)(l - l0) * 32 + lane], x[l], t0);
+            tb[lane] = (t0 + t1) + (t2 + t3);
+            __syncwarp();
+            const double* di = Dinv + (size_t)I * 1024 + lane;     // row `lane` of the upper-triangular block inverse
+            double s = 0.0;
+#pragma unroll 8
+            for (int rp = 0; rp < 32; ++rp) s = fma(__ldg(di + 32 * rp), tb[rp], s);
+            x[32 * I + lane] = -s;
+            __syncwarp();
+        }
     }
-    for (int i = j + lane; i < M; i += 32) {
-        const float x = (float)z[i];
-        const float hi = tc::tf32_hi(x);
-        Winv.hi()[(size_t)j + (size_t)Winv.ld * i] = hi;
-        Winv.lo()[(size_t)j + (size_t)Winv.ld * i] = x - hi;
-        WinvT.hi()[(size_t)i + (size_t)WinvT.ld * j] = hi;      // the transpose (lower triangular), used by the time-blocked phase
-        WinvT.lo()[(size_t)i + (size_t)WinvT.ld * j] = x - hi;
+    if (!live) return;
+    for (int i = lane; i <= c; i += 32) {
+        const float xv = (float)x[i];
+        const float hi = tc::tf32_hi(xv);
+        Winv.hi()[(size_t)i + (size_t)Winv.ld * c] = hi;
+        Winv.lo()[(size_t)i + (size_t)Winv.ld * c] = xv - hi;
+        WinvT.hi()[(size_t)c + (size_t)WinvT.ld * i] = hi;
+        WinvT.lo()[(size_t)c + (size_t)WinvT.ld * i] = xv - hi;
     }
 }
 
@@ -174,7 +204,7 @@ __global__ void k_advance_conv(long long* step, long long delta, unsigned* conv,
 
 struct TcWs {
     TcOp At, Ht, Pa, Pb, W, Vt, V, B, Winv, WinvT;
-    double *S, *m, *mp, *r, *alpha, *lml;
+    double *S, *m, *mp, *r, *alpha, *lml, *Dinv;
     long long* step;
     unsigned long long* err;
     unsigned* conv = nullptr;      // steady-state detection (time-invariant models only)
@@ -247,8 +277,8 @@ static int tc_step(tgp_ctx* h, const tgp_lgssm& d, const double* dy, TcWs& w, lo
         TGP_TRY(tc_gemm(h, "tc:gemm S=Vt'Ht+R", w.Vt, w.Ht, D, e4));
         for (int k0 = 0; k0 < M; k0 += kCholNB) {
             const int nbk = std::min(kCholNB, M - k0);
-            TGP_K(h, "dense:k_chol_panel");
-            k_chol_panel<<<1, 1024, sizeof(double) * nbk * (M - k0), st>>>(w.S, M, k0, w.step, w.err);
+            TGP_K(h, "dense:k_chol_panel2");
+            k_chol_panel2<<<1, 256, 0, st>>>(w.S, M, k0, w.step, w.err, w.Dinv);
             TGP_LAUNCH_CHECK(h);
             const int n = M - k0 - nbk;
             if (n > 0) {
@@ -257,8 +287,8 @@ static int tc_step(tgp_ctx* h, const tgp_lgssm& d, const double* dy, TcWs& w, lo
                 TGP_LAUNCH_CHECK(h);
             }
         }
-        TGP_K(h, "tc:k_tri_inv");
-        k_tri_inv<<<(M + 7) / 8, 256, sizeof(double) * 8 * M, st>>>(w.S, M, w.Winv.pr, w.WinvT.pr);
+        TGP_K(h, "tc:k_tri_inv2");
+        k_tri_inv2<<<(M + 7) / 8, 256, sizeof(double) * (8 * ((M + 31) / 32 * 32 + 32) + 32 * ((M + 31) / 32 * 32)), st>>>(w.S, M, w.Dinv, w.Winv.pr, w.WinvT.pr);
         TGP_LAUNCH_CHECK(h);
         tc::Epi e5;
         e5.Mx = M; e5.N = D; e5.out_hi = w.B.pr.hi(); e5.out_lo = w.B.pr.lo(); e5.ld_out = w.B.pr.ld;
@@ -445,6 +475,7 @@ static int tc_steady_blocked(tgp_ctx* h, const tgp_lgssm& d, const double* dy, T
         yv[j].pr = Yp;
         yv[j].pr.cpad = (int)nbp;        // lo plane of the view: nbp view-columns behind the hi plane
         TGP_TRY(tc_encode_map(h, Yp.p + (size_t)Yp.ld * j, M, 2 * nbp, (size_t)Yp.ld * L * sizeof(float), 64u, &yv[j].m64));
+        TGP_TRY(tc_encode_map(h, Yp.p + (size_t)Yp.ld * j, M, 2 * nbp, (size_t)Yp.ld * L * sizeof(float), 128u, &yv[j].m128));
     }
 
     // ---- pass 1: zero-state response of every block (block 0 starts from the current mean) ---------------------------------
@@ -547,6 +578,7 @@ int dense_filter_tc(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml
     TGP_TRY(tc_make_op(h, M, M, &w.Winv));
     TGP_TRY(tc_make_op(h, M, M, &w.WinvT));
     TGP_TRY(dalloc(h, (size_t)M * M, &w.S));
+    TGP_TRY(dalloc(h, (size_t)((M + 31) / 32) * 1024, &w.Dinv));
     TGP_TRY(dalloc(h, D, &w.m));
     TGP_TRY(dalloc(h, D, &w.mp));
     TGP_TRY(dalloc(h, M, &w.r));
@@ -579,10 +611,11 @@ int dense_filter_tc(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml
     *pt0 = rev ? T - 1 : 0;
     TGP_CUDA(h, cudaMemcpyAsync(w.step, pt0, sizeof(long long), cudaMemcpyHostToDevice, st));
 
-    const size_t pan_bytes = sizeof(double) * kCholNB * (size_t)M;
-    if (pan_bytes > 200 * 1024) return fail(h, TGP_EUNSUPPORTED, "observation dimension M=%d too large for the Cholesky panel kernel", M);
-    if (pan_bytes > 48 * 1024) TGP_CUDA(h, cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pan_bytes));
-    if (sizeof(double) * 8 * M > 48 * 1024) TGP_CUDA(h, cudaFuncSetAttribute(k_tri_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 8 * M)));
+    {
+        const size_t tb = sizeof(double) * (8 * ((M + 31) / 32 * 32 + 32) + 32 * ((M + 31) / 32 * 32));
+        if (tb > 200 * 1024) return fail(h, TGP_EUNSUPPORTED, "observation dimension M=%d too large for the triangular-inverse kernel", M);
+        if (tb > 48 * 1024) TGP_CUDA(h, cudaFuncSetAttribute(k_tri_inv2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
+    }
     if (ti && T >= 8 && !h->timing) {
         // One step captured into a CUDA graph and replayed. Every kPoll steps the host looks at the steady-state word;
         // once the covariance recursion has converged the remaining steps replay the mean-only graph.

@@ -37,6 +37,10 @@ function handle(dev::Int)
         h[]
     end
 end
+# Arithmetic of the large-state / vector-observation path follows the storage tag's element type (tgp_b200.h: TGP_OPT_DENSE_MATH):
+# Float32 -> FP32 storage on the tcgen05 tensor cores (3xTF32), otherwise FP64. The small-state scan kernels are FP64 either way.
+set_dense_math(h, ::Type{T}) where {T} =
+    ccall((:tgp_set_option, LIB), Cint, (Ptr{Cvoid}, Cint, Int64), h, 6, T === Float32 ? 1 : 0)
 function check(h, rc)
     rc == 0 && return nothing
     msg = unsafe_string(ccall((:tgp_last_error, LIB), Cstring, (Ptr{Cvoid},), h))

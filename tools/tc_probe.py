@@ -54,6 +54,8 @@ def run(Nr, T, Tcpu):
     print(json.dumps(out), flush=True)
 
 
-run(24, 200, 200)
-run(64, 300, 100)
+import sys as _s
+if '--big-only' not in _s.argv:
+    run(24, 200, 200)
+    run(64, 300, 100)
 run(256, 200, 12)
