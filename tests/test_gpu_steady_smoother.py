@@ -1,0 +1,73 @@
+"""GPU tests of the steady-state posterior-marginals path (tgp_steady_smooth.cuh): time-invariant models, long series — head and
+tail by the general scan kernels, the rest by constant-coefficient scans over vectors. Compared with the sequential C oracle
+(filter + RTS smoother, oracle/lgssm_ref.c) at north_star's tolerances: 1e-6 relative on logpdf, 1e-5 on means / variances."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle, tgp_oracle as O
+
+pytestmark = pytest.mark.gpu
+LML_RTOL, MV_RTOL = 1e-6, 1e-5
+
+
+def _cfg3_kernels(pkg):
+    TK = pkg.gp.TransformedKernel
+    kp = 1.0 * pkg.Matern32Kernel() + 0.7 * pkg.Matern52Kernel() + 0.5 * TK(pkg.Matern52Kernel(), 0.5) + 0.3 * TK(pkg.Matern32Kernel(), 2.0)
+    ko = 1.0 * O.Matern32() + 0.7 * O.Matern52() + 0.5 * O.Matern52().stretch(0.5) + 0.3 * O.Matern32().stretch(2.0)
+    return kp, ko
+
+
+def _run(pkg, handle, kp, ko, T, dt, sigma2, r_new, seed):
+    mo = O.build_lgssm(ko, O.RegularSpacing(0.0, dt, T), sigma2)
+    rng = np.random.default_rng(seed)
+    y = np.sin(np.arange(T) * 0.004) + 0.3 * np.cos(np.arange(T) * 0.05) + 0.35 * rng.standard_normal(T)
+    model = pkg.to_sde(pkg.GP(kp))(pkg.RegularSpacing(0.0, dt, T), sigma2).build_lgssm()
+    c0 = handle.counters()["launches"]
+    mu, var, lml = pkg.lgssm.posterior_marginals(model, y, r_new, handle, return_lml=True)
+    launches = handle.counters()["launches"] - c0
+    mu_o, var_o, lml_o = c_oracle.posterior_marginals(c_oracle.Model.from_lgssm(mo), y, r_new)
+    return (mu, var, lml), (mu_o, var_o, lml_o), launches, (model, y)
+
+
+@pytest.mark.parametrize("name,T", [("matern52", 40_000), ("matern32", 33_001), ("cfg3", 50_000), ("matern12", 70_007)])
+def test_steady_posterior_marginals_match_oracle(pkg, handle, name, T):
+    if name == "cfg3":
+        kp, ko = _cfg3_kernels(pkg)           # D = 10 (BASELINE config 3's stand-in kernel)
+    else:
+        kp = {"matern52": pkg.Matern52Kernel, "matern32": pkg.Matern32Kernel, "matern12": pkg.Matern12Kernel}[name]()
+        ko = {"matern52": O.Matern52, "matern32": O.Matern32, "matern12": O.Matern12}[name]()
+    got, ref, launches, (model, y) = _run(pkg, handle, kp, ko, T, 0.01, 0.1, 1e-2, 31)
+    np.testing.assert_allclose(got[0], ref[0], rtol=MV_RTOL, atol=1e-7)
+    np.testing.assert_allclose(got[1], ref[1], rtol=MV_RTOL)
+    assert abs(got[2] - ref[2]) <= LML_RTOL * abs(ref[2])
+    # the steady path was taken (it launches the constant-coefficient scan kernels: more launches than the general path's ~12)
+    handle.set_algo(pkg.TGP_ALGO_SCAN)
+    try:
+        c0 = handle.counters()["launches"]
+        mu_g, var_g, lml_g = pkg.lgssm.posterior_marginals(model, y, 1e-2, handle, return_lml=True)
+        launches_general = handle.counters()["launches"] - c0
+    finally:
+        handle.set_algo(pkg.TGP_ALGO_AUTO)
+    assert launches > launches_general
+    np.testing.assert_allclose(got[0], mu_g, rtol=MV_RTOL, atol=1e-7)
+    np.testing.assert_allclose(got[1], var_g, rtol=MV_RTOL)
+
+
+def test_steady_posterior_marginals_heteroscedastic_prediction_noise(pkg, handle):
+    """R_new per step (stride 1): only the emitted variances change."""
+    T = 36_000
+    rng = np.random.default_rng(5)
+    r_new = rng.uniform(0.01, 0.5, T)
+    got, ref, _, _ = _run(pkg, handle, pkg.Matern52Kernel(), O.Matern52(), T, 0.01, 0.1, r_new, 32)
+    np.testing.assert_allclose(got[0], ref[0], rtol=MV_RTOL, atol=1e-7)
+    np.testing.assert_allclose(got[1], ref[1], rtol=MV_RTOL)
+
+
+def test_steady_posterior_marginals_falls_back_when_not_converged(pkg, handle):
+    """A very fine grid: the covariances have not converged inside the 4096-step head / tail, the device-side test fails and the
+    call is redone by the general kernels — same answer."""
+    T = 40_000
+    got, ref, launches, _ = _run(pkg, handle, pkg.Matern52Kernel(), O.Matern52(), T, 1e-5, 0.1, 1e-2, 33)
+    np.testing.assert_allclose(got[0], ref[0], rtol=MV_RTOL, atol=1e-7)
+    np.testing.assert_allclose(got[1], ref[1], rtol=MV_RTOL)
+    assert abs(got[2] - ref[2]) <= LML_RTOL * abs(ref[2])
