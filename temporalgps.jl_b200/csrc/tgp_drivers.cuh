@@ -194,52 +194,43 @@ int do_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* m_f, int6
 // ---- backward pass over the stored filtering distributions (posterior marginals) -----------------
 // ---- posterior marginals of a time-invariant model: head / tail by the general kernels, the rest by constant-coefficient
 // scans over vectors (tgp_steady_smooth.cuh). *converged = false: nothing was delivered, the caller redoes the call generally.
-constexpr int64_t kSmHead = 4096, kSmTail = 4096;
-
-template <int D>
-int run_smoother_segment(tgp_ctx* h, const SmootherProvider<D>& prov, int64_t Tseg, const double* xinit, double* xfinal, const EmitOut& eo) {
-    constexpr int SN = D + Sym<D>::N;
-    cudaStream_t st = h->stream;
-    const int L = h->chunk > 1 ? h->chunk : 16;
-    const int64_t nchunk = (Tseg + L - 1) / L;
-    const int64_t grid = (nchunk + kBlock - 1) / kBlock;
-    const int64_t nthreads = grid * kBlock, nwarps = nthreads / 32;
-    double *excl, *wagg, *wstate;
-    TGP_TRY(dalloc(h, (size_t)Aff<D>::N * nthreads, &excl));
-    TGP_TRY(dalloc(h, (size_t)Aff<D>::N * nwarps, &wagg));
-    TGP_TRY(dalloc(h, (size_t)SN * nwarps, &wstate));
-    TGP_K(h, "k_aff_reduce");
-    k_aff_reduce<D, SmootherProvider<D>><<<(unsigned)grid, kBlock, 0, st>>>(prov, Tseg, L, nthreads, excl, wagg, nwarps);
-    TGP_LAUNCH_CHECK(h);
-    TGP_K(h, "k_aff_mid");
-    k_aff_mid<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, xinit, wstate, xfinal);
-    TGP_LAUNCH_CHECK(h);
-    TGP_K(h, "k_aff_apply");
-    k_aff_apply<D, SmootherProvider<D>><<<(unsigned)grid, kBlock, 0, st>>>(prov, Tseg, L, nthreads, excl, wstate, nwarps, eo, 1);
-    TGP_LAUNCH_CHECK(h);
-    return TGP_OK;
-}
+constexpr int64_t kSmMaxEnd = 8192;      // budget (steps) for each covariance recursion to stop moving
 
 template <int D>
 int posterior_marginals_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, const double* dRn, int64_t sRnew, double* dmean, double* dvar,
                                double* lml_out, bool* converged) {
-    constexpr int SN = D + Sym<D>::N;
-    const int64_t T = d.T, Nh = kSmHead, Nt = kSmTail;
+    const int64_t T = d.T;
     cudaStream_t st = h->stream;
-    // head, forward: filtering distributions of [0, Nh) kept for its backward pass
-    tgp_lgssm dh = d;
-    dh.T = Nh;
-    FilterReq rq;
-    rq.keep_ws = true;
-    TGP_TRY(filter_general<D>(h, dh, dy, rq));
+    *converged = false;
     SmConst<D>* cst;
+    double *wsh, *x0buf, *MFh, *GG, *gg, *SS;
+    unsigned long long* err;
+    constexpr int SN = D + Sym<D>::N;
     TGP_TRY(dalloc(h, 1, &cst));
-    const DevModel dmT{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, dy, 1, T};
-    TGP_K(h, "k_sm_setup");
-    k_sm_setup<D><<<1, 128, 0, st>>>(dmT, rq.ws, Nh, h->ss_tol, cst);
+    TGP_TRY(dalloc(h, (size_t)kSmMaxEnd * SN, &wsh));
+    TGP_TRY(dalloc(h, SN, &x0buf));
+    TGP_TRY(dalloc(h, (size_t)kSmMaxEnd * D, &MFh));
+    TGP_TRY(dalloc(h, 1, &err));
+    TGP_CUDA(h, cudaMemsetAsync(err, 0xFF, sizeof(unsigned long long), st));
+    const DevModel dm{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, dy, 1, T};
+    // head, forward (one CTA, sequential) and the constants of the steady phase
+    TGP_K(h, "k_sm_head_fwd");
+    k_sm_head_fwd<D><<<1, 128, 0, st>>>(dm, d.m0, d.P0, kSmMaxEnd, h->ss_tol, wsh, MFh, cst, err);
     TGP_LAUNCH_CHECK(h);
-    // forward means of [Nh, T)
-    const int64_t nf = T - Nh;
+    TGP_K(h, "k_sm_setup");
+    k_sm_setup<D><<<1, 128, 0, st>>>(dm, cst);
+    TGP_LAUNCH_CHECK(h);
+    // the host needs N0 to size the scans
+    long long* pN0 = (long long*)(h->pinned + 24);
+    int* pconv = (int*)(h->pinned + 25);
+    TGP_CUDA(h, cudaMemcpyAsync(pN0, &cst->N0, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    TGP_CUDA(h, cudaMemcpyAsync(pconv, &cst->conv_f, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TGP_CUDA(h, cudaStreamSynchronize(st));
+    h->d2h += 12;
+    const int64_t N0 = *pN0;
+    if (!*pconv || T < N0 + 2 * kSmMaxEnd) return TGP_OK;          // not converged (or too short): general path
+    // forward means of [N0, T): MF[j] = m_f[N0 - 1 + j]
+    const int64_t nf = T - N0;
     double *MF, *partials, *lml_dev, *xlast;
     TGP_TRY(dalloc(h, (size_t)(nf + 1) * D, &MF));
     const int64_t nblk = ((nf + kCsL - 1) / kCsL + kCsThreads - 1) / kCsThreads;
@@ -249,57 +240,43 @@ int posterior_marginals_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy,
     TGP_K(h, "k_sm_set_mstart");
     k_sm_set_mstart<D><<<1, 32, 0, st>>>(cst, MF);
     TGP_LAUNCH_CHECK(h);
-    FwdItems<D> fi{dy, Nh, MF, partials};
+    FwdItems<D> fi{dy, N0, MF, partials};
     BwdItems<D> bi{};
     TGP_TRY((cs_scan<D, true>(h, cst, fi, bi, nf, cst->mstart, nullptr)));
     TGP_K(h, "k_sm_lml");
-    k_sm_lml<D><<<1, 256, 0, st>>>(cst, partials, nblk, nf, rq.lml_dev, lml_dev);
+    k_sm_lml<D><<<1, 256, 0, st>>>(cst, partials, nblk, nf, lml_dev);
     TGP_LAUNCH_CHECK(h);
-    // tail, backward: general kernels on (m_f, P_f^inf) of [T - Nt, T)
-    double *ws_tail, *x0_tail, *xT_tail, *xfin;
-    TGP_TRY(dalloc(h, (size_t)SN * Nt, &ws_tail));
-    TGP_TRY(dalloc(h, SN, &x0_tail));
-    TGP_TRY(dalloc(h, SN, &xT_tail));
-    TGP_TRY(dalloc(h, SN, &xfin));
-    const int64_t j0 = (T - Nt) - (Nh - 1);
-    TGP_K(h, "k_sm_fill_tail");
-    k_sm_fill_tail<D><<<(unsigned)((Nt + 255) / 256), 256, 0, st>>>(MF, j0, Nt, rq.xT, ws_tail, x0_tail, xT_tail);
+    // backward means of t = T-1 .. N0-1 (item 0 = the filtered mean at T-1), var = vss + R_new; the tail variances are overwritten below
+    TGP_K(h, "k_sm_set_xfirst");
+    k_sm_set_xfirst<D><<<1, 32, 0, st>>>(cst, MF + (size_t)nf * D);
     TGP_LAUNCH_CHECK(h);
-    {
-        SmootherProvider<D> pt;
-        pt.dm = DevModel{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, nullptr, 1, Nt};
-        pt.ws = ws_tail;
-        pt.x0buf = x0_tail;
-        pt.err_step = rq.err;
-        const int64_t tl = T - 1;
-        EmitOut eo{d.H, d.h, dRn + tl * sRnew, 0, 0, -sRnew, dmean + tl, dvar + tl, -1};
-        TGP_TRY(run_smoother_segment<D>(h, pt, Nt, xT_tail, xfin, eo));
-    }
-    TGP_K(h, "k_sm_after_tail");
-    k_sm_after_tail<D><<<1, 32, 0, st>>>(xfin, h->ss_tol, cst);
-    TGP_LAUNCH_CHECK(h);
-    // middle, backward: t = T - Nt - 1 down to Nh - 1
-    const int64_t nbk = T - Nt - Nh + 1;
-    bi = BwdItems<D>{MF, T - Nt - Nh, T - Nt - 1, dRn, sRnew, dmean, dvar};
+    const int64_t nbk = T - N0 + 1;
+    bi = BwdItems<D>{MF, nf, T - 1, dRn, sRnew, dmean, dvar};
     TGP_TRY((cs_scan<D, false>(h, cst, fi, bi, nbk, nullptr, xlast)));
+    TGP_K(h, "k_sm_tail_var");
+    k_sm_tail_var<D><<<1, 128, 0, st>>>(cst, T, kSmMaxEnd, h->ss_tol, dRn, sRnew, dvar);
+    TGP_LAUNCH_CHECK(h);
+    // head, backward
+    TGP_TRY(dalloc(h, (size_t)N0 * D * D, &GG));
+    TGP_TRY(dalloc(h, (size_t)N0 * D * D, &SS));
+    TGP_TRY(dalloc(h, (size_t)N0 * D, &gg));
     int* flag;
     TGP_TRY(dalloc(h, 1, &flag));
-    TGP_K(h, "k_sm_finish");
-    k_sm_finish<D><<<1, 32, 0, st>>>(xlast, cst, flag);
-    TGP_LAUNCH_CHECK(h);
-    // head, backward, from (m_s[Nh - 1], P_s^inf)
-    {
-        SmootherProvider<D> ph;
-        ph.dm = DevModel{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, nullptr, 1, Nh};
-        ph.ws = rq.ws;
-        ph.x0buf = rq.x0buf;
-        ph.err_step = rq.err;
-        const int64_t tl = Nh - 1;
-        EmitOut eo{d.H, d.h, dRn + tl * sRnew, 0, 0, -sRnew, dmean + tl, dvar + tl, -1};
-        TGP_TRY(run_smoother_segment<D>(h, ph, Nh, cst->sback, nullptr, eo));
+    if (N0 > 1) {
+        SmootherProvider<D> ph;     // stored states of the head, SoA with stride kSmMaxEnd (the provider's dm.T is that stride)
+        ph.dm = DevModel{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, nullptr, 1, kSmMaxEnd};
+        ph.ws = wsh;
+        ph.x0buf = x0buf;           // never read: t >= 1
+        ph.err_step = err;
+        TGP_K(h, "k_sm_head_dyn");
+        k_sm_head_dyn<D><<<(unsigned)((N0 + kBlock - 1) / kBlock), kBlock, 0, st>>>(ph, N0, GG, gg, SS);
+        TGP_LAUNCH_CHECK(h);
     }
+    TGP_K(h, "k_sm_head_bwd");
+    k_sm_head_bwd<D><<<1, 128, 0, st>>>(dm, cst, xlast, GG, gg, SS, dRn, sRnew, dmean, dvar, flag);
+    TGP_LAUNCH_CHECK(h);
     TGP_TRY(deliver_scalar(h, lml_dev, lml_out));
-    return end_call(h, rq.err, T, false, flag, converged);
+    return end_call(h, err, T, false, flag, converged);
 }
 
 template <int D>
@@ -309,7 +286,7 @@ int do_posterior_marginals(tgp_ctx* h, const tgp_lgssm* m, const double* y, cons
     constexpr int SN = D + Sym<D>::N;
     const int64_t T = m->T;
     cudaStream_t st = h->stream;
-    if (h->algo == TGP_ALGO_AUTO && time_invariant(*m) && T >= 4 * (kSmHead + kSmTail)) {
+    if (h->algo == TGP_ALGO_AUTO && time_invariant(*m) && T >= 4 * kSmMaxEnd) {
         tgp_lgssm d;
         const double* dy;
         TGP_TRY(stage_model(h, m, y, &d, &dy));

@@ -8,12 +8,17 @@
 //     forward   m_f[t]   = Abar m_f[t-1] + K y_t + c          v_t = y_t - w'm_f[t-1] - hh,  lml_t = -(log 2pi + log S + v_t^2/S)/2
 //     backward  m_s[t-1] = G m_s[t] + E m_f[t-1] + e0          E = I - G A,  e0 = -G a        (lgssm.jl:231-240 with frozen P)
 //     output    mean_t = H m_s[t] + h,   var_t = H P_s^inf H' + R_new[t]
-// so the series is cut in three:
-//     head  [0, Nh)        the general scan kernels (tgp_scan_small.cuh), forward and backward: time-varying gains;
-//     tail  [T - Nt, T)    the general backward kernels on (m_f from the steady pass, P_f^inf): P_s still moving;
-//     rest                 two constant-coefficient scans over vectors (this file): a D x D mat-VEC per step and pass.
-// Convergence is CHECKED on the device (|P_f[Nh-1] - P_f[Nh-2]|, |P_s[T-Nt-1] - P_s^inf| against TGP_OPT_SS_TOL); if either test
-// fails the caller redoes the call with the general path.
+// so only the two ENDS of the series need matrix work, and there it is data-free except for the means:
+//     head  [0, N0)        k_sm_head_fwd: ONE CTA runs the filter sequentially (block-cooperative D x D products in shared memory)
+//                          until |P_f[t] - P_f[t-1]| <= tol |P_f| (N0 ~ 10^3), keeping P_f[t], P_p[t], m_f[t];
+//                          k_sm_head_dyn: (G_t, Sigma_t) of those steps, one thread per step (invert_dynamics, lgssm.jl:231-240);
+//                          k_sm_head_bwd: ONE CTA runs the RTS recursion back from (m_s[N0-1], P_s^inf) and emits the marginals;
+//     tail  (T - n1, T)    k_sm_tail_var: ONE CTA iterates P_s <- G P_s G' + Sigma back from P_s[T-1] = P_f^inf until it stops moving,
+//                          emitting var_t (the tail MEANS follow the constant-coefficient recursion: G is constant there);
+//     means [N0, T)        two constant-coefficient scans over vectors (forward filter means, backward smoother means).
+// Convergence is CHECKED on the device against TGP_OPT_SS_TOL (the forward test inside k_sm_head_fwd, the backward one inside
+// k_sm_tail_var, cross-checked against P_s^inf obtained independently by doubling); if either fails the caller redoes the call
+// with the general scan kernels.
 //
 // The constant-coefficient scan x_i = Phi x_{i-1} + u_i is three levels of chunks of kCsL items (Phi^(L^k) precomputed): fold every
 // chunk from zero (reduce), recurse on the chunk aggregates, a short sequential pass on top, then re-run every chunk from its true
@@ -39,9 +44,108 @@ struct SmConst {
     double xfirst[D];        // smoothed mean at the first backward item (from the tail)
     double mstart[D];        // filtered mean entering the forward scan (m_f[Nh - 1])
     double sback[D + Sym<D>::N];   // packed (m_s[Nh - 1], P_s^inf): initial state of the head's backward pass
+    double Sig[D * D];       // row-major Sigma of the steady reverse-time dynamics
+    double Pfinf[D * D];     // filtering covariance at its fixed point (full)
+    double lml_head;         // log marginal likelihood of the head steps
+    long long N0, n1;        // head length; tail length (steps until P_s stopped moving)
     int conv_f, conv_b;
     double err_f, err_b;
 };
+
+// ---- block-cooperative D x D helpers (row-major matrices in shared memory, one element per thread) -------------------------------
+template <int D> __device__ __forceinline__ void bk_mm(const double* A, const double* B, double* C) {        // C = A B
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+        const int i = e / D, j = e % D;
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s = fma(A[i * D + k], B[k * D + j], s);
+        C[e] = s;
+    }
+    __syncthreads();
+}
+template <int D> __device__ __forceinline__ void bk_mmT_add(const double* A, const double* B, const double* Q, double* C) {   // C = A B' + Q
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+        const int i = e / D, j = e % D;
+        double s = Q ? Q[e] : 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) s = fma(A[i * D + k], B[j * D + k], s);
+        C[e] = s;
+    }
+    __syncthreads();
+}
+// block max of a per-thread value (blockDim = 128)
+__device__ __forceinline__ double bk_max(double v, double* red) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+    __syncthreads();
+    return v;
+}
+
+// ---- head, forward: sequential filter in one CTA until the covariance stops moving ---------------------------------------------------
+// Keeps the filtering distributions of t < N0 in the smoother's SoA layout (ws[k * Nmax + t]: mean, then the packed upper triangle)
+// and MFh[t] = m_f[t]. Same arithmetic as predict (LGC:46-52) and posterior_and_lml(::ScalarOutputLGC) (LGC:247-257).
+template <int D>
+__global__ void __launch_bounds__(128) k_sm_head_fwd(const DevModel dm, const double* __restrict__ m0, const double* __restrict__ P0, long long Nmax,
+                                                     double tol, double* __restrict__ ws, double* __restrict__ MFh,
+                                                     SmConst<D>* __restrict__ cst, unsigned long long* __restrict__ err_step) {
+    __shared__ double sA[D * D], sQ[D * D], sP[D * D], sT[D * D], sPp[D * D];
+    __shared__ double sh[D], sa[D], sm[D], smp[D], sV[D], red[4];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < D * D; e += 128) {
+        const int i = e / D, j = e % D;
+        sA[e] = dm.A[i + D * j]; sQ[e] = dm.Q[i + D * j]; sP[e] = P0[i + D * j];
+    }
+    if (tid < D) { sh[tid] = dm.H[tid]; sa[tid] = dm.a[tid]; sm[tid] = m0[tid]; }
+    __syncthreads();
+    const double h0 = *dm.h, R = *dm.R;
+    double lml = 0.0;
+    long long N0 = Nmax;
+    int conv = 0;
+    for (long long t = 0; t < Nmax; ++t) {
+        bk_mm<D>(sA, sP, sT);
+        bk_mmT_add<D>(sT, sA, sQ, sPp);                              // P_p = A P A' + Q
+        if (tid < D) {
+            double v = 0.0, mp = sa[tid];
+#pragma unroll
+            for (int k = 0; k < D; ++k) { v = fma(sPp[tid * D + k], sh[k], v); mp = fma(sA[tid * D + k], sm[k], mp); }
+            sV[tid] = v; smp[tid] = mp;
+        }
+        __syncthreads();
+        double S = R, pred = h0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) { S = fma(sh[k], sV[k], S); pred = fma(sh[k], smp[k], pred); }
+        if (!(S > 1e-300) || !(S < 1e300)) { if (tid == 0) atomicMin(err_step, (unsigned long long)t); S = 1.0; }
+        const double invS = 1.0 / S, v = __ldg(dm.y + t) - pred;
+        if (tid == 0) lml -= 0.5 * (kLog2Pi + log(S) + v * v * invS);
+        double dmax = 0.0, amax = 0.0;
+        for (int e = tid; e < D * D; e += 128) {
+            const int i = e / D, j = e % D;
+            const double pf = fma(-sV[i] * invS, sV[j], sPp[e]);
+            if (i <= j) ws[(size_t)(D + Sym<D>::idx(i, j)) * Nmax + t] = pf;
+            dmax = fmax(dmax, fabs(pf - sP[e]));
+            amax = fmax(amax, fabs(pf));
+            sP[e] = pf;
+        }
+        if (tid < D) {
+            const double mf = fma(sV[tid] * invS, v, smp[tid]);
+            sm[tid] = mf;
+            MFh[t * D + tid] = mf;
+            ws[(size_t)tid * Nmax + t] = mf;
+        }
+        __syncthreads();
+        if ((t & 15) == 15 && t >= 31) {                             // test every 16 steps: a block reduction costs two barriers
+            const double d = bk_max(dmax, red), a = bk_max(amax, red);
+            if (d <= tol * a) { N0 = t + 1; conv = 1; if (tid == 0) cst->err_f = a > 0.0 ? d / a : 0.0; break; }
+        }
+    }
+    for (int e = tid; e < D * D; e += 128) cst->Pfinf[e] = sP[e];
+    if (tid < D) cst->mstart[tid] = sm[tid];
+    if (tid == 0) { cst->N0 = N0; cst->conv_f = conv; cst->lml_head = lml; }
+}
+
 
 // y = M x (M row-major in shared memory, x in registers)
 template <int D> __device__ __forceinline__ void cs_matvec(const double* __restrict__ M, const double (&x)[D], double (&y)[D]) {
@@ -67,19 +171,13 @@ template <int D> __device__ __forceinline__ void cs_matmul(const double* A, cons
 }
 
 template <int D>
-__global__ void __launch_bounds__(128) k_sm_setup(const DevModel dm, const double* __restrict__ ws_head, long long Nh, double tol,
-                                                  SmConst<D>* __restrict__ cst) {
+__global__ void __launch_bounds__(128) k_sm_setup(const DevModel dm, SmConst<D>* __restrict__ cst) {
     __shared__ double sA[D * D], sB[D * D], sC[D * D], sG[D * D], sS[D * D], sT[D * D];
     const int tid = threadIdx.x;
     if (tid == 0) {
-        Vec<D> m1, m0;
-        Sym<D> Pf, P0;
-        load_state<D>(ws_head, Nh, Nh - 1, m1, Pf);
-        load_state<D>(ws_head, Nh, Nh - 2, m0, P0);
-        double md = 0.0, ma = 0.0;
-        for (int k = 0; k < Sym<D>::N; ++k) { md = fmax(md, fabs(Pf.v[k] - P0.v[k])); ma = fmax(ma, fabs(Pf.v[k])); }
-        cst->err_f = ma > 0.0 ? md / ma : 0.0;
-        cst->conv_f = md <= tol * ma;
+        Sym<D> Pf;
+        for (int j = 0; j < D; ++j)
+            for (int i = 0; i <= j; ++i) Pf(i, j) = 0.5 * (cst->Pfinf[i * D + j] + cst->Pfinf[j * D + i]);
         const Mat<D> A = ldg_mat<D>(dm.A);
         const Vec<D> a = ldg_vec<D>(dm.a);
         const Sym<D> Q = ldg_sym_full<D>(dm.Q);
@@ -90,7 +188,7 @@ __global__ void __launch_bounds__(128) k_sm_setup(const DevModel dm, const doubl
         predict(mp, Pp, A, vzero<D>(), Q);                        // P_p = A P_f A' + Q
         const Vec<D> V = symvec(Pp, H);
         const double S = dot(V, H) + R;
-        for (int i = 0; i < D; ++i) { cst->K[i] = V[i] / S; cst->H[i] = H[i]; cst->mstart[i] = m1[i]; }
+        for (int i = 0; i < D; ++i) { cst->K[i] = V[i] / S; cst->H[i] = H[i]; }
         cst->S = S; cst->invS = 1.0 / S; cst->logS = log(S); cst->h0 = h0;
         cst->hh = dot(H, a) + h0;
         const Vec<D> w = matTvec(A, H);
@@ -111,6 +209,7 @@ __global__ void __launch_bounds__(128) k_sm_setup(const DevModel dm, const doubl
                 cst->E[i * D + j] = (i == j ? 1.0 : 0.0) - ga;
                 ge = fma(inv.A(i, j), a[j], ge);
                 sS[i * D + j] = inv.C(i, j);
+                cst->Sig[i * D + j] = inv.C(i, j);
             }
             cst->e0[i] = -ge;
         }
@@ -158,23 +257,108 @@ __global__ void __launch_bounds__(128) k_sm_setup(const DevModel dm, const doubl
     }
 }
 
-// After the tail: test the backward covariance, hand over the first backward mean. xtail = packed (m_s, P_s) at T - Nt - 1.
+// ---- tail: smoothing covariance back from P_s[T-1] = P_f^inf until it stops moving; emits var_t of those steps ------------------------
 template <int D>
-__global__ void k_sm_after_tail(const double* __restrict__ xtail, double tol, SmConst<D>* __restrict__ cst) {
-    if (threadIdx.x || blockIdx.x) return;
-    double md = 0.0, ma = 0.0;
-    for (int k = 0; k < Sym<D>::N; ++k) { md = fmax(md, fabs(xtail[D + k] - cst->Psinf[k])); ma = fmax(ma, fabs(cst->Psinf[k])); }
-    cst->err_b = ma > 0.0 ? md / ma : 0.0;
-    cst->conv_b = md <= 100.0 * tol * ma;      // P_s^inf comes from a different summation order than the recursion: allow roundoff
-    for (int i = 0; i < D; ++i) cst->xfirst[i] = xtail[i];
+__global__ void __launch_bounds__(128) k_sm_tail_var(SmConst<D>* __restrict__ cst, long long T, long long nmax, double tol, const double* __restrict__ Rn,
+                                                     long long sR, double* __restrict__ var) {
+    __shared__ double sG[D * D], sSig[D * D], sP[D * D], sT[D * D], sN[D * D], sh[D], red[4];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < D * D; e += 128) { sG[e] = cst->PhiB[0][e]; sSig[e] = cst->Sig[e]; sP[e] = cst->Pfinf[e]; }
+    if (tid < D) sh[tid] = cst->H[tid];
+    __syncthreads();
+    long long n1 = nmax;
+    int conv = 0;
+    for (long long n = 0; n < nmax; ++n) {
+        if (tid == 0) {
+            double v = 0.0;
+            for (int i = 0; i < D; ++i)
+                for (int j = 0; j < D; ++j) v = fma(sh[i] * sh[j], sP[i * D + j], v);
+            var[T - 1 - n] = v + Rn[(T - 1 - n) * sR];
+        }
+        bk_mm<D>(sG, sP, sT);
+        bk_mmT_add<D>(sT, sG, sSig, sN);                             // P_s <- G P_s G' + Sigma
+        double dmax = 0.0, amax = 0.0;
+        for (int e = tid; e < D * D; e += 128) {
+            dmax = fmax(dmax, fabs(sN[e] - sP[e]));
+            amax = fmax(amax, fabs(sN[e]));
+            sP[e] = sN[e];
+        }
+        __syncthreads();
+        if ((n & 15) == 15) {
+            const double d = bk_max(dmax, red), a = bk_max(amax, red);
+            if (d <= tol * a) { n1 = n + 1; conv = 1; break; }
+        }
+    }
+    // cross-check against the fixed point obtained by doubling in k_sm_setup (different summation order: allow roundoff)
+    double dmax = 0.0, amax = 0.0;
+    for (int e = tid; e < D * D; e += 128) {
+        const int i = e / D, j = e % D;
+        const double ps = cst->Psinf[Sym<D>::idx(i, j)];
+        dmax = fmax(dmax, fabs(sP[e] - ps));
+        amax = fmax(amax, fabs(ps));
+    }
+    const double d = bk_max(dmax, red), a = bk_max(amax, red);
+    if (tid == 0) { cst->n1 = n1; cst->err_b = a > 0.0 ? d / a : 0.0; cst->conv_b = conv && d <= 1000.0 * tol * a; }
 }
-// After the backward scan: packed initial state of the head's backward pass, and the combined convergence word.
+
+// ---- head, backward ------------------------------------------------------------------------------------------------------------------
+// Reverse-time dynamics (G_t, g_t, Sigma_t) mapping x_t -> x_{t-1}, t = 1 .. N0-1, one thread per t: the same provider the general
+// backward kernels use (SmootherProvider: predict + invert_dynamics, lgssm.jl:215-240, jitter 1e-10) on the head's stored states.
 template <int D>
-__global__ void k_sm_finish(const double* __restrict__ xlast, SmConst<D>* __restrict__ cst, int* __restrict__ flag) {
-    if (threadIdx.x || blockIdx.x) return;
-    for (int i = 0; i < D; ++i) cst->sback[i] = xlast[i];
-    for (int k = 0; k < Sym<D>::N; ++k) cst->sback[D + k] = cst->Psinf[k];
-    *flag = cst->conv_f && cst->conv_b;
+__global__ void __launch_bounds__(kBlock) k_sm_head_dyn(const SmootherProvider<D> prov, long long N0, double* __restrict__ GG, double* __restrict__ gg,
+                                                        double* __restrict__ SS) {
+    const long long t = (long long)blockIdx.x * kBlock + threadIdx.x + 1;
+    if (t >= N0) return;
+    Aff<D> e;
+    prov.get(prov.dm.T - 1 - t, e);
+    for (int i = 0; i < D; ++i) {
+        gg[t * D + i] = e.b[i];
+        for (int j = 0; j < D; ++j) { GG[t * D * D + i * D + j] = e.A(i, j); SS[t * D * D + i * D + j] = e.C(i, j); }
+    }
+}
+// RTS recursion back from (m_s[N0-1] = xlast, P_s^inf): m_s[t-1] = G_t m_s[t] + g_t, P_s[t-1] = G_t P_s[t] G_t' + Sigma_t;
+// emits mean / var of t = N0-2 .. 0 (t = N0-1 was emitted by the backward scan). Also sets the combined convergence word.
+template <int D>
+__global__ void __launch_bounds__(128) k_sm_head_bwd(const DevModel dm, const SmConst<D>* __restrict__ cst, const double* __restrict__ xlast,
+                                                     const double* __restrict__ GG, const double* __restrict__ gg, const double* __restrict__ SS,
+                                                     const double* __restrict__ Rn, long long sR, double* __restrict__ mean, double* __restrict__ var,
+                                                     int* __restrict__ flag) {
+    __shared__ double sG[D * D], sSig[D * D], sP[D * D], sT[D * D], sN[D * D];
+    __shared__ double sh[D], sm[D], sd[D], sg[D];
+    const int tid = threadIdx.x;
+    const long long N0 = cst->N0;
+    for (int e = tid; e < D * D; e += 128) {
+        const int i = e / D, j = e % D;
+        sP[e] = cst->Psinf[Sym<D>::idx(i, j)];
+    }
+    if (tid < D) { sh[tid] = cst->H[tid]; sm[tid] = xlast[tid]; }
+    if (tid == 0) *flag = cst->conv_f && cst->conv_b;
+    __syncthreads();
+    const double h0 = cst->h0;
+    for (long long t = N0 - 1; t >= 1; --t) {
+        for (int e = tid; e < D * D; e += 128) { sG[e] = GG[t * D * D + e]; sSig[e] = SS[t * D * D + e]; }
+        if (tid < D) { sg[tid] = gg[t * D + tid]; sd[tid] = sm[tid]; }
+        __syncthreads();
+        bk_mm<D>(sG, sP, sT);
+        bk_mmT_add<D>(sT, sG, sSig, sN);
+        if (tid < D) {
+            double ms = sg[tid];
+#pragma unroll
+            for (int k = 0; k < D; ++k) ms = fma(sG[tid * D + k], sd[k], ms);
+            sm[tid] = ms;
+        }
+        for (int e = tid; e < D * D; e += 128) sP[e] = sN[e];
+        __syncthreads();
+        if (tid == 0) {
+            double mu = h0, v = 0.0;
+            for (int i = 0; i < D; ++i) {
+                mu = fma(sh[i], sm[i], mu);
+                for (int j = 0; j < D; ++j) v = fma(sh[i] * sh[j], sP[i * D + j], v);
+            }
+            mean[t - 1] = mu;
+            var[t - 1] = v + Rn[(t - 1) * sR];
+        }
+    }
 }
 
 // ---- item sources / sinks of level 0 -------------------------------------------------------------------------------------------
@@ -375,7 +559,7 @@ __global__ void __launch_bounds__(kCsThreads) k_cs_apply0(const SmConst<D>* __re
 // lml of the steady steps from the per-CTA sums of v^2, added to the head's lml
 template <int D>
 __global__ void __launch_bounds__(256) k_sm_lml(const SmConst<D>* __restrict__ cst, const double* __restrict__ partials, long long np, long long n,
-                                                const double* __restrict__ lml_head, double* __restrict__ out) {
+                                                double* __restrict__ out) {
     __shared__ double sm[256];
     double s = 0.0;
     for (long long i = threadIdx.x; i < np; i += 256) s += partials[i];
@@ -385,29 +569,19 @@ __global__ void __launch_bounds__(256) k_sm_lml(const SmConst<D>* __restrict__ c
         if (threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = *lml_head - 0.5 * ((double)n * (kLog2Pi + cst->logS) + sm[0] * cst->invS);
-}
-
-// filtering distributions of the tail in the smoother's SoA layout: means from MF, covariance P_f^inf (= the head's last one)
-template <int D>
-__global__ void __launch_bounds__(256) k_sm_fill_tail(const double* __restrict__ MF, long long j0, long long Nt, const double* __restrict__ xT_head,
-                                                      double* __restrict__ ws_tail, double* __restrict__ x0_tail, double* __restrict__ xT_tail) {
-    constexpr int SN = D + Sym<D>::N;
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;   // local tail time
-    if (i < Nt) {
-        for (int k = 0; k < D; ++k) ws_tail[(size_t)k * Nt + i] = MF[(j0 + i) * D + k];
-        for (int k = D; k < SN; ++k) ws_tail[(size_t)k * Nt + i] = xT_head[k];
-    }
-    if (i == 0) {
-        for (int k = 0; k < D; ++k) { x0_tail[k] = MF[(j0 - 1) * D + k]; xT_tail[k] = MF[(j0 + Nt - 1) * D + k]; }
-        for (int k = D; k < SN; ++k) { x0_tail[k] = xT_head[k]; xT_tail[k] = xT_head[k]; }
-    }
+    if (threadIdx.x == 0) *out = cst->lml_head - 0.5 * ((double)n * (kLog2Pi + cst->logS) + sm[0] * cst->invS);
 }
 
 template <int D>
 __global__ void k_sm_set_mstart(const SmConst<D>* __restrict__ cst, double* __restrict__ MF) {
     if (threadIdx.x || blockIdx.x) return;
     for (int k = 0; k < D; ++k) MF[k] = cst->mstart[k];
+}
+// the backward scan starts from the smoothed mean at T-1 = the filtered mean there (last entry of MF)
+template <int D>
+__global__ void k_sm_set_xfirst(SmConst<D>* __restrict__ cst, const double* __restrict__ mf_last) {
+    if (threadIdx.x || blockIdx.x) return;
+    for (int k = 0; k < D; ++k) cst->xfirst[k] = mf_last[k];
 }
 
 // Constant-coefficient scan driver. Level sizes n0 = n, n_{k+1} = ceil(n_k / L); three chunk levels and a sequential top.
