@@ -29,13 +29,14 @@
 
 namespace tgp {
 
-constexpr int kCsL = 64;
+constexpr int kCsL = 64;          // items per chunk at level 0
+constexpr int kCsLu = 16;         // items per chunk at the upper levels (few items there: shorter chunks = more threads)
 constexpr int kCsThreads = 128;
 
 template <int D>
 struct SmConst {
-    double PhiF[4][D * D];   // row-major Abar^(L^k), k = 0..3
-    double PhiB[4][D * D];   // row-major G^(L^k)
+    double PhiF[4][D * D];   // row-major Abar^e_k, e = 1, L, L Lu, L Lu^2: the transfer of one item at level k
+    double PhiB[4][D * D];   // row-major G^e_k
     double K[D], c[D], w[D];
     double E[D * D], e0[D];  // row-major E
     double H[D];
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(128) k_sm_head_fwd(const DevModel dm, const do
                                                      SmConst<D>* __restrict__ cst, unsigned long long* __restrict__ err_step) {
     __shared__ double sA[D * D], sQ[D * D], sP[D * D], sT[D * D], sPp[D * D];
     __shared__ double sh[D], sa[D], sm[D], smp[D], sV[D], red[4];
+    __shared__ double sSq[2048];                                    // (S_t, v_t^2 / S_t) of up to 1024 steps awaiting their log
     const int tid = threadIdx.x;
     for (int e = tid; e < D * D; e += 128) {
         const int i = e / D, j = e % D;
@@ -119,7 +121,12 @@ __global__ void __launch_bounds__(128) k_sm_head_fwd(const DevModel dm, const do
         for (int k = 0; k < D; ++k) { S = fma(sh[k], sV[k], S); pred = fma(sh[k], smp[k], pred); }
         if (!(S > 1e-300) || !(S < 1e300)) { if (tid == 0) atomicMin(err_step, (unsigned long long)t); S = 1.0; }
         const double invS = 1.0 / S, v = __ldg(dm.y + t) - pred;
-        if (tid == 0) lml -= 0.5 * (kLog2Pi + log(S) + v * v * invS);
+        if (tid == 0) { sSq[(t & 1023) * 2] = S; sSq[(t & 1023) * 2 + 1] = v * v * invS; }
+        if ((t & 1023) == 1023) {                                   // drain: the logs of 1024 steps, in parallel
+            __syncthreads();
+            for (int q = tid; q < 1024; q += 128) lml -= 0.5 * (kLog2Pi + log(sSq[2 * q]) + sSq[2 * q + 1]);
+            __syncthreads();
+        }
         double dmax = 0.0, amax = 0.0;
         for (int e = tid; e < D * D; e += 128) {
             const int i = e / D, j = e % D;
@@ -141,9 +148,19 @@ __global__ void __launch_bounds__(128) k_sm_head_fwd(const DevModel dm, const do
             if (d <= tol * a) { N0 = t + 1; conv = 1; if (tid == 0) cst->err_f = a > 0.0 ? d / a : 0.0; break; }
         }
     }
+    __syncthreads();
+    {   // the steps since the last drain, then the block total
+        const long long done = N0 & ~1023LL;
+        for (long long q = done + tid; q < N0; q += 128) lml -= 0.5 * (kLog2Pi + log(sSq[2 * (q & 1023)]) + sSq[2 * (q & 1023) + 1]);
+        __shared__ double lred[128];
+        lred[tid] = lml;
+        __syncthreads();
+        for (int off = 64; off > 0; off >>= 1) { if (tid < off) lred[tid] += lred[tid + off]; __syncthreads(); }
+        if (tid == 0) cst->lml_head = lred[0];
+    }
     for (int e = tid; e < D * D; e += 128) cst->Pfinf[e] = sP[e];
     if (tid < D) cst->mstart[tid] = sm[tid];
-    if (tid == 0) { cst->N0 = N0; cst->conv_f = conv; cst->lml_head = lml; }
+    if (tid == 0) { cst->N0 = N0; cst->conv_f = conv; }
 }
 
 
@@ -215,13 +232,13 @@ __global__ void __launch_bounds__(128) k_sm_setup(const DevModel dm, SmConst<D>*
         }
     }
     __syncthreads();
-    // powers Phi^(L^k): L = 64 = 2^6
+    // powers: level-1 items span L = 2^6 steps, every further level Lu = 2^4 items of the previous one
     for (int which = 0; which < 2; ++which) {
         double* base = which == 0 ? sA : sG;
         for (int e = tid; e < D * D; e += blockDim.x) { sB[e] = base[e]; (which == 0 ? cst->PhiF[0] : cst->PhiB[0])[e] = base[e]; }
         __syncthreads();
         for (int lev = 1; lev < 4; ++lev) {
-            for (int sq = 0; sq < 6; ++sq) {
+            for (int sq = 0; sq < (lev == 1 ? 6 : 4); ++sq) {
                 cs_matmul<D>(sB, sB, sC);
                 for (int e = tid; e < D * D; e += blockDim.x) sB[e] = sC[e];
                 __syncthreads();
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(128) k_sm_setup(const DevModel dm, SmConst<D>*
 template <int D>
 __global__ void __launch_bounds__(128) k_sm_tail_var(SmConst<D>* __restrict__ cst, long long T, long long nmax, double tol, const double* __restrict__ Rn,
                                                      long long sR, double* __restrict__ var) {
-    __shared__ double sG[D * D], sSig[D * D], sP[D * D], sT[D * D], sN[D * D], sh[D], red[4];
+    __shared__ double sG[D * D], sSig[D * D], sP[D * D], sT[D * D], sN[D * D], sh[D], sV[D], red[4];
     const int tid = threadIdx.x;
     for (int e = tid; e < D * D; e += 128) { sG[e] = cst->PhiB[0][e]; sSig[e] = cst->Sig[e]; sP[e] = cst->Pfinf[e]; }
     if (tid < D) sh[tid] = cst->H[tid];
@@ -269,13 +286,20 @@ __global__ void __launch_bounds__(128) k_sm_tail_var(SmConst<D>* __restrict__ cs
     long long n1 = nmax;
     int conv = 0;
     for (long long n = 0; n < nmax; ++n) {
-        if (tid == 0) {
+        if (tid >= 128 - D) {                                        // the last warp is idle in the products: V = P h there
+            const int i = tid - (128 - D);
             double v = 0.0;
-            for (int i = 0; i < D; ++i)
-                for (int j = 0; j < D; ++j) v = fma(sh[i] * sh[j], sP[i * D + j], v);
-            var[T - 1 - n] = v + Rn[(T - 1 - n) * sR];
+#pragma unroll
+            for (int j = 0; j < D; ++j) v = fma(sP[i * D + j], sh[j], v);
+            sV[i] = v;
         }
         bk_mm<D>(sG, sP, sT);
+        if (tid == 127) {
+            double v = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) v = fma(sh[i], sV[i], v);
+            var[T - 1 - n] = v + Rn[(T - 1 - n) * sR];
+        }
         bk_mmT_add<D>(sT, sG, sSig, sN);                             // P_s <- G P_s G' + Sigma
         double dmax = 0.0, amax = 0.0;
         for (int e = tid; e < D * D; e += 128) {
@@ -324,7 +348,7 @@ __global__ void __launch_bounds__(128) k_sm_head_bwd(const DevModel dm, const Sm
                                                      const double* __restrict__ Rn, long long sR, double* __restrict__ mean, double* __restrict__ var,
                                                      int* __restrict__ flag) {
     __shared__ double sG[D * D], sSig[D * D], sP[D * D], sT[D * D], sN[D * D];
-    __shared__ double sh[D], sm[D], sd[D], sg[D];
+    __shared__ double sh[D], sm[D], sd[D], sg[D], sV[D];
     const int tid = threadIdx.x;
     const long long N0 = cst->N0;
     for (int e = tid; e < D * D; e += 128) {
@@ -348,13 +372,18 @@ __global__ void __launch_bounds__(128) k_sm_head_bwd(const DevModel dm, const Sm
             sm[tid] = ms;
         }
         for (int e = tid; e < D * D; e += 128) sP[e] = sN[e];
+        if (tid >= 128 - D) {                                        // V = P_s h from the fresh sN (the idle last warp)
+            const int i = tid - (128 - D);
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) v = fma(sN[i * D + j], sh[j], v);
+            sV[i] = v;
+        }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 127) {
             double mu = h0, v = 0.0;
-            for (int i = 0; i < D; ++i) {
-                mu = fma(sh[i], sm[i], mu);
-                for (int j = 0; j < D; ++j) v = fma(sh[i] * sh[j], sP[i * D + j], v);
-            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) { mu = fma(sh[i], sm[i], mu); v = fma(sh[i], sV[i], v); }
             mean[t - 1] = mu;
             var[t - 1] = v + Rn[(t - 1) * sR];
         }
@@ -430,7 +459,7 @@ __global__ void __launch_bounds__(kCsThreads) k_cs_reduce(const double* __restri
     for (int e = threadIdx.x; e < D * D; e += kCsThreads) Phi[e] = PhiG[e];
     __syncthreads();
     const long long ch = (long long)blockIdx.x * kCsThreads + threadIdx.x;
-    const long long s = ch * kCsL, e = min(s + (long long)kCsL, n);
+    const long long s = ch * kCsLu, e = min(s + (long long)kCsLu, n);
     if (s >= n) return;
     double x[D], t[D];
 #pragma unroll
@@ -470,7 +499,7 @@ __global__ void __launch_bounds__(kCsThreads) k_cs_apply(const double* __restric
     for (int e = threadIdx.x; e < D * D; e += kCsThreads) Phi[e] = PhiG[e];
     __syncthreads();
     const long long ch = (long long)blockIdx.x * kCsThreads + threadIdx.x;
-    const long long s = ch * kCsL, e = min(s + (long long)kCsL, n);
+    const long long s = ch * kCsLu, e = min(s + (long long)kCsLu, n);
     if (s >= n) return;
     double x[D], t[D];
 #pragma unroll
@@ -584,11 +613,12 @@ __global__ void k_sm_set_xfirst(SmConst<D>* __restrict__ cst, const double* __re
     for (int k = 0; k < D; ++k) cst->xfirst[k] = mf_last[k];
 }
 
-// Constant-coefficient scan driver. Level sizes n0 = n, n_{k+1} = ceil(n_k / L); three chunk levels and a sequential top.
+// Constant-coefficient scan driver. Level sizes n1 = ceil(n / L), n2 = ceil(n1 / Lu), n3 = ceil(n2 / Lu); three chunk levels and a
+// sequential top over n3 items.
 template <int D, bool FWD>
 int cs_scan(tgp_ctx* h, const SmConst<D>* cst, const FwdItems<D>& fi, const BwdItems<D>& bi, long long n, const double* xinit, double* xlast) {
     cudaStream_t st = h->stream;
-    const long long n1 = (n + kCsL - 1) / kCsL, n2 = (n1 + kCsL - 1) / kCsL, n3 = (n2 + kCsL - 1) / kCsL;
+    const long long n1 = (n + kCsL - 1) / kCsL, n2 = (n1 + kCsLu - 1) / kCsLu, n3 = (n2 + kCsLu - 1) / kCsLu;
     double *z1, *z2, *z3, *X1, *X2, *X3;
     TGP_TRY(dalloc(h, (size_t)n1 * D, &z1));
     TGP_TRY(dalloc(h, (size_t)n2 * D, &z2));
