@@ -76,6 +76,7 @@ int begin_call(tgp_ctx* h) {
     h->pending.clear();
     TGP_CUDA(h, cudaSetDevice(h->device));
     TGP_TRY(resolve_deferred(h));
+    if (h->aux_stream) TGP_CUDA(h, cudaStreamSynchronize(h->aux_stream));   // nothing of an earlier (failed) call may still use the arena
     TGP_CUDA(h, h->arena.reset());
     return TGP_OK;
 }
@@ -135,6 +136,7 @@ void tgp_destroy(tgp_handle h) {
     for (auto& sp : h->spans) { cudaEventDestroy(sp.t0); cudaEventDestroy(sp.t1); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->aux_fork); cudaEventDestroy(h->aux_join); }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }

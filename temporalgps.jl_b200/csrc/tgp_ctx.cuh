@@ -69,6 +69,8 @@ struct tgp_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;     // side stream for work that can overlap the main chain (created on first use)
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     tgp::Arena arena;
     std::string err;
     int64_t launches = 0, h2d = 0, d2h = 0;
@@ -206,6 +208,23 @@ inline void prof_end(tgp_ctx* h) {
         ++(h)->launches;                                                                        \
         tgp::prof_end(h);                                                                       \
     } while (0)
+
+// Side stream: aux_begin makes it wait for everything enqueued on h->stream so far; aux_end makes h->stream wait for it.
+inline int aux_begin(tgp_ctx* h) {
+    if (!h->aux_stream) {
+        TGP_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        TGP_CUDA(h, cudaEventCreateWithFlags(&h->aux_fork, cudaEventDisableTiming));
+        TGP_CUDA(h, cudaEventCreateWithFlags(&h->aux_join, cudaEventDisableTiming));
+    }
+    TGP_CUDA(h, cudaEventRecord(h->aux_fork, h->stream));
+    TGP_CUDA(h, cudaStreamWaitEvent(h->aux_stream, h->aux_fork, 0));
+    return TGP_OK;
+}
+inline int aux_end(tgp_ctx* h) {
+    TGP_CUDA(h, cudaEventRecord(h->aux_join, h->aux_stream));
+    TGP_CUDA(h, cudaStreamWaitEvent(h->stream, h->aux_join, 0));
+    return TGP_OK;
+}
 
 template <class T>
 inline int dalloc(tgp_ctx* h, size_t n, T** out) {

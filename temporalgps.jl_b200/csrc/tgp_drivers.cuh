@@ -229,6 +229,28 @@ int posterior_marginals_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy,
     h->d2h += 12;
     const int64_t N0 = *pN0;
     if (!*pconv || T < N0 + 2 * kSmMaxEnd) return TGP_OK;          // not converged (or too short): general path
+    // side stream: the tail's covariance recursion and the head's reverse-time dynamics need only the set-up; they overlap the scans
+    double* tvar;
+    TGP_TRY(dalloc(h, (size_t)kSmMaxEnd, &tvar));
+    TGP_TRY(dalloc(h, (size_t)N0 * D * D, &GG));
+    TGP_TRY(dalloc(h, (size_t)N0 * D * D, &SS));
+    TGP_TRY(dalloc(h, (size_t)N0 * D, &gg));
+    const bool overlap = !h->timing;                         // per-kernel timing brackets launches on h->stream only
+    cudaStream_t sx = st;
+    if (overlap) { TGP_TRY(aux_begin(h)); sx = h->aux_stream; }
+    TGP_K(h, "k_sm_tail_var");
+    k_sm_tail_var<D><<<1, 128, 0, sx>>>(cst, kSmMaxEnd, h->ss_tol, tvar);
+    TGP_LAUNCH_CHECK(h);
+    if (N0 > 1) {
+        SmootherProvider<D> ph;     // stored states of the head, SoA with stride kSmMaxEnd (the provider's dm.T is that stride)
+        ph.dm = DevModel{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, nullptr, 1, kSmMaxEnd};
+        ph.ws = wsh;
+        ph.x0buf = x0buf;           // never read: t >= 1
+        ph.err_step = err;
+        TGP_K(h, "k_sm_head_dyn");
+        k_sm_head_dyn<D><<<(unsigned)((N0 + kBlock - 1) / kBlock), kBlock, 0, sx>>>(ph, N0, GG, gg, SS);
+        TGP_LAUNCH_CHECK(h);
+    }
     // forward means of [N0, T): MF[j] = m_f[N0 - 1 + j]
     const int64_t nf = T - N0;
     double *MF, *partials, *lml_dev, *xlast;
@@ -253,25 +275,13 @@ int posterior_marginals_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy,
     const int64_t nbk = T - N0 + 1;
     bi = BwdItems<D>{MF, nf, T - 1, dRn, sRnew, dmean, dvar};
     TGP_TRY((cs_scan<D, false>(h, cst, fi, bi, nbk, nullptr, xlast)));
-    TGP_K(h, "k_sm_tail_var");
-    k_sm_tail_var<D><<<1, 128, 0, st>>>(cst, T, kSmMaxEnd, h->ss_tol, dRn, sRnew, dvar);
+    if (overlap) TGP_TRY(aux_end(h));
+    TGP_K(h, "k_sm_tail_copy");
+    k_sm_tail_copy<D><<<8, 256, 0, st>>>(cst, tvar, T, dRn, sRnew, dvar);
     TGP_LAUNCH_CHECK(h);
     // head, backward
-    TGP_TRY(dalloc(h, (size_t)N0 * D * D, &GG));
-    TGP_TRY(dalloc(h, (size_t)N0 * D * D, &SS));
-    TGP_TRY(dalloc(h, (size_t)N0 * D, &gg));
     int* flag;
     TGP_TRY(dalloc(h, 1, &flag));
-    if (N0 > 1) {
-        SmootherProvider<D> ph;     // stored states of the head, SoA with stride kSmMaxEnd (the provider's dm.T is that stride)
-        ph.dm = DevModel{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, nullptr, 1, kSmMaxEnd};
-        ph.ws = wsh;
-        ph.x0buf = x0buf;           // never read: t >= 1
-        ph.err_step = err;
-        TGP_K(h, "k_sm_head_dyn");
-        k_sm_head_dyn<D><<<(unsigned)((N0 + kBlock - 1) / kBlock), kBlock, 0, st>>>(ph, N0, GG, gg, SS);
-        TGP_LAUNCH_CHECK(h);
-    }
     TGP_K(h, "k_sm_head_bwd");
     k_sm_head_bwd<D><<<1, 128, 0, st>>>(dm, cst, xlast, GG, gg, SS, dRn, sRnew, dmean, dvar, flag);
     TGP_LAUNCH_CHECK(h);

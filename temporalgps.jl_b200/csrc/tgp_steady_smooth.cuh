@@ -13,7 +13,7 @@
 //                          until |P_f[t] - P_f[t-1]| <= tol |P_f| (N0 ~ 10^3), keeping P_f[t], P_p[t], m_f[t];
 //                          k_sm_head_dyn: (G_t, Sigma_t) of those steps, one thread per step (invert_dynamics, lgssm.jl:231-240);
 //                          k_sm_head_bwd: ONE CTA runs the RTS recursion back from (m_s[N0-1], P_s^inf) and emits the marginals;
-//     tail  (T - n1, T)    k_sm_tail_var: ONE CTA iterates P_s <- G P_s G' + Sigma back from P_s[T-1] = P_f^inf until it stops moving,
+//     tail  (T - n1, T)    k_sm_tail_var (on a side stream, overlapping the scans): ONE CTA iterates P_s <- G P_s G' + Sigma back from P_s[T-1] = P_f^inf until it stops moving,
 //                          emitting var_t (the tail MEANS follow the constant-coefficient recursion: G is constant there);
 //     means [N0, T)        two constant-coefficient scans over vectors (forward filter means, backward smoother means).
 // Convergence is CHECKED on the device against TGP_OPT_SS_TOL (the forward test inside k_sm_head_fwd, the backward one inside
@@ -276,8 +276,7 @@ __global__ void __launch_bounds__(128) k_sm_setup(const DevModel dm, SmConst<D>*
 
 // ---- tail: smoothing covariance back from P_s[T-1] = P_f^inf until it stops moving; emits var_t of those steps ------------------------
 template <int D>
-__global__ void __launch_bounds__(128) k_sm_tail_var(SmConst<D>* __restrict__ cst, long long T, long long nmax, double tol, const double* __restrict__ Rn,
-                                                     long long sR, double* __restrict__ var) {
+__global__ void __launch_bounds__(128) k_sm_tail_var(SmConst<D>* __restrict__ cst, long long nmax, double tol, double* __restrict__ tvar) {
     __shared__ double sG[D * D], sSig[D * D], sP[D * D], sT[D * D], sN[D * D], sh[D], sV[D], red[4];
     const int tid = threadIdx.x;
     for (int e = tid; e < D * D; e += 128) { sG[e] = cst->PhiB[0][e]; sSig[e] = cst->Sig[e]; sP[e] = cst->Pfinf[e]; }
@@ -298,7 +297,7 @@ __global__ void __launch_bounds__(128) k_sm_tail_var(SmConst<D>* __restrict__ cs
             double v = 0.0;
 #pragma unroll
             for (int i = 0; i < D; ++i) v = fma(sh[i], sV[i], v);
-            var[T - 1 - n] = v + Rn[(T - 1 - n) * sR];
+            tvar[n] = v;                                              // H P_s[T-1-n] H' (the caller adds R_new)
         }
         bk_mmT_add<D>(sT, sG, sSig, sN);                             // P_s <- G P_s G' + Sigma
         double dmax = 0.0, amax = 0.0;
@@ -323,6 +322,15 @@ __global__ void __launch_bounds__(128) k_sm_tail_var(SmConst<D>* __restrict__ cs
     }
     const double d = bk_max(dmax, red), a = bk_max(amax, red);
     if (tid == 0) { cst->n1 = n1; cst->err_b = a > 0.0 ? d / a : 0.0; cst->conv_b = conv && d <= 1000.0 * tol * a; }
+}
+
+// var[T-1-n] = tvar[n] + R_new for the n1 tail steps (runs after both the tail recursion and the backward scan)
+template <int D>
+__global__ void __launch_bounds__(256) k_sm_tail_copy(const SmConst<D>* __restrict__ cst, const double* __restrict__ tvar, long long T,
+                                                      const double* __restrict__ Rn, long long sR, double* __restrict__ var) {
+    const long long n1 = cst->n1;
+    for (long long n = (long long)blockIdx.x * 256 + threadIdx.x; n < n1; n += (long long)gridDim.x * 256)
+        var[T - 1 - n] = tvar[n] + Rn[(T - 1 - n) * sR];
 }
 
 // ---- head, backward ------------------------------------------------------------------------------------------------------------------
