@@ -178,6 +178,21 @@ int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial);
  * (tgp_shard_phase2: TGP_ENOTPD / TGP_EUNSUPPORTED "not converged"). The next call on the handle does the same. */
 int tgp_synchronize(tgp_handle h);
 
+/* Peer-memory exchange for the sharded path (one process per GPU, NVLink / NVSwitch P2P): replaces the all-gather of the
+ * records and the all-reduce of the partial log-likelihoods by direct stores into every peer's buffer + a flag, all
+ * stream-ordered on the handle's stream (no NCCL call, no host round trip):
+ *     tgp_shard_phase1 -> tgp_xchg_put(0, rec) -> tgp_xchg_wait(0, n, recs, 0) -> tgp_shard_phase2 -> tgp_xchg_put(1, lml)
+ *     -> tgp_xchg_wait(1, 1, lml_total, 1)
+ * tgp_xchg_create allocates this rank's buffer and returns its 64-byte CUDA IPC handle; the caller gathers the handles of
+ * all ranks (any transport) and passes them, rank-ordered, to tgp_xchg_open. put copies n doubles (n <= slot_doubles) into
+ * this rank's slot of `channel` (0 or 1) on EVERY rank and raises the slot's flag; wait mode 0 waits for the ranks before
+ * this one and copies their slots to dst[p*n ..]; mode 1 waits for all ranks and writes the sum over ranks to dst[0..n).
+ * src / dst are device pointers. Every rank must issue the same sequence of put / wait calls. */
+int tgp_xchg_create(tgp_handle h, int rank, int world, int slot_doubles, void* ipc_handle_out);
+int tgp_xchg_open(tgp_handle h, const void* ipc_handles_all);
+int tgp_xchg_put(tgp_handle h, int channel, const double* src, int n);
+int tgp_xchg_wait(tgp_handle h, int channel, int n, double* dst, int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,6 +132,7 @@ void tgp_destroy(tgp_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    xchg_destroy(h);
     h->arena.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.t0); cudaEventDestroy(sp.t1); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
@@ -309,6 +310,25 @@ int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial) 
 }
 
 int tgp_shard_xchg_size(int D) { return D * D + D; }
+
+int tgp_xchg_create(tgp_handle h, int rank, int world, int slot_doubles, void* ipc_handle_out) {
+    if (!h || !ipc_handle_out) return TGP_EINVAL;
+    TGP_CUDA(h, cudaSetDevice(h->device));
+    return xchg_create(h, rank, world, slot_doubles, ipc_handle_out);
+}
+int tgp_xchg_open(tgp_handle h, const void* ipc_handles_all) {
+    if (!h || !ipc_handles_all) return TGP_EINVAL;
+    TGP_CUDA(h, cudaSetDevice(h->device));
+    return xchg_open(h, ipc_handles_all);
+}
+int tgp_xchg_put(tgp_handle h, int channel, const double* src, int n) {
+    if (!h) return TGP_EINVAL;
+    return xchg_put(h, channel, src, n);
+}
+int tgp_xchg_wait(tgp_handle h, int channel, int n, double* dst, int mode) {
+    if (!h) return TGP_EINVAL;
+    return xchg_wait(h, channel, n, dst, mode);
+}
 
 int tgp_synchronize(tgp_handle h) {
     if (!h) return TGP_EINVAL;

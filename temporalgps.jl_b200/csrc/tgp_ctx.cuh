@@ -93,6 +93,7 @@ struct tgp_ctx {
     tgp_shard_state shard;
     const unsigned long long* deferred_res = nullptr;   // result block {err, lml, converged} of an un-synchronised call
     int64_t deferred_T = 0;
+    void* xchg = nullptr;                               // tgp::XchgState: peer-memory exchange of the time-sharded path (tgp_xchg.cu)
 };
 
 namespace tgp {

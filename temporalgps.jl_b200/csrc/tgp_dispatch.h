@@ -22,6 +22,13 @@ template <int D> int do_shard_prefix(int n, const double* elems, const double* m
 int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out, double* lml_steps, double* m_f, int64_t s_m,
                  double* P_f, int64_t s_P);
 
+// Peer-memory exchange of the time-sharded path (tgp_xchg.cu).
+int xchg_create(tgp_ctx* h, int rank, int world, int slot_doubles, void* ipc_handle_out);
+int xchg_open(tgp_ctx* h, const void* handles_all);
+int xchg_put(tgp_ctx* h, int ch, const double* src, int n);
+int xchg_wait(tgp_ctx* h, int ch, int n, double* dst, int mode);
+void xchg_destroy(tgp_ctx* h);
+
 // Test hook for the tcgen05 contraction kernel alone (tgp_dense_tc.cuh).
 int tc_gemm_selftest(tgp_ctx* h, int K, int Mx, int N, const float* X, const float* Y, float* C, int symmetric);
 

@@ -1,0 +1,147 @@
+// tgp_xchg.cu — peer-memory exchange for the time-sharded path: the per-shard record and the partial
+// log-likelihood travel by direct NVLink / NVSwitch stores into every peer's buffer, with a flag per (channel, source rank),
+// instead of an NCCL all-gather / all-reduce. One process per GPU: the buffers are shared through CUDA IPC handles that the
+// host exchanges once (any transport; sharded.py uses torch.distributed). Everything is stream-ordered on the handle's stream:
+//     tgp_shard_phase1 -> tgp_xchg_put(0) -> tgp_xchg_wait(0) -> tgp_shard_phase2 -> tgp_xchg_put(1) -> tgp_xchg_wait(1)
+// Slots are double-buffered by epoch parity (a fast rank may start the next call before a slow one has read this call's slot;
+// it cannot get two epochs ahead because the log-likelihood channel waits for every rank).
+#include "tgp_ctx.cuh"
+
+namespace tgp {
+
+constexpr int kXchgChannels = 2;
+
+struct XchgState {
+    int rank = 0, world = 0, slot = 0;          // slot: doubles per (channel, parity, rank)
+    char* self = nullptr;                       // this rank's buffer (cudaMalloc)
+    std::vector<char*> peers;                   // mapped buffers of all ranks (peers[rank] = self)
+    char** d_peers = nullptr;                   // the same on the device
+    unsigned long long epoch[kXchgChannels] = {0, 0};
+    size_t flag_off = 0, bytes = 0;
+};
+
+__device__ __forceinline__ size_t xchg_data_off(int ch, int parity, int world, int slot, int r) {
+    return ((size_t)((ch * 2 + parity) * world + r) * slot) * sizeof(double);
+}
+
+// Copy n doubles into slot[rank] of every peer, then raise flag[ch][rank] = epoch there.
+__global__ void __launch_bounds__(128) k_xchg_put(char* const* __restrict__ peers, int world, int rank, int ch, int parity, int slot,
+                                                  const double* __restrict__ src, int n, unsigned long long epoch, size_t flag_off) {
+    const size_t off = xchg_data_off(ch, parity, world, slot, rank);
+    for (int e = threadIdx.x; e < n * world; e += blockDim.x) {
+        const int p = e / n, i = e % n;
+        reinterpret_cast<double*>(peers[p] + off)[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + flag_off) + (size_t)ch * world + rank;
+        *f = epoch;
+    }
+}
+
+// mode 0: wait for the ranks before this one, copy their slots to dst[p * n ..] (the records a shard's phase 2 folds);
+// mode 1: wait for every rank, dst[0 .. n) = sum over ranks (the log-likelihood). Bounded spin: a lost peer traps.
+__global__ void __launch_bounds__(128) k_xchg_wait(const char* __restrict__ self, int world, int rank, int ch, int parity, int slot, int n,
+                                                   unsigned long long epoch, size_t flag_off, double* __restrict__ dst, int mode) {
+    const int need = mode == 0 ? rank : world;
+    if (threadIdx.x < need) {
+        const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(self + flag_off) + (size_t)ch * world + threadIdx.x;
+        unsigned long long spins = 0;
+        while (*f < epoch) {
+            if (++spins > (1ull << 31)) __trap();
+            __nanosleep(20);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (mode == 0) {
+        for (int e = threadIdx.x; e < need * n; e += blockDim.x) {
+            const int p = e / n, i = e % n;
+            dst[(size_t)p * n + i] = __ldcg(reinterpret_cast<const double*>(self + xchg_data_off(ch, parity, world, slot, p)) + i);
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            double s = 0.0;
+            for (int p = 0; p < world; ++p) s += __ldcg(reinterpret_cast<const double*>(self + xchg_data_off(ch, parity, world, slot, p)) + i);
+            dst[i] = s;
+        }
+    }
+}
+
+int xchg_create(tgp_ctx* h, int rank, int world, int slot_doubles, void* ipc_handle_out) {
+    if (h->xchg) return fail(h, TGP_EINVAL, "tgp_xchg_create called twice on this handle");
+    if (world < 1 || world > 128 || rank < 0 || rank >= world || slot_doubles < 1) return fail(h, TGP_EINVAL, "bad rank / world / slot size");
+    XchgState* x = new XchgState();
+    x->rank = rank; x->world = world; x->slot = slot_doubles;
+    x->flag_off = (size_t)kXchgChannels * 2 * world * slot_doubles * sizeof(double);
+    x->bytes = x->flag_off + (size_t)kXchgChannels * world * sizeof(unsigned long long);
+    if (cudaMalloc((void**)&x->self, x->bytes) != cudaSuccess || cudaMemset(x->self, 0, x->bytes) != cudaSuccess) {
+        delete x;
+        return fail(h, TGP_ENOMEM, "exchange buffer allocation failed");
+    }
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, x->self);
+    if (e != cudaSuccess) {
+        cudaFree(x->self);
+        delete x;
+        return fail(h, TGP_ECUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(ipc_handle_out, &hd, 64);
+    h->xchg = x;
+    return TGP_OK;
+}
+
+int xchg_open(tgp_ctx* h, const void* handles_all) {
+    XchgState* x = (XchgState*)h->xchg;
+    if (!x) return fail(h, TGP_EINVAL, "tgp_xchg_open before tgp_xchg_create");
+    x->peers.assign(x->world, nullptr);
+    for (int p = 0; p < x->world; ++p) {
+        if (p == x->rank) { x->peers[p] = x->self; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)handles_all + (size_t)p * 64, 64);
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(h, TGP_ECUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", p, cudaGetErrorString(e));
+        x->peers[p] = (char*)ptr;
+    }
+    TGP_CUDA(h, cudaMalloc((void**)&x->d_peers, sizeof(char*) * x->world));
+    TGP_CUDA(h, cudaMemcpy(x->d_peers, x->peers.data(), sizeof(char*) * x->world, cudaMemcpyHostToDevice));
+    return TGP_OK;
+}
+
+int xchg_put(tgp_ctx* h, int ch, const double* src, int n) {
+    XchgState* x = (XchgState*)h->xchg;
+    if (!x || !x->d_peers) return fail(h, TGP_EINVAL, "exchange not opened");
+    if (ch < 0 || ch >= kXchgChannels || n < 1 || n > x->slot || !is_device_ptr(src)) return fail(h, TGP_EINVAL, "bad channel / size / pointer");
+    const unsigned long long ep = ++x->epoch[ch];
+    TGP_K(h, "k_xchg_put");
+    k_xchg_put<<<1, 128, 0, h->stream>>>(x->d_peers, x->world, x->rank, ch, (int)(ep & 1), x->slot, src, n, ep, x->flag_off);
+    TGP_LAUNCH_CHECK(h);
+    return TGP_OK;
+}
+
+int xchg_wait(tgp_ctx* h, int ch, int n, double* dst, int mode) {
+    XchgState* x = (XchgState*)h->xchg;
+    if (!x || !x->d_peers) return fail(h, TGP_EINVAL, "exchange not opened");
+    if (ch < 0 || ch >= kXchgChannels || n < 1 || n > x->slot || !is_device_ptr(dst) || (mode != 0 && mode != 1)) return fail(h, TGP_EINVAL, "bad channel / size / pointer / mode");
+    const unsigned long long ep = x->epoch[ch];
+    TGP_K(h, "k_xchg_wait");
+    k_xchg_wait<<<1, 128, 0, h->stream>>>(x->self, x->world, x->rank, ch, (int)(ep & 1), x->slot, n, ep, x->flag_off, dst, mode);
+    TGP_LAUNCH_CHECK(h);
+    return TGP_OK;
+}
+
+void xchg_destroy(tgp_ctx* h) {
+    XchgState* x = (XchgState*)h->xchg;
+    if (!x) return;
+    for (int p = 0; p < (int)x->peers.size(); ++p)
+        if (p != x->rank && x->peers[p]) cudaIpcCloseMemHandle(x->peers[p]);
+    if (x->d_peers) cudaFree(x->d_peers);
+    if (x->self) cudaFree(x->self);
+    delete x;
+    h->xchg = nullptr;
+}
+
+}  // namespace tgp

@@ -54,17 +54,49 @@ class ShardedLogpdf:
         d = marshalled.desc
         self.time_invariant = not (d.sA or d.sa or d.sQ or d.sH or d.sh or d.sR) and d.ordering == 0 and d.T >= 65536
         XS = self.D * self.D + self.D
+        self.XS = XS
         self.rec = torch.zeros(XS, dtype=torch.float64, device=device)
         self.recs = torch.zeros(world * XS, dtype=torch.float64, device=device)
+        # Exchange transport of the steady route: "p2p" = the library's peer-memory kernels (NVLink / NVSwitch stores + flags,
+        # tgp_xchg_*), "nccl" = all_gather + all_reduce. p2p needs CUDA IPC between the ranks' GPUs; fall back if it is unavailable.
+        import os
+        self.transport = "nccl"
+        if self.time_invariant and world > 1 and device.type == "cuda" and os.environ.get("TGP_XCHG", "p2p") == "p2p":
+            mine, err = None, None
+            try:
+                mine = handle.xchg_create(rank, world, max(XS, 16))
+            except Exception as exc:      # noqa: BLE001 — reported below, NCCL is used instead
+                err = str(exc)
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)          # once per run: 64-byte CUDA IPC handles, any backend
+            ok = False
+            if all(hd is not None for hd in handles):
+                try:
+                    handle.xchg_open(b"".join(handles))
+                    ok = True
+                except Exception as exc:  # noqa: BLE001
+                    err = str(exc)
+            oks = [None] * world
+            dist.all_gather_object(oks, ok)                # every rank must agree on the transport
+            self.transport_error = err
+            if all(oks):
+                self.transport = "p2p"
 
     def logpdf(self, y_dev, lml_out_dev):
         """y_dev: this rank's shard, resident on its GPU. lml_out_dev: 1-element CUDA tensor (all ranks get the total)."""
         h, dist = self.h, self.dist
         if self.time_invariant:
             h.shard_phase1(self.mm.desc, y_dev, self.rank, self.world, self.rec)
-            dist.all_gather_into_tensor(self.recs, self.rec)
-            h.shard_phase2(self.recs, lml_out_dev)     # enqueued, not synchronised
-            dist.all_reduce(lml_out_dev)
+            if self.transport == "p2p":
+                h.xchg_put(0, self.rec, self.XS)            # record -> every peer's slot, over NVLink
+                h.xchg_wait(0, self.XS, self.recs, 0)       # records of the ranks before this one
+                h.shard_phase2(self.recs, self.part)        # enqueued, not synchronised
+                h.xchg_put(1, self.part, 1)
+                h.xchg_wait(1, 1, lml_out_dev, 1)           # sum of the partial log-likelihoods, on every rank
+            else:
+                dist.all_gather_into_tensor(self.recs, self.rec)
+                h.shard_phase2(self.recs, lml_out_dev)     # enqueued, not synchronised
+                dist.all_reduce(lml_out_dev)
             h.synchronize()                             # status of the shard (convergence, positive-definiteness)
             return
         h.shard_reduce(self.mm.desc, y_dev, self.elem)

@@ -1,0 +1,62 @@
+"""GPU test of the peer-memory exchange (tgp_xchg.cu) through the time-sharded steady-state logpdf: TWO processes, both on
+cuda:0 (the test box has one GPU; CUDA IPC works between processes on the same device), rendezvous over gloo. Each rank
+owns half of one series; records and partial log-likelihoods travel through the mapped peer buffers + flags, no NCCL. The
+total must equal the sequential oracle on the whole series (1e-6 relative, north_star) for several consecutive calls (epoch
+parity, slot reuse)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["TGP_ROOT"])
+import __graft_entry__ as g
+from oracle import c_oracle, tgp_oracle as O
+pkg = g.load_package()
+from temporalgps_jl_b200 import sharded
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+dev = torch.device("cuda:0")
+torch.cuda.set_device(0)
+Ts = 100_000                                  # per shard (the steady route needs >= 65536)
+T = Ts * world
+h = pkg.Handle(0)
+h.set_stream(torch.cuda.current_stream().cuda_stream)
+fx = pkg.to_sde(pkg.GP(pkg.Matern52Kernel()))(pkg.RegularSpacing(0.0, 0.01, Ts), 0.1)
+mm = pkg.lgssm._Marshalled(fx.build_lgssm())
+sh = sharded.ShardedLogpdf(h, mm, rank, world, dev, dist)
+assert sh.transport == "p2p", getattr(sh, "transport_error", None)
+mo = O.build_lgssm(O.Matern52(), O.RegularSpacing(0.0, 0.01, T), 0.1)
+cm = c_oracle.Model.from_lgssm(mo)
+out = torch.zeros(1, dtype=torch.float64, device=dev)
+for rep in range(4):
+    rng = np.random.default_rng(100 + rep)    # same series on every rank
+    y = np.sin(np.arange(T) * 0.003) + 0.4 * rng.standard_normal(T)
+    yd = torch.from_numpy(np.ascontiguousarray(y[rank * Ts:(rank + 1) * Ts])).to(dev)
+    sh.logpdf(yd, out)
+    torch.cuda.synchronize()
+    ref = c_oracle.logpdf(cm, y)
+    got = float(out.item())
+    assert abs(got - ref) <= 1e-6 * abs(ref), (rep, got, ref)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_time_sharded_logpdf_peer_memory_exchange(pkg, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, TGP_ROOT=ROOT, OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    assert p.stdout.count("ok") == 2
