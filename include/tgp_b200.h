@@ -56,6 +56,9 @@ extern "C" {
 #define TGP_OPT_TIMING       4  /* 1: bracket every kernel launch with CUDA events (tgp_get_timing) */
 #define TGP_OPT_SS_PREFIX    5  /* steps filtered by the general scan before the steady-state test */
 #define TGP_OPT_DENSE_MATH   6  /* arithmetic of the large-state / vector-observation path (tgp_dense.cu)      */
+#define TGP_OPT_DEFER_STATUS 7  /* 1: tgp_shard_phase2 calls fold their status into a sticky device block and the next call does
+                                 * NOT wait for it (consecutive sharded calls queue back to back on the stream);
+                                 * tgp_synchronize() reports and clears the accumulated status                  */
 #define TGP_DENSE_F64        0  /* FP64 throughout (reference ArrayStorage(Float64)); library GEMMs              */
 #define TGP_DENSE_TF32X3     1  /* FP32 storage (reference ArrayStorage(Float32)): covariance algebra on the tcgen05
                                  * tensor cores as 3xTF32 split products with FP32 accumulation in TMEM; innovation
@@ -187,7 +190,10 @@ int tgp_synchronize(tgp_handle h);
  * all ranks (any transport) and passes them, rank-ordered, to tgp_xchg_open. put copies n doubles (n <= slot_doubles) into
  * this rank's slot of `channel` (0 or 1) on EVERY rank and raises the slot's flag; wait mode 0 waits for the ranks before
  * this one and copies their slots to dst[p*n ..]; mode 1 waits for all ranks and writes the sum over ranks to dst[0..n).
- * src / dst are device pointers. Every rank must issue the same sequence of put / wait calls. */
+ * src / dst are device pointers. Every rank must issue the same sequence of put / wait calls.
+ * FUSED FORM: once tgp_xchg_open has succeeded, tgp_shard_phase1 / tgp_shard_phase2 do the channel-0 put / wait and the
+ * channel-1 put INSIDE their kernels (the sequence is then phase1 -> phase2 -> tgp_xchg_wait(1, 1, total, 1)); the caller must
+ * not put on those channels itself. xchg_all of tgp_shard_phase2 is then unused (the records are read from the exchange buffer). */
 int tgp_xchg_create(tgp_handle h, int rank, int world, int slot_doubles, void* ipc_handle_out);
 int tgp_xchg_open(tgp_handle h, const void* ipc_handles_all);
 int tgp_xchg_put(tgp_handle h, int channel, const double* src, int n);

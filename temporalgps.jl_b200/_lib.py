@@ -20,6 +20,7 @@ TGP_R_SCALAR, TGP_R_DIAG, TGP_R_DENSE = 0, 1, 2
 TGP_OPT_ALGO, TGP_OPT_CHUNK, TGP_OPT_SS_TOL, TGP_OPT_TIMING, TGP_OPT_SS_PREFIX = 1, 2, 3, 4, 5
 TGP_ALGO_AUTO, TGP_ALGO_SCAN = 0, 1
 TGP_OPT_DENSE_MATH = 6
+TGP_OPT_DEFER_STATUS = 7
 TGP_DENSE_F64, TGP_DENSE_TF32X3 = 0, 1
 
 

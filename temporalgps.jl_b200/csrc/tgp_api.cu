@@ -137,6 +137,7 @@ void tgp_destroy(tgp_handle h) {
     for (auto& sp : h->spans) { cudaEventDestroy(sp.t0); cudaEventDestroy(sp.t1); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->sticky) cudaFree(h->sticky);
     if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->aux_fork); cudaEventDestroy(h->aux_join); }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
@@ -173,6 +174,15 @@ int tgp_set_option(tgp_handle h, int option, int64_t value) {
         case TGP_OPT_SS_PREFIX:
             if (value < 0 || value > (int64_t(1) << 24)) return fail(h, TGP_EINVAL, "steady-state prefix must be in 0..2^24");
             h->ss_prefix = value;
+            return TGP_OK;
+        case TGP_OPT_DEFER_STATUS:
+            h->defer_status = value != 0;
+            if (h->defer_status && !h->sticky) {
+                const unsigned long long init[2] = {~0ull, 0ull};
+                TGP_CUDA(h, cudaSetDevice(h->device));
+                TGP_CUDA(h, cudaMalloc((void**)&h->sticky, sizeof init));
+                TGP_CUDA(h, cudaMemcpy(h->sticky, init, sizeof init, cudaMemcpyHostToDevice));
+            }
             return TGP_OK;
         case TGP_OPT_DENSE_MATH:
             if (value != TGP_DENSE_F64 && value != TGP_DENSE_TF32X3) return fail(h, TGP_EINVAL, "unknown dense arithmetic %lld", (long long)value);
@@ -334,6 +344,20 @@ int tgp_synchronize(tgp_handle h) {
     if (!h) return TGP_EINVAL;
     TGP_CUDA(h, cudaSetDevice(h->device));
     if (h->deferred_res) return resolve_deferred(h);
+    if (h->sticky) {    // status accumulated by un-synchronised calls (TGP_OPT_DEFER_STATUS): report and clear
+        unsigned long long* p = (unsigned long long*)(h->pinned + 32);
+        const unsigned long long init[2] = {~0ull, 0ull};
+        TGP_CUDA(h, cudaMemcpyAsync(p, h->sticky, 16, cudaMemcpyDeviceToHost, h->stream));
+        TGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->d2h += 16;
+        const unsigned long long err = p[0], notconv = p[1];
+        if (err != ~0ull || notconv) TGP_CUDA(h, cudaMemcpy(h->sticky, init, sizeof init, cudaMemcpyHostToDevice));
+        if (err != ~0ull) return fail(h, TGP_ENOTPD, "covariance not positive definite at time index %lld (0-based) of a shard", (long long)err);
+        if (notconv)
+            return fail(h, TGP_EUNSUPPORTED, "the filtering covariance did not converge within the transient budget on this shard in %llu call(s); "
+                                             "use the general sharded path (tgp_shard_reduce / tgp_shard_prefix)", notconv);
+        return TGP_OK;
+    }
     TGP_CUDA(h, cudaStreamSynchronize(h->stream));
     return TGP_OK;
 }

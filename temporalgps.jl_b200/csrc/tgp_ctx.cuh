@@ -61,6 +61,7 @@ struct tgp_shard_state {
     bool active = false;
     int D = 0, rank = 0, world = 0;
     int64_t T = 0;
+    bool fused_xchg = false;     // phase 1 shipped its record through the peer-memory exchange (phase 2 must wait there)
     const double* dy = nullptr;
     alignas(8) char work[256];   // tgp::SSWork<D>: device pointers of the run's workspace
 };
@@ -93,6 +94,10 @@ struct tgp_ctx {
     tgp_shard_state shard;
     const unsigned long long* deferred_res = nullptr;   // result block {err, lml, converged} of an un-synchronised call
     int64_t deferred_T = 0;
+    // TGP_OPT_DEFER_STATUS: un-synchronised calls fold their status into a sticky device block {min failing step, #not converged}
+    // instead of being resolved by the next call, so consecutive sharded calls queue back to back; tgp_synchronize reads it.
+    bool defer_status = false;
+    unsigned long long* sticky = nullptr;
     void* xchg = nullptr;                               // tgp::XchgState: peer-memory exchange of the time-sharded path (tgp_xchg.cu)
 };
 

@@ -28,6 +28,11 @@ int xchg_open(tgp_ctx* h, const void* handles_all);
 int xchg_put(tgp_ctx* h, int ch, const double* src, int n);
 int xchg_wait(tgp_ctx* h, int ch, int n, double* dst, int mode);
 void xchg_destroy(tgp_ctx* h);
+// Device view of an opened exchange (false: none is open) and its per-channel epochs, for the kernels that put / wait themselves.
+struct XchgView { char* const* peers; char* self; int slot, world, rank; unsigned long long flag_off; };
+bool xchg_view(tgp_ctx* h, XchgView* v);
+unsigned long long xchg_next_epoch(tgp_ctx* h, int ch);
+unsigned long long xchg_epoch(tgp_ctx* h, int ch);
 
 // Test hook for the tcgen05 contraction kernel alone (tgp_dense_tc.cuh).
 int tc_gemm_selftest(tgp_ctx* h, int K, int Mx, int N, const float* X, const float* Y, float* C, int symmetric);

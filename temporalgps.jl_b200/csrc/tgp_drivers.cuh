@@ -3,6 +3,7 @@
 // instantiations compile in parallel; tgp_api.cu sees the declarations in tgp_dispatch.h.
 #pragma once
 #include "tgp_ctx.cuh"
+#include "tgp_dispatch.h"
 #include "tgp_scan_small.cuh"
 #include "tgp_steady.cuh"
 #include "tgp_steady_smooth.cuh"
@@ -28,6 +29,12 @@ inline int stage_model(tgp_ctx* h, const tgp_lgssm* m, const double* y, tgp_lgss
 
 inline bool time_invariant(const tgp_lgssm& m) { return !(m.sA | m.sa | m.sQ | m.sH | m.sh | m.sR); }
 
+// Folds the result block {err step, lml, converged} of an un-synchronised call into the handle's sticky status.
+static __global__ void k_sticky_status(const unsigned long long* __restrict__ res, unsigned long long* __restrict__ sticky) {
+    if (res[0] < sticky[0]) sticky[0] = res[0];
+    if (*reinterpret_cast<const int*>(res + 2) == 0) sticky[1] += 1ull;
+}
+
 // End of a call: copy back host outputs, fetch the failing-step word (and the steady-state
 // convergence word, if any), wait. *ss_converged is left untouched when ss_flag is NULL.
 inline int end_call(tgp_ctx* h, const unsigned long long* err_step, int64_t T, bool reverse_t, const int* ss_flag = nullptr,
@@ -37,6 +44,16 @@ inline int end_call(tgp_ctx* h, const unsigned long long* err_step, int64_t T, b
     int* pflag = (int*)(h->pinned + 2);
     *perr = ~0ull;
     *pflag = 1;
+    if (h->defer_status && h->sticky && packed && packed->packed_result && h->pending.empty() &&
+        (!packed->lml_out || is_device_ptr(packed->lml_out))) {
+        // TGP_OPT_DEFER_STATUS and nothing to bring back to the host: the call stays un-synchronised, its status (failing step,
+        // steady-state convergence) is folded into the sticky block that tgp_synchronize reports. No general-scan fallback here.
+        TGP_K(h, "k_sticky_status");
+        k_sticky_status<<<1, 1, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(packed->err), h->sticky);
+        TGP_LAUNCH_CHECK(h);
+        if (ss_converged) *ss_converged = true;
+        return TGP_OK;
+    }
     if (packed && packed->packed_result) {   // {err, lml, flag} contiguous on the device: one copy
         TGP_CUDA(h, cudaMemcpyAsync(perr, packed->err, 24, cudaMemcpyDeviceToHost, h->stream));
         h->d2h += 24;
@@ -486,7 +503,12 @@ int do_shard_phase1(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, i
         tgp_lgssm d;
         const double* dy;
         TGP_TRY(stage_model(h, m, y, &d, &dy));
-        return shard_phase1<D>(h, &h->shard, d, dy, rank, world, xchg_out);
+        // An opened peer-memory exchange (tgp_xchg_open) of matching shape: the kernels ship / await the records themselves.
+        SSXchg xd{};
+        XchgView xv;
+        h->shard.fused_xchg = xchg_view(h, &xv) && xv.world == world && xv.rank == rank && xv.slot >= D * D + D;
+        if (h->shard.fused_xchg) xd = SSXchg{xv.peers, xv.self, xv.slot, xv.flag_off, xchg_next_epoch(h, 0), 0ull};
+        return shard_phase1<D>(h, &h->shard, d, dy, rank, world, xchg_out, xd);
     } else {
         return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path is instantiated for D <= %d", TGP_REG_D);
     }
@@ -499,11 +521,20 @@ int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double* lml_partial) {
     if constexpr (D <= TGP_REG_D) {
         const int64_t T = h->shard.T;
         SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(h->shard.work);
-        TGP_TRY(shard_phase2<D>(h, &h->shard, xchg_all, lml_partial));
+        SSXchg xd{};
+        XchgView xv;
+        if (h->shard.fused_xchg && xchg_view(h, &xv)) xd = SSXchg{xv.peers, xv.self, xv.slot, xv.flag_off, xchg_epoch(h, 0), xchg_next_epoch(h, 1)};
+        TGP_TRY(shard_phase2<D>(h, &h->shard, xchg_all, lml_partial, xd));
         // no synchronisation here: the caller enqueues its all-reduce right behind this kernel; status (convergence,
         // positive-definiteness) is collected by tgp_synchronize() or by the next call on this handle.
-        h->deferred_res = w.resblk;
-        h->deferred_T = T;
+        if (h->defer_status && h->sticky) {
+            TGP_K(h, "k_sticky_status");
+            k_sticky_status<<<1, 1, 0, h->stream>>>(w.resblk, h->sticky);
+            TGP_LAUNCH_CHECK(h);
+        } else {
+            h->deferred_res = w.resblk;
+            h->deferred_T = T;
+        }
         return TGP_OK;
     } else {
         return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path is instantiated for D <= %d", TGP_REG_D);

@@ -81,11 +81,47 @@ struct SSOut {
 // Time-sharded (multi-GPU) use of the steady kernel: phase 0 = whole filter in one launch (single GPU);
 // phase 1 = zero-state pass only, ending with the shard record (Phi_shard, Z_shard) in xchg_out; phase 2 = the
 // per-step pass, starting from the mean folded out of the gathered records of the ranks before this one.
+// Peer-memory exchange fused into the shard kernels (tgp_xchg.cu owns the buffers): phase 1 stores this rank's record straight
+// into every peer's slot over NVLink and raises a flag; phase 2 waits for the flags of the ranks before it and reads the records
+// from its own buffer; its last CTA ships the partial log-likelihood the same way. No collective, no extra launch.
+struct SSXchg {
+    char* const* peers;       // mapped buffers of all ranks (device array), nullptr = exchange through xchg_out / xchg_all
+    char* self;
+    int slot;                 // doubles per slot
+    unsigned long long flag_off;
+    unsigned long long ep_rec, ep_lml;
+};
+__device__ __forceinline__ size_t ssx_data_off(int ch, unsigned long long ep, int world, int slot, int r) {
+    return ((size_t)((ch * 2 + (int)(ep & 1ull)) * world + r) * slot) * sizeof(double);
+}
+__device__ __forceinline__ void ssx_put(const SSXchg& x, int ch, unsigned long long ep, int world, int rank, const double* v, int n) {
+    const size_t off = ssx_data_off(ch, ep, world, x.slot, rank);
+    for (int p = 0; p < world; ++p) {
+        double* d = reinterpret_cast<double*>(x.peers[p] + off);
+        for (int i = 0; i < n; ++i) d[i] = v[i];
+    }
+    __threadfence_system();
+    for (int p = 0; p < world; ++p)
+        *(reinterpret_cast<volatile unsigned long long*>(x.peers[p] + x.flag_off) + (size_t)ch * world + rank) = ep;
+}
+__device__ __forceinline__ void ssx_wait(const SSXchg& x, int ch, unsigned long long ep, int world, int upto) {
+    for (int p = 0; p < upto; ++p) {
+        const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(x.self + x.flag_off) + (size_t)ch * world + p;
+        unsigned long long spins = 0;
+        while (*f < ep) {
+            if (++spins > (1ull << 31)) __trap();     // a lost peer: fail loudly instead of hanging the GPU
+            __nanosleep(20);
+        }
+    }
+    __threadfence_system();
+}
+
 struct SSShard {
     int phase, rank, world;
     double* xchg_out;         // D*D + D doubles (phase 1)
     const double* xchg_all;   // world x (D*D + D) doubles (phase 2)
     const void* sq;           // Mat<D>[kSqN]: squares table Abar^(2^k) (global memory)
+    SSXchg xd;
 };
 
 template <int D> __device__ __forceinline__ Vec<D> shfl_up_vec(const Vec<D>& v, int off) {
@@ -542,6 +578,14 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             for (int i = 0; i < D * D; ++i) sh.xchg_out[i] = Phi.v[i];
 #pragma unroll
             for (int i = 0; i < D; ++i) sh.xchg_out[D * D + i] = Z[i];
+            if (sh.xd.peers) {
+                double rec[D * D + D];
+#pragma unroll
+                for (int i = 0; i < D * D; ++i) rec[i] = Phi.v[i];
+#pragma unroll
+                for (int i = 0; i < D; ++i) rec[D * D + i] = Z[i];
+                ssx_put(sh.xd, 0, sh.xd.ep_rec, sh.world, sh.rank, rec, D * D + D);
+            }
         }
         return;
     }
@@ -569,15 +613,20 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
     }
     Vec<D> x_in = c.x_in;
     if (sh.phase == 2 && sh.rank > 0) {   // fold the records of the ranks before this one: x <- Phi_r x + Z_r
+        if (sh.xd.peers) {                  // peer-memory exchange: the records arrive in this GPU's own buffer
+            if (tid == 0) ssx_wait(sh.xd, 0, sh.xd.ep_rec, sh.world, sh.rank);
+            __syncthreads();
+        }
         Vec<D> x = vzero<D>();
         for (int r = 0; r < sh.rank; ++r) {
-            const double* rec = sh.xchg_all + (size_t)r * (D * D + D);
+            const double* rec = sh.xd.peers ? reinterpret_cast<const double*>(sh.xd.self + ssx_data_off(0, sh.xd.ep_rec, sh.world, sh.xd.slot, r))
+                                            : sh.xchg_all + (size_t)r * (D * D + D);
             Mat<D> Ph;
             Vec<D> Zr;
 #pragma unroll
-            for (int i = 0; i < D * D; ++i) Ph.v[i] = __ldg(rec + i);
+            for (int i = 0; i < D * D; ++i) Ph.v[i] = __ldcg(rec + i);
 #pragma unroll
-            for (int i = 0; i < D; ++i) Zr[i] = __ldg(rec + D * D + i);
+            for (int i = 0; i < D; ++i) Zr[i] = __ldcg(rec + D * D + i);
             x = affine(Ph, x, Zr);
         }
         x_in = x;
@@ -743,6 +792,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             const double lml = *out.lml_prefix + (double)Ts * (-0.5 * (kLog2Pi + c.logS)) - 0.5 * c.invS * s;
             *out.lml_out = lml;
             if (out.lml_user) *out.lml_user = lml;
+            if (sh.phase == 2 && sh.xd.peers) ssx_put(sh.xd, 1, sh.xd.ep_lml, sh.world, sh.rank, &lml, 1);
         }
     }
 }
@@ -861,7 +911,7 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
     so.lml_out = rq.lml_dev;
     so.lml_user = (rq.lml_out && is_device_ptr(rq.lml_out)) ? rq.lml_out : nullptr;   // device destination: written by the kernel
     so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
-    const SSShard sh{0, 0, 1, nullptr, nullptr, w.sq};
+    const SSShard sh{0, 0, 1, nullptr, nullptr, w.sq, SSXchg{}};
     const bool outs = rq.lml_steps || rq.m_f || rq.P_f;
     TGP_TRY(dispatch_ss_main<D>(h, small_L, outs, stage_m, w.cst, dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh));
     rq.xT = w.xT;
@@ -874,7 +924,8 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
 
 // ---- time-sharded steady-state logpdf: two stream-ordered phases around the caller's all-gather -------------------
 template <int D>
-int shard_phase1(tgp_ctx* h, tgp_shard_state* st, const tgp_lgssm& d, const double* dy, int rank, int world, double* xchg_out) {
+int shard_phase1(tgp_ctx* h, tgp_shard_state* st, const tgp_lgssm& d, const double* dy, int rank, int world, double* xchg_out,
+                 const SSXchg& xd = SSXchg{}) {
     static_assert(sizeof(SSWork<D>) <= sizeof(st->work), "SSWork must fit tgp_shard_state::work");
     const int64_t T = d.T;
     const int64_t max_blocks = std::max<int64_t>(1, std::min<int64_t>(h->ss_prefix > 0 ? (h->ss_prefix + kTrBlock - 1) / kTrBlock : 8,
@@ -890,14 +941,14 @@ int shard_phase1(tgp_ctx* h, tgp_shard_state* st, const tgp_lgssm& d, const doub
     so.lml_prefix = w.lml_prefix;
     so.lml_out = reinterpret_cast<double*>(w.resblk + 1);
     so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
-    const SSShard sh{1, rank, world, xchg_out, nullptr, w.sq};
+    const SSShard sh{1, rank, world, xchg_out, nullptr, w.sq, xd};
     TGP_TRY(dispatch_ss_main<D>(h, false, false, false, w.cst, dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh));
     st->active = true; st->D = D; st->rank = rank; st->world = world; st->T = T; st->dy = dy;
     return TGP_OK;
 }
 
 template <int D>
-int shard_phase2(tgp_ctx* h, tgp_shard_state* st, const double* xchg_all, double* lml_partial_dev) {
+int shard_phase2(tgp_ctx* h, tgp_shard_state* st, const double* xchg_all, double* lml_partial_dev, const SSXchg& xd = SSXchg{}) {
     SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(st->work);
     SSOut so{};
     so.xT = w.xT;
@@ -906,7 +957,7 @@ int shard_phase2(tgp_ctx* h, tgp_shard_state* st, const double* xchg_all, double
     so.lml_out = reinterpret_cast<double*>(w.resblk + 1);
     so.lml_user = lml_partial_dev;
     so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
-    const SSShard sh{2, st->rank, st->world, nullptr, xchg_all, w.sq};
+    const SSShard sh{2, st->rank, st->world, nullptr, xchg_all, w.sq, xd};
     TGP_TRY(dispatch_ss_main<D>(h, false, false, false, w.cst, st->dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh));
     st->active = false;
     return TGP_OK;

@@ -6,6 +6,7 @@
 // Slots are double-buffered by epoch parity (a fast rank may start the next call before a slow one has read this call's slot;
 // it cannot get two epochs ahead because the log-likelihood channel waits for every rank).
 #include "tgp_ctx.cuh"
+#include "tgp_dispatch.h"
 
 namespace tgp {
 
@@ -132,6 +133,15 @@ int xchg_wait(tgp_ctx* h, int ch, int n, double* dst, int mode) {
     TGP_LAUNCH_CHECK(h);
     return TGP_OK;
 }
+
+bool xchg_view(tgp_ctx* h, XchgView* v) {
+    XchgState* x = (XchgState*)h->xchg;
+    if (!x || !x->d_peers) return false;
+    *v = XchgView{x->d_peers, x->self, x->slot, x->world, x->rank, (unsigned long long)x->flag_off};
+    return true;
+}
+unsigned long long xchg_next_epoch(tgp_ctx* h, int ch) { return ++((XchgState*)h->xchg)->epoch[ch]; }
+unsigned long long xchg_epoch(tgp_ctx* h, int ch) { return ((XchgState*)h->xchg)->epoch[ch]; }
 
 void xchg_destroy(tgp_ctx* h) {
     XchgState* x = (XchgState*)h->xchg;

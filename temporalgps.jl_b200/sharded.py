@@ -42,6 +42,15 @@ class ShardedLogpdf:
             import torch.distributed as dist
         self.dist = dist
         self.h, self.mm, self.rank, self.world, self.dev = handle, marshalled, rank, world, device
+        # The library's kernels and torch's collectives must be ordered on ONE stream. torch's default stream has handle 0, which
+        # tgp_set_stream reads as "use the handle's own stream" — so run everything on a real side stream and make it current.
+        if getattr(device, "type", "cpu") == "cuda":
+            st = torch.cuda.current_stream(device)
+            if st.cuda_stream == 0:
+                st = torch.cuda.Stream(device=device)
+                torch.cuda.set_stream(st)
+            self.stream = st
+            handle.set_stream(st.cuda_stream)
         self.D = marshalled.D
         self.ES = 3 * self.D * self.D + 2 * self.D
         self.elem = torch.zeros(self.ES, dtype=torch.float64, device=device)
@@ -55,6 +64,9 @@ class ShardedLogpdf:
         self.time_invariant = not (d.sA or d.sa or d.sQ or d.sH or d.sh or d.sR) and d.ordering == 0 and d.T >= 65536
         XS = self.D * self.D + self.D
         self.XS = XS
+        if self.time_invariant:
+            from ._lib import TGP_OPT_DEFER_STATUS
+            handle.set_option(TGP_OPT_DEFER_STATUS, 1)
         self.rec = torch.zeros(XS, dtype=torch.float64, device=device)
         self.recs = torch.zeros(world * XS, dtype=torch.float64, device=device)
         # Exchange transport of the steady route: "p2p" = the library's peer-memory kernels (NVLink / NVSwitch stores + flags,
@@ -82,22 +94,24 @@ class ShardedLogpdf:
             if all(oks):
                 self.transport = "p2p"
 
-    def logpdf(self, y_dev, lml_out_dev):
-        """y_dev: this rank's shard, resident on its GPU. lml_out_dev: 1-element CUDA tensor (all ranks get the total)."""
+    def logpdf(self, y_dev, lml_out_dev, sync=True):
+        """y_dev: this rank's shard, resident on its GPU. lml_out_dev: 1-element CUDA tensor (all ranks get the total).
+        sync=False (steady route): nothing waits on the host — the call is only ENQUEUED on the stream, consecutive calls queue
+        back to back, and the shard's status (convergence, positive-definiteness) accumulates on the device until check()."""
         h, dist = self.h, self.dist
         if self.time_invariant:
             h.shard_phase1(self.mm.desc, y_dev, self.rank, self.world, self.rec)
             if self.transport == "p2p":
-                h.xchg_put(0, self.rec, self.XS)            # record -> every peer's slot, over NVLink
-                h.xchg_wait(0, self.XS, self.recs, 0)       # records of the ranks before this one
+                # with an exchange open the shard kernels ship / await the records themselves (NVLink stores + flags inside
+                # k_ss_main): phase 1 puts, phase 2 waits for the ranks before it and puts its partial log-likelihood
                 h.shard_phase2(self.recs, self.part)        # enqueued, not synchronised
-                h.xchg_put(1, self.part, 1)
                 h.xchg_wait(1, 1, lml_out_dev, 1)           # sum of the partial log-likelihoods, on every rank
             else:
                 dist.all_gather_into_tensor(self.recs, self.rec)
                 h.shard_phase2(self.recs, lml_out_dev)     # enqueued, not synchronised
                 dist.all_reduce(lml_out_dev)
-            h.synchronize()                             # status of the shard (convergence, positive-definiteness)
+            if sync:
+                h.synchronize()                         # status of the shard (convergence, positive-definiteness)
             return
         h.shard_reduce(self.mm.desc, y_dev, self.elem)
         dist.all_gather_into_tensor(self.all, self.elem)
@@ -109,6 +123,10 @@ class ShardedLogpdf:
         h.logpdf(self.desc2, y_dev, self.part)
         dist.all_reduce(self.part)
         lml_out_dev.copy_(self.part)
+
+    def check(self):
+        """Wait for the stream and raise if any un-synchronised call since the last check failed."""
+        self.h.synchronize()
 
     def logpdf_host(self, y_host_pinned):
         """End-to-end variant: the shard's observations start in pinned host memory."""
