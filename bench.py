@@ -252,7 +252,8 @@ def run_ours(args):
     tim = h.timing()
     h.set_timing(False)
     if os.environ.get("TGP_BENCH_DEBUG"):
-        print(f"[rank {rank}] kernels us/launch:", [(n, round(ms / c * 1e3, 1)) for n, ms, c in tim], file=sys.stderr, flush=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"kernels_rank{rank}.txt"), "w") as fh:
+            fh.write(repr([(n, round(ms / c * 1e3, 1)) for n, ms, c in tim]) + "\n")
     tot = sum(t[1] for t in tim) or 1.0
     top = tim[0]
     hbm, peak_src = peaks()
