@@ -195,6 +195,11 @@ int tgp_synchronize(tgp_handle h);
  * channel-1 put INSIDE their kernels (the sequence is then phase1 -> phase2 -> tgp_xchg_wait(1, 1, total, 1)); the caller must
  * not put on those channels itself. xchg_all of tgp_shard_phase2 is then unused (the records are read from the exchange buffer). */
 int tgp_xchg_create(tgp_handle h, int rank, int world, int slot_doubles, void* ipc_handle_out);
+/* ONE-LAUNCH FORM (needs an opened exchange): phase 1, the record exchange and phase 2 inside a single cooperative kernel — the
+ * grid barrier between the two phases doubles as the exchange point (the CTA arriving last ships the record over NVLink before
+ * releasing the grid; ranks > 0 then wait for their predecessors' flags). Writes the shard's partial log-likelihood to
+ * lml_partial (DEVICE) and ships it on channel 1; the caller follows with tgp_xchg_wait(1, 1, total, 1). Un-synchronised. */
+int tgp_shard_step(tgp_handle h, const tgp_lgssm* shard, const double* y, int rank, int world, double* lml_partial);
 int tgp_xchg_open(tgp_handle h, const void* ipc_handles_all);
 int tgp_xchg_put(tgp_handle h, int channel, const double* src, int n);
 int tgp_xchg_wait(tgp_handle h, int channel, int n, double* dst, int mode);

@@ -78,6 +78,7 @@ _SIGS = {
     "tgp_shard_phase1": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tgp_shard_phase2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgp_synchronize": (C.c_int, [C.c_void_p]),
+    "tgp_shard_step": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tgp_xchg_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tgp_xchg_open": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tgp_xchg_put": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -225,6 +226,9 @@ class Handle:
 
     def shard_phase1(self, desc, y, rank, world, xchg_out):
         self.check(lib().tgp_shard_phase1(self._h, C.byref(desc), ptr(y), int(rank), int(world), ptr(xchg_out)))
+
+    def shard_step(self, desc, y, rank, world, lml_partial):
+        self.check(lib().tgp_shard_step(self._h, C.byref(desc), ptr(y), int(rank), int(world), ptr(lml_partial)))
 
     def synchronize(self):
         self.check(lib().tgp_synchronize(self._h))

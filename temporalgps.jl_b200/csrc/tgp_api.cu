@@ -310,6 +310,16 @@ int tgp_shard_phase1(tgp_handle h, const tgp_lgssm* shard, const double* y, int 
 #undef CALL
 }
 
+int tgp_shard_step(tgp_handle h, const tgp_lgssm* shard, const double* y, int rank, int world, double* lml_partial) {
+    TGP_TRY(validate(h, shard, true, y));
+    TGP_TRY(require_scalar_obs(h, shard));
+    if (rank < 0 || world < 1 || rank >= world || !lml_partial) return fail(h, TGP_EINVAL, "bad rank / world / lml_partial");
+    TGP_TRY(begin_call(h));
+#define CALL(Dv) do_shard_step<Dv>(h, shard, y, rank, world, lml_partial)
+    TGP_DISPATCH_D(h, shard->D)
+#undef CALL
+}
+
 int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial) {
     if (!h) return TGP_EINVAL;
     if (!xchg_all || !lml_partial) return fail(h, TGP_EINVAL, "xchg_all and lml_partial must be non-NULL");

@@ -15,6 +15,7 @@ template <int D> int do_marginals(tgp_ctx* h, const tgp_lgssm* m, double* mean_o
 template <int D> int do_shard_reduce(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* elem_out);
 template <int D> int do_shard_phase1(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, int world, double* xchg_out);
 template <int D> int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double* lml_partial);
+template <int D> int do_shard_step(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, int world, double* lml_partial);
 template <int D> int do_shard_prefix(int n, const double* elems, const double* m0, const double* P0, double* m_in,
                                      double* P_in);
 
@@ -48,6 +49,7 @@ int tc_gemm_selftest(tgp_ctx* h, int K, int Mx, int N, const float* X, const flo
     extern template int do_shard_reduce<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, double*);                     \
     extern template int do_shard_phase1<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, int, int, double*);           \
     extern template int do_shard_phase2<Dv>(tgp_ctx*, const double*, double*);                                       \
+    extern template int do_shard_step<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, int, int, double*);             \
     extern template int do_shard_prefix<Dv>(int, const double*, const double*, const double*, double*, double*);
 
 // The set of latent dimensions with kernel instantiations (keep in step with build.py's TGP_DIMS).

@@ -541,6 +541,38 @@ int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double* lml_partial) {
     }
 }
 
+// One-launch sharded step (needs an opened peer-memory exchange of matching shape): phase 1 -> record to the peers -> wait for
+// the predecessors -> phase 2 -> partial log-likelihood to the peers, all inside k_ss_main. Returns WITHOUT synchronising; the
+// caller follows with tgp_xchg_wait(1, 1, total, 1). Status: as tgp_shard_phase2 (tgp_synchronize / TGP_OPT_DEFER_STATUS).
+template <int D>
+int do_shard_step(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, int world, double* lml_partial) {
+    if (m->ordering != TGP_FORWARD || !time_invariant(*m))
+        return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path runs Forward, time-invariant models (use tgp_shard_reduce otherwise)");
+    if (!is_device_ptr(lml_partial)) return fail(h, TGP_EINVAL, "lml_partial must be a device pointer");
+    if constexpr (D <= TGP_REG_D) {
+        XchgView xv;
+        if (!xchg_view(h, &xv) || xv.world != world || xv.rank != rank || xv.slot < D * D + D)
+            return fail(h, TGP_EINVAL, "tgp_shard_step needs an opened exchange (tgp_xchg_open) of matching rank / world / slot size");
+        tgp_lgssm d;
+        const double* dy;
+        TGP_TRY(stage_model(h, m, y, &d, &dy));
+        const SSXchg xd{xv.peers, xv.self, xv.slot, xv.flag_off, xchg_next_epoch(h, 0), xchg_next_epoch(h, 1)};
+        SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(h->shard.work);
+        TGP_TRY(shard_step_fused<D>(h, d, dy, rank, world, lml_partial, xd, &w));
+        if (h->defer_status && h->sticky) {
+            TGP_K(h, "k_sticky_status");
+            k_sticky_status<<<1, 1, 0, h->stream>>>(w.resblk, h->sticky);
+            TGP_LAUNCH_CHECK(h);
+        } else {
+            h->deferred_res = w.resblk;
+            h->deferred_T = m->T;
+        }
+        return TGP_OK;
+    } else {
+        return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path is instantiated for D <= %d", TGP_REG_D);
+    }
+}
+
 template <int D>
 int do_shard_prefix(int n, const double* elems, const double* m0, const double* P0, double* m_in, double* P_in) {
     Vec<D> m;

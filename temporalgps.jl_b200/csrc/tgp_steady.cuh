@@ -62,6 +62,7 @@ struct SSConst {
     Mat<D> Plane[32];         // Abar^(L lane)
     Vec<D> gK[16];            // Abar^(L-1-j) K: the zero-state response of a chunk is sum_j gK[j] y_j + zc (3 instead of 12 DFMA per step)
     Vec<D> zc;                // sum_j Abar^(L-1-j) c
+    Mat<D> PTs, Prem;         // Abar^Ts and Abar^(Ts - e_last Rw): the shard record's powers (data-independent, built once here)
 };
 
 struct SSOut {
@@ -307,6 +308,11 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
     if (Rw < wt) Rw = wt;
     cst->Plane[lane] = pow_from_squares<D>(sq, (unsigned long long)ssL * lane);
     if (lane < ssL && lane < 16) cst->gK[lane] = matvec(pow_from_squares<D>(sq, (unsigned long long)(ssL - 1 - lane)), K);
+    if (lane == 18) cst->PTs = pow_from_squares<D>(sq, (unsigned long long)Ts);
+    if (lane == 19) {
+        const long long e_last = Ts > 0 ? (Ts - 1) / Rw : 0;
+        cst->Prem = pow_from_squares<D>(sq, (unsigned long long)(Ts - e_last * Rw));
+    }
     if (lane == 17) {
         Vec<D> cc, z = vzero<D>();
 #pragma unroll
@@ -485,7 +491,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             if (it + NS - 1 < ntiles) issue_tile(ts + (NS - 1) * WT, (int)((it + NS - 1) % NS), pol);
             cp_async_commit();
             const double* yc = ybuf + (int)(it % NS) * LY::YB + lane * LY::YS;
-            const bool tail = sh.phase == 1 && ts + WT > Ts;   // the shard's last, partial tile: its aggregate is consumed
+            const bool tail = (sh.phase == 1 || sh.phase == 3) && ts + WT > Ts;   // the shard's last, partial tile: its aggregate is consumed
             Vec<D> z = vzero<D>();                             // by the next rank, so it must be aligned at step Ts-1 exactly
             if (!tail) {      // full chunk: z = sum_j Abar^(L-1-j) (K y_j + c) through the precomputed coefficient table
                 z = c.zc;
@@ -542,13 +548,9 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
         }
         __threadfence();
     }
-    if (sh.phase == 1) {
-        // ---- shard record by the last CTA to finish: Z_shard = Abar^rem * (sum of the full ranges) + last range ----
-        int* s_last = reinterpret_cast<int*>(red + 2 * (kSSWarps + 2) * D - 1);   // last word of the scratch area
-        __syncthreads();
-        if (tid == 0) *s_last = (atomicAdd(counters, 1u) == (unsigned)G - 1) ? 1 : 0;
-        __syncthreads();
-        if (!*s_last) return;
+    int* s_last = reinterpret_cast<int*>(red + 2 * (kSSWarps + 2) * D - 1);   // last word of the scratch area
+    // ---- shard record (whole CTA): Z_shard = Abar^rem * (sum of the full ranges) + last range; shipped to the peers if an exchange is open
+    auto emit_record = [&]() {
         __threadfence();
         const Mat<D>* sqt = reinterpret_cast<const Mat<D>*>(sh.sq);
         const long long e_last = Ts > 0 ? (Ts - 1) / Rw : 0;
@@ -571,13 +573,15 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             Vec<D> zl;
 #pragma unroll
             for (int i = 0; i < D; ++i) zl[i] = __ldcg(agg + (size_t)e_last * D + i);
-            Vec<D> Z = affine(pow_from_squares<D>(sqt, (unsigned long long)rem), Sfull, zl);
-            const Mat<D> Phi = pow_from_squares<D>(sqt, (unsigned long long)Ts);
+            Vec<D> Z = affine(c.Prem, Sfull, zl);          // powers precomputed by k_transient (no serial matrix chain here)
+            const Mat<D> Phi = c.PTs;
             if (sh.rank == 0) Z = affine(Phi, c.x_in, Z);     // rank 0 knows its incoming mean: ship the end STATE
+            if (sh.xchg_out) {
 #pragma unroll
-            for (int i = 0; i < D * D; ++i) sh.xchg_out[i] = Phi.v[i];
+                for (int i = 0; i < D * D; ++i) sh.xchg_out[i] = Phi.v[i];
 #pragma unroll
-            for (int i = 0; i < D; ++i) sh.xchg_out[D * D + i] = Z[i];
+                for (int i = 0; i < D; ++i) sh.xchg_out[D * D + i] = Z[i];
+            }
             if (sh.xd.peers) {
                 double rec[D * D + D];
 #pragma unroll
@@ -587,6 +591,12 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
                 ssx_put(sh.xd, 0, sh.xd.ep_rec, sh.world, sh.rank, rec, D * D + D);
             }
         }
+    };
+    if (sh.phase == 1) {   // the last CTA to finish builds the record
+        __syncthreads();
+        if (tid == 0) *s_last = (atomicAdd(counters, 1u) == (unsigned)G - 1) ? 1 : 0;
+        __syncthreads();
+        if (*s_last) emit_record();
         return;
     }
     {   // prefetch the first tiles of phase 2 (across the barrier when phase == 0)
@@ -605,6 +615,23 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             __threadfence();
         }
         __syncthreads();
+    } else if (sh.phase == 3) {
+        // Fused sharded step (one launch per shard and call): the grid barrier between the two phases doubles as the exchange point.
+        // The CTA that arrives last holds the complete set of warp aggregates: it builds the shard record, stores it into every
+        // peer's buffer over NVLink, and only then releases the grid (counter G + 1). Ranks > 0 wait below for their predecessors.
+        __syncthreads();
+        if (tid == 0) *s_last = (atomicAdd(counters, 1u) == (unsigned)G - 1) ? 1 : 0;
+        __syncthreads();
+        if (*s_last) {
+            emit_record();
+            __syncthreads();
+            if (tid == 0) { __threadfence(); atomicAdd(counters, 1u); }
+        }
+        if (tid == 0) {
+            while (*reinterpret_cast<volatile unsigned*>(counters) < (unsigned)G + 1u) { __nanosleep(32); }
+            __threadfence();
+        }
+        __syncthreads();
     }
     // this CTA's warp aggregates -> shared memory (phase 2 of a sharded run reads what phase 1 left in agg)
     if (lane == 0) {
@@ -612,7 +639,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
         for (int i = 0; i < D; ++i) red[(kSSWarps + 2 + wp) * D + i] = __ldcg(agg + (size_t)gw * D + i);
     }
     Vec<D> x_in = c.x_in;
-    if (sh.phase == 2 && sh.rank > 0) {   // fold the records of the ranks before this one: x <- Phi_r x + Z_r
+    if ((sh.phase == 2 || sh.phase == 3) && sh.rank > 0) {   // fold the records of the ranks before this one: x <- Phi_r x + Z_r
         if (sh.xd.peers) {                  // peer-memory exchange: the records arrive in this GPU's own buffer
             if (tid == 0) ssx_wait(sh.xd, 0, sh.xd.ep_rec, sh.world, sh.rank);
             __syncthreads();
@@ -792,7 +819,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             const double lml = *out.lml_prefix + (double)Ts * (-0.5 * (kLog2Pi + c.logS)) - 0.5 * c.invS * s;
             *out.lml_out = lml;
             if (out.lml_user) *out.lml_user = lml;
-            if (sh.phase == 2 && sh.xd.peers) ssx_put(sh.xd, 1, sh.xd.ep_lml, sh.world, sh.rank, &lml, 1);
+            if ((sh.phase == 2 || sh.phase == 3) && sh.xd.peers) ssx_put(sh.xd, 1, sh.xd.ep_lml, sh.world, sh.rank, &lml, 1);
         }
     }
 }
@@ -811,7 +838,7 @@ int launch_ss_main(tgp_ctx* h, bool stage_m, const SSConst<D>* cst, const double
         attr_smem = smem;
     }
     void* args[] = {(void*)&cst, (void*)&dy, (void*)&zbuf, (void*)&zstride, (void*)&agg, (void*)&counters, (void*)&so, (void*)&sh};
-    TGP_K(h, sh.phase == 1 ? "k_ss_main(phase1)" : (sh.phase == 2 ? "k_ss_main(phase2)" : "k_ss_main"));
+    TGP_K(h, sh.phase == 1 ? "k_ss_main(phase1)" : (sh.phase == 2 ? "k_ss_main(phase2)" : (sh.phase == 3 ? "k_ss_main(fused shard step)" : "k_ss_main")));
     TGP_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_ss_main<D, L, NS, OUTS>, dim3((unsigned)G), dim3(kSSThreads), args, smem,
                                             h->stream));
     TGP_LAUNCH_CHECK(h);
@@ -945,6 +972,29 @@ int shard_phase1(tgp_ctx* h, tgp_shard_state* st, const tgp_lgssm& d, const doub
     TGP_TRY(dispatch_ss_main<D>(h, false, false, false, w.cst, dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh));
     st->active = true; st->D = D; st->rank = rank; st->world = world; st->T = T; st->dy = dy;
     return TGP_OK;
+}
+
+// Fused form (needs an opened peer-memory exchange): phase 1, the exchange and phase 2 in ONE cooperative launch.
+template <int D>
+int shard_step_fused(tgp_ctx* h, const tgp_lgssm& d, const double* dy, int rank, int world, double* lml_partial_dev, const SSXchg& xd,
+                     SSWork<D>* wout) {
+    const int64_t T = d.T;
+    const int64_t max_blocks = std::max<int64_t>(1, std::min<int64_t>(h->ss_prefix > 0 ? (h->ss_prefix + kTrBlock - 1) / kTrBlock : 8,
+                                                                      T / (2 * kTrBlock)));
+    if (T < 65536) return fail(h, TGP_EUNSUPPORTED, "time shards must hold at least 65536 steps for the steady-state sharded path");
+    SSWork<D>& w = *wout;
+    TGP_TRY(ss_alloc<D>(h, T, false, &w));
+    FilterReq rq;
+    TGP_TRY(ss_transient<D>(h, d, dy, rq, w, max_blocks, rank > 0 ? 1 : 0));
+    SSOut so{};
+    so.xT = w.xT;
+    so.partials = w.partials;
+    so.lml_prefix = w.lml_prefix;
+    so.lml_out = reinterpret_cast<double*>(w.resblk + 1);
+    so.lml_user = lml_partial_dev;
+    so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
+    const SSShard sh{3, rank, world, nullptr, nullptr, w.sq, xd};
+    return dispatch_ss_main<D>(h, false, false, false, w.cst, dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh);
 }
 
 template <int D>

@@ -73,6 +73,7 @@ class ShardedLogpdf:
         # tgp_xchg_*), "nccl" = all_gather + all_reduce. p2p needs CUDA IPC between the ranks' GPUs; fall back if it is unavailable.
         import os
         self.transport = "nccl"
+        self.fused = os.environ.get("TGP_SHARD_FUSED", "1") == "1"     # one-launch form of the p2p step (tgp_shard_step)
         if self.time_invariant and world > 1 and device.type == "cuda" and os.environ.get("TGP_XCHG", "p2p") == "p2p":
             mine, err = None, None
             try:
@@ -99,6 +100,13 @@ class ShardedLogpdf:
         sync=False (steady route): nothing waits on the host — the call is only ENQUEUED on the stream, consecutive calls queue
         back to back, and the shard's status (convergence, positive-definiteness) accumulates on the device until check()."""
         h, dist = self.h, self.dist
+        if self.time_invariant and self.transport == "p2p" and self.fused:
+            # ONE cooperative launch per shard: phase 1 -> record over NVLink -> wait for the predecessors -> phase 2 -> partial lml
+            h.shard_step(self.mm.desc, y_dev, self.rank, self.world, self.part)
+            h.xchg_wait(1, 1, lml_out_dev, 1)               # sum of the partial log-likelihoods, on every rank
+            if sync:
+                h.synchronize()
+            return
         if self.time_invariant:
             h.shard_phase1(self.mm.desc, y_dev, self.rank, self.world, self.rec)
             if self.transport == "p2p":

@@ -66,10 +66,13 @@ print("rank", rank, "ok")
 '''
 
 
-def test_time_sharded_logpdf_peer_memory_exchange(pkg, tmp_path):
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_time_sharded_logpdf_peer_memory_exchange(pkg, tmp_path, fused):
+    """fused = 1: tgp_shard_step (phase 1, exchange and phase 2 in ONE cooperative launch); 0: tgp_shard_phase1 / phase2 with the
+    put / wait inside those two kernels."""
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, TGP_ROOT=ROOT, OMP_NUM_THREADS="1")
+    env = dict(os.environ, TGP_ROOT=ROOT, OMP_NUM_THREADS="1", TGP_SHARD_FUSED=fused)
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29541", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
