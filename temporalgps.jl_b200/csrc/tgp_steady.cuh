@@ -270,7 +270,7 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
         double t = 0.0;
 #pragma unroll
         for (int i = 0; i < kTrWarps; ++i) t += red[i];
-        *lml_prefix = constants_only ? 0.0 : t;   // constants_only: a later shard of a time-sharded series; its steps are all steady
+        *lml_prefix = (constants_only & 1) ? 0.0 : t;   // constants_only: a later shard of a time-sharded series; its steps are all steady
     }
     if (wp != 0) return;
     // ---- constants of the steady phase (warp 0) ---------------------------------------------------
@@ -299,7 +299,7 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
         }
     }
     __syncwarp();
-    const long long N0 = constants_only ? 0 : (long long)nb * kTrBlock;
+    const long long N0 = (constants_only & 1) ? 0 : (long long)nb * kTrBlock;
     const long long Ts = dm.T - N0;
     const long long wt = 32ll * ssL;               // warp tile
     const long long nwarps = (long long)G * kSSWarps;
@@ -308,8 +308,8 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
     if (Rw < wt) Rw = wt;
     cst->Plane[lane] = pow_from_squares<D>(sq, (unsigned long long)ssL * lane);
     if (lane < ssL && lane < 16) cst->gK[lane] = matvec(pow_from_squares<D>(sq, (unsigned long long)(ssL - 1 - lane)), K);
-    if (lane == 18) cst->PTs = pow_from_squares<D>(sq, (unsigned long long)Ts);
-    if (lane == 19) {
+    if (lane == 18 && (constants_only & 2)) cst->PTs = pow_from_squares<D>(sq, (unsigned long long)Ts);
+    if (lane == 19 && (constants_only & 2)) {
         const long long e_last = Ts > 0 ? (Ts - 1) / Rw : 0;
         cst->Prem = pow_from_squares<D>(sq, (unsigned long long)(Ts - e_last * Rw));
     }
@@ -334,7 +334,7 @@ k_transient(const DevModel dm, const double* __restrict__ m0, const double* __re
         cst->n_blocks = nb;
         cst->N0 = N0; cst->Ts = Ts; cst->Rw = Rw;
         cst->S = S; cst->invS = invS; cst->logS = log(S); cst->hh = hh; cst->conv_err = conv_err;
-        cst->K = K; cst->w = w; cst->a = a; cst->x_in = constants_only ? vzero<D>() : mT;
+        cst->K = K; cst->w = w; cst->a = a; cst->x_in = (constants_only & 1) ? vzero<D>() : mT;
 #pragma unroll
         for (int i = 0; i < D; ++i) cst->c[i] = fma(-K[i], hh, a[i]);
         cst->A = A; cst->Abar = Abar;
@@ -421,12 +421,13 @@ struct SSLayout {
     static size_t bytes(bool stage_m) { return (size_t)(o_ms + (stage_m ? kSSWarps * 32 * MS : 0)) * sizeof(double); }
 };
 
-template <int D, int L, int NS, bool OUTS>
+template <int D, int L, int NS, bool OUTS, bool SHARDED>
 __global__ void __launch_bounds__(kSSThreads, 1)
 k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, double* __restrict__ zbuf, long long zstride,
           double* __restrict__ agg, unsigned* __restrict__ counters, const SSOut out, const SSShard sh) {
     using LY = SSLayout<D, L, NS>;
     static_assert(L % 2 == 0 && (128 % L) == 0 && NS >= 2 && L <= 16, "layout assumptions");
+    const int phase = SHARDED ? sh.phase : 0;   // single-GPU instantiation: every shard branch below is dead code
     extern __shared__ __align__(16) double smem[];
     SSConst<D>& c = *reinterpret_cast<SSConst<D>*>(smem);
     double* red = smem + LY::o_red;
@@ -473,7 +474,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
     const long long ntiles = (r1 - r0 + WT - 1) / WT;
 
     // ---- phase 1: zero-state responses, warp by warp ----------------------------------------------------
-    if (sh.phase != 2) {
+    if (phase != 2) {
         const unsigned long long pol = l2_policy_evict_last();
         const Mat<D>* sqt = reinterpret_cast<const Mat<D>*>(sh.sq);
         Vec<D> Zw = vzero<D>();
@@ -491,7 +492,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             if (it + NS - 1 < ntiles) issue_tile(ts + (NS - 1) * WT, (int)((it + NS - 1) % NS), pol);
             cp_async_commit();
             const double* yc = ybuf + (int)(it % NS) * LY::YB + lane * LY::YS;
-            const bool tail = (sh.phase == 1 || sh.phase == 3) && ts + WT > Ts;   // the shard's last, partial tile: its aggregate is consumed
+            const bool tail = (phase == 1 || phase == 3) && ts + WT > Ts;   // the shard's last, partial tile: its aggregate is consumed
             Vec<D> z = vzero<D>();                             // by the next rank, so it must be aligned at step Ts-1 exactly
             if (!tail) {      // full chunk: z = sum_j Abar^(L-1-j) (K y_j + c) through the precomputed coefficient table
                 z = c.zc;
@@ -592,7 +593,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             }
         }
     };
-    if (sh.phase == 1) {   // the last CTA to finish builds the record
+    if (phase == 1) {   // the last CTA to finish builds the record
         __syncthreads();
         if (tid == 0) *s_last = (atomicAdd(counters, 1u) == (unsigned)G - 1) ? 1 : 0;
         __syncthreads();
@@ -607,7 +608,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             cp_async_commit();
         }
     }
-    if (sh.phase == 0) {
+    if (phase == 0) {
         __syncthreads();
         if (tid == 0) {
             atomicAdd(counters, 1u);
@@ -615,7 +616,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             __threadfence();
         }
         __syncthreads();
-    } else if (sh.phase == 3) {
+    } else if (phase == 3) {
         // Fused sharded step (one launch per shard and call): the grid barrier between the two phases doubles as the exchange point.
         // The CTA that arrives last holds the complete set of warp aggregates: it builds the shard record, stores it into every
         // peer's buffer over NVLink, and only then releases the grid (counter G + 1). Ranks > 0 wait below for their predecessors.
@@ -639,7 +640,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
         for (int i = 0; i < D; ++i) red[(kSSWarps + 2 + wp) * D + i] = __ldcg(agg + (size_t)gw * D + i);
     }
     Vec<D> x_in = c.x_in;
-    if ((sh.phase == 2 || sh.phase == 3) && sh.rank > 0) {   // fold the records of the ranks before this one: x <- Phi_r x + Z_r
+    if ((phase == 2 || phase == 3) && sh.rank > 0) {   // fold the records of the ranks before this one: x <- Phi_r x + Z_r
         if (sh.xd.peers) {                  // peer-memory exchange: the records arrive in this GPU's own buffer
             if (tid == 0) ssx_wait(sh.xd, 0, sh.xd.ep_rec, sh.world, sh.rank);
             __syncthreads();
@@ -819,7 +820,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             const double lml = *out.lml_prefix + (double)Ts * (-0.5 * (kLog2Pi + c.logS)) - 0.5 * c.invS * s;
             *out.lml_out = lml;
             if (out.lml_user) *out.lml_user = lml;
-            if ((sh.phase == 2 || sh.phase == 3) && sh.xd.peers) ssx_put(sh.xd, 1, sh.xd.ep_lml, sh.world, sh.rank, &lml, 1);
+            if ((phase == 2 || phase == 3) && sh.xd.peers) ssx_put(sh.xd, 1, sh.xd.ep_lml, sh.world, sh.rank, &lml, 1);
         }
     }
 }
@@ -827,19 +828,19 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
 // Forward declaration: a non-converged series is redone by the general scan driver (tgp_drivers.cuh).
 template <int D> int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& rq);
 
-template <int D, int L, int NS, bool OUTS>
+template <int D, int L, int NS, bool OUTS, bool SHARDED>
 int launch_ss_main(tgp_ctx* h, bool stage_m, const SSConst<D>* cst, const double* dy, double* zbuf, long long zstride, int G, double* agg,
                    unsigned* counters, const SSOut& so, const SSShard& sh) {
     using LY = SSLayout<D, L, NS>;
     const size_t smem = LY::bytes(stage_m);
     static size_t attr_smem = 0;   // opt in to exactly what this instantiation needs (static + dynamic must stay <= 227 KB)
     if (smem > attr_smem) {
-        TGP_CUDA(h, cudaFuncSetAttribute(k_ss_main<D, L, NS, OUTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TGP_CUDA(h, cudaFuncSetAttribute(k_ss_main<D, L, NS, OUTS, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
     void* args[] = {(void*)&cst, (void*)&dy, (void*)&zbuf, (void*)&zstride, (void*)&agg, (void*)&counters, (void*)&so, (void*)&sh};
     TGP_K(h, sh.phase == 1 ? "k_ss_main(phase1)" : (sh.phase == 2 ? "k_ss_main(phase2)" : (sh.phase == 3 ? "k_ss_main(fused shard step)" : "k_ss_main")));
-    TGP_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_ss_main<D, L, NS, OUTS>, dim3((unsigned)G), dim3(kSSThreads), args, smem,
+    TGP_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_ss_main<D, L, NS, OUTS, SHARDED>, dim3((unsigned)G), dim3(kSSThreads), args, smem,
                                             h->stream));
     TGP_LAUNCH_CHECK(h);
     return TGP_OK;
@@ -852,9 +853,13 @@ int dispatch_ss_main(tgp_ctx* h, bool small_L, bool outs, bool stage_m, const SS
     constexpr size_t kSmemMax = 227 * 1024;
 #define TGP_SS_LAUNCH(Lv, Ov, sm)                                                                                          \
     do {                                                                                                                   \
-        if (SSLayout<D, Lv, 3>::bytes(sm) <= kSmemMax) return launch_ss_main<D, Lv, 3, Ov>(h, sm, cst, dy, zbuf, zstride, G, agg, counters, so, sh); \
-        return launch_ss_main<D, Lv, 2, Ov>(h, sm, cst, dy, zbuf, zstride, G, agg, counters, so, sh);                      \
+        if (SSLayout<D, Lv, 3>::bytes(sm) <= kSmemMax) return launch_ss_main<D, Lv, 3, Ov, false>(h, sm, cst, dy, zbuf, zstride, G, agg, counters, so, sh); \
+        return launch_ss_main<D, Lv, 2, Ov, false>(h, sm, cst, dy, zbuf, zstride, G, agg, counters, so, sh);               \
     } while (0)
+    if (sh.phase != 0) {  // time-sharded phases: their own instantiation, so the single-GPU kernel carries none of that code
+        if (SSLayout<D, 16, 3>::bytes(false) <= kSmemMax) return launch_ss_main<D, 16, 3, false, true>(h, false, cst, dy, zbuf, zstride, G, agg, counters, so, sh);
+        return launch_ss_main<D, 16, 2, false, true>(h, false, cst, dy, zbuf, zstride, G, agg, counters, so, sh);
+    }
     if (!outs) {          // logpdf: no per-step output, branch-free inner loops
         if (small_L) TGP_SS_LAUNCH(8, false, false);
         TGP_SS_LAUNCH(16, false, false);
@@ -961,7 +966,7 @@ int shard_phase1(tgp_ctx* h, tgp_shard_state* st, const tgp_lgssm& d, const doub
     SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(st->work);
     TGP_TRY(ss_alloc<D>(h, T, false, &w));
     FilterReq rq;
-    TGP_TRY(ss_transient<D>(h, d, dy, rq, w, max_blocks, rank > 0 ? 1 : 0));
+    TGP_TRY(ss_transient<D>(h, d, dy, rq, w, max_blocks, (rank > 0 ? 1 : 0) | 2));   // bit 1: also the shard record's powers
     SSOut so{};
     so.xT = w.xT;
     so.partials = w.partials;
@@ -985,7 +990,7 @@ int shard_step_fused(tgp_ctx* h, const tgp_lgssm& d, const double* dy, int rank,
     SSWork<D>& w = *wout;
     TGP_TRY(ss_alloc<D>(h, T, false, &w));
     FilterReq rq;
-    TGP_TRY(ss_transient<D>(h, d, dy, rq, w, max_blocks, rank > 0 ? 1 : 0));
+    TGP_TRY(ss_transient<D>(h, d, dy, rq, w, max_blocks, (rank > 0 ? 1 : 0) | 2));   // bit 1: also the shard record's powers
     SSOut so{};
     so.xT = w.xT;
     so.partials = w.partials;
