@@ -291,6 +291,13 @@ def run_ours(args):
                               "algorithmic_bytes_per_step": 104.0, "note": "whole call (all kernels), y read + (m_f,P_f) written"}}
         del mf, Pf
 
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        try:
+            secondary = secondary_configs(pkg, h, torch)
+        except Exception as exc:      # noqa: BLE001 — extras must never take the headline down
+            secondary = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -331,6 +338,7 @@ def run_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu,
         "filter_emit": extra,
+        "secondary": secondary,
         "clocks": clk,
         "lml": float(lml_e2e),
     }
@@ -338,6 +346,56 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def secondary_configs(pkg, h, torch):
+    """BASELINE configs 3 and 5 at full size on this GPU (device-resident inputs, synchronous calls, wall clock around
+    torch.cuda.synchronize): reported beside the headline, not part of it. Parity of these paths is the GPU test-suite's job
+    (tests/test_gpu_steady_smoother.py, tests/test_gpu_tensorcore.py); details and CPU-oracle times: tools/bench_configs.py,
+    tools/cfg5_bench.py, profiles/."""
+    out = {}
+
+    def timeit(fn, n, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n
+
+    hbm, _ = peaks()
+    # config 3: D = 10 sum kernel, T = 1e6, posterior marginals at the training inputs (filter + RTS smoother)
+    T3 = 1_000_000
+    TK = pkg.gp.TransformedKernel
+    k3 = 1.0 * pkg.Matern32Kernel() + 0.7 * pkg.Matern52Kernel() + 0.5 * TK(pkg.Matern52Kernel(), 0.5) + 0.3 * TK(pkg.Matern32Kernel(), 2.0)
+    m3 = pkg.lgssm._Marshalled(pkg.to_sde(pkg.GP(k3))(pkg.RegularSpacing(0.0, 0.01, T3), 0.1).build_lgssm())
+    rng = np.random.default_rng(20261017 + 3)
+    y3 = torch.from_numpy(np.sin(np.arange(T3) * 0.004) + 0.3 * np.cos(np.arange(T3) * 0.05) + 0.35 * rng.standard_normal(T3)).cuda()
+    Rn = torch.full((1,), 1e-2, dtype=torch.float64, device="cuda")
+    md = torch.empty(T3, dtype=torch.float64, device="cuda")
+    vd = torch.empty(T3, dtype=torch.float64, device="cuda")
+    t3 = timeit(lambda: h.posterior_marginals(m3.desc, y3, Rn, 0, md, vd, None), 10, 3)
+    out["cfg3_posterior_marginals_D10_T1e6"] = {"ms": t3 * 1e3, "steps_per_s": T3 / t3, "dtype": "f64",
+                                                "hbm_frac_of_measured": 1784.0 * T3 / t3 / 1e9 / hbm, "algorithmic_bytes_per_step": 1784.0}
+    del y3, md, vd
+    # config 5: Separable(SE, Matern52), 256 spatial points x T = 1e5 (D = 768, M = 256), FP32 storage on the tensor cores, logpdf
+    Nr, T5 = 256, 100_000
+    r = np.linspace(-3.0, 3.0, Nr)
+    fx5 = pkg.to_sde(pkg.GP(pkg.Separable(pkg.SEKernel(), pkg.Matern52Kernel())), pkg.ArrayStorage(np.float32))(
+        pkg.RectilinearGrid(r, pkg.RegularSpacing(0.0, 0.01, T5)), 0.1)
+    m5 = pkg.lgssm._Marshalled(fx5.build_lgssm())
+    y5 = torch.from_numpy(np.random.default_rng(20261017 + 5).standard_normal((T5, Nr))).cuda()
+    lml5 = np.zeros(1)
+    h5 = fx5._handle()           # the same handle, switched to the FP32-storage tensor-core arithmetic
+    try:
+        t5 = timeit(lambda: h5.logpdf(m5.desc, y5, lml5), 2, 1)
+    finally:
+        h5.set_dense_math(pkg.lgssm.TGP_DENSE_F64)
+    out["cfg5_logpdf_D768_M256_T1e5_fp32_tensorcore"] = {"s": t5, "steps_per_s": T5 / t5, "dtype": "f32 storage, 3xTF32 tcgen05, FP64 Cholesky / means",
+                                                         "lml": float(lml5[0])}
+    return out
 
 
 def main():
@@ -350,6 +408,7 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "scan"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-filter", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs 3 / 5 extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -553,9 +553,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
     // ---- shard record (whole CTA): Z_shard = Abar^rem * (sum of the full ranges) + last range; shipped to the peers if an exchange is open
     auto emit_record = [&]() {
         __threadfence();
-        const Mat<D>* sqt = reinterpret_cast<const Mat<D>*>(sh.sq);
         const long long e_last = Ts > 0 ? (Ts - 1) / Rw : 0;
-        const long long rem = Ts - e_last * Rw;
         const long long J = (e_last + kSSThreads - 1) / kSSThreads;
         const long long pad = J * kSSThreads - e_last;
         const Mat<D> Bt = c.PRt;
