@@ -617,7 +617,7 @@ int dense_filter_tc(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml
         if (tb > 48 * 1024) TGP_CUDA(h, cudaFuncSetAttribute(k_tri_inv2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb));
     }
     if (ti && T >= 8 && !h->timing) {
-        // One step captured into a CUDA graph and replayed. Every kPoll steps the host looks at the steady-state word;
+        // One step captured into a CUDA graph and replayed. Every kPoll (4) steps the host looks at the steady-state word;
         // once the covariance recursion has converged the remaining steps replay the mean-only graph.
         cudaGraph_t graph[2] = {nullptr, nullptr};
         cudaGraphExec_t exec[2] = {nullptr, nullptr};
@@ -634,7 +634,7 @@ int dense_filter_tc(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml
             TGP_CUDA(h, ce);
             TGP_CUDA(h, cudaGraphInstantiate(&exec[fz], graph[fz], 0));
         }
-        constexpr int64_t kPoll = 16;
+        constexpr int64_t kPoll = 4;       // a full step costs ~0.5 ms at D = 768: looking every 4 steps costs one ~20 us sync per 2 ms
         long long* pss = (long long*)(h->pinned + 16);
         *pss = -1;
         bool frozen = false;
