@@ -178,6 +178,50 @@ int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& 
 // err_step holds a scan step; map it to a memory index for the message.
 inline int64_t err_T(const tgp_lgssm& d) { return d.ordering == TGP_REVERSE ? d.T - 1 : d.T; }
 
+constexpr int64_t kSmMaxEnd = 8192;      // budget (steps) for each covariance recursion of tgp_steady_smooth.cuh to stop moving
+
+// ---- logpdf of a time-invariant model whose D has no register-resident steady kernel (D = 8, 10): the head by the sequential
+// single-CTA filter, the rest by ONE constant-coefficient forward scan over vectors (tgp_steady_smooth.cuh). Log-likelihood only.
+template <int D>
+int logpdf_steady_vec(tgp_ctx* h, const tgp_lgssm& d, const double* dy, double* lml_out, bool* converged) {
+    const int64_t T = d.T;
+    cudaStream_t st = h->stream;
+    *converged = false;
+    SmConst<D>* cst;
+    unsigned long long* err;
+    TGP_TRY(dalloc(h, 1, &cst));
+    TGP_TRY(dalloc(h, 1, &err));
+    TGP_CUDA(h, cudaMemsetAsync(err, 0xFF, sizeof(unsigned long long), st));
+    const DevModel dm{d.A, d.a, d.Q, d.H, d.h, d.R, 0, 0, 0, 0, 0, 0, dy, 1, T};
+    TGP_K(h, "k_sm_head_fwd");
+    k_sm_head_fwd<D><<<1, 128, 0, st>>>(dm, d.m0, d.P0, kSmMaxEnd, h->ss_tol, nullptr, nullptr, cst, err);
+    TGP_LAUNCH_CHECK(h);
+    TGP_K(h, "k_sm_setup");
+    k_sm_setup<D><<<1, 128, 0, st>>>(dm, cst);
+    TGP_LAUNCH_CHECK(h);
+    long long* pN0 = (long long*)(h->pinned + 24);
+    int* pconv = (int*)(h->pinned + 25);
+    TGP_CUDA(h, cudaMemcpyAsync(pN0, &cst->N0, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    TGP_CUDA(h, cudaMemcpyAsync(pconv, &cst->conv_f, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TGP_CUDA(h, cudaStreamSynchronize(st));
+    h->d2h += 12;
+    const int64_t N0 = *pN0;
+    if (!*pconv || T < N0 + 2 * kCsL) return TGP_OK;
+    const int64_t nf = T - N0;
+    double *partials, *lml_dev;
+    const int64_t nblk = ((nf + kCsL - 1) / kCsL + kCsThreads - 1) / kCsThreads;
+    TGP_TRY(dalloc(h, (size_t)nblk, &partials));
+    TGP_TRY(dalloc(h, 1, &lml_dev));
+    FwdItems<D> fi{dy, N0, nullptr, partials};
+    BwdItems<D> bi{};
+    TGP_TRY((cs_scan<D, true>(h, cst, fi, bi, nf, cst->mstart, nullptr)));
+    TGP_K(h, "k_sm_lml");
+    k_sm_lml<D><<<1, 256, 0, st>>>(cst, partials, nblk, nf, lml_dev);
+    TGP_LAUNCH_CHECK(h);
+    TGP_TRY(deliver_scalar(h, lml_dev, lml_out));
+    return end_call(h, err, T, false, &cst->conv_f, converged);
+}
+
 template <int D>
 int do_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* m_f, int64_t s_m, double* P_f, int64_t s_P,
               double* lml_out, double* lml_steps) {
@@ -197,6 +241,17 @@ int do_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* m_f, int6
             if (attempt == 0 && h->algo == TGP_ALGO_AUTO && m->ordering == TGP_FORWARD && time_invariant(*m))
                 TGP_TRY(filter_steady<D>(h, d, dy, rq, &handled, &flag));
         }
+        if constexpr (D > TGP_REG_D) {
+            if (attempt == 0 && h->algo == TGP_ALGO_AUTO && m->ordering == TGP_FORWARD && time_invariant(*m) && !m_f && !P_f && !lml_steps &&
+                m->T >= 4 * kSmMaxEnd) {
+                bool conv = false;
+                TGP_TRY(logpdf_steady_vec<D>(h, d, dy, lml_out, &conv));
+                if (conv) return TGP_OK;
+                h->pending.clear();               // P did not settle within the head budget: the general scan below
+                TGP_CUDA(h, h->arena.reset());
+                continue;
+            }
+        }
         if (!handled) TGP_TRY(filter_general<D>(h, d, dy, rq));
         bool converged = true;
         TGP_TRY(end_call(h, rq.err, err_T(d), m->ordering == TGP_REVERSE, flag, &converged, &rq));
@@ -211,7 +266,6 @@ int do_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* m_f, int6
 // ---- backward pass over the stored filtering distributions (posterior marginals) -----------------
 // ---- posterior marginals of a time-invariant model: head / tail by the general kernels, the rest by constant-coefficient
 // scans over vectors (tgp_steady_smooth.cuh). *converged = false: nothing was delivered, the caller redoes the call generally.
-constexpr int64_t kSmMaxEnd = 8192;      // budget (steps) for each covariance recursion to stop moving
 
 template <int D>
 int posterior_marginals_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, const double* dRn, int64_t sRnew, double* dmean, double* dvar,

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128) k_sm_head_fwd(const DevModel dm, const do
         for (int e = tid; e < D * D; e += 128) {
             const int i = e / D, j = e % D;
             const double pf = fma(-sV[i] * invS, sV[j], sPp[e]);
-            if (i <= j) ws[(size_t)(D + Sym<D>::idx(i, j)) * Nmax + t] = pf;
+            if (ws && i <= j) ws[(size_t)(D + Sym<D>::idx(i, j)) * Nmax + t] = pf;
             dmax = fmax(dmax, fabs(pf - sP[e]));
             amax = fmax(amax, fabs(pf));
             sP[e] = pf;
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(128) k_sm_head_fwd(const DevModel dm, const do
         if (tid < D) {
             const double mf = fma(sV[tid] * invS, v, smp[tid]);
             sm[tid] = mf;
-            MFh[t * D + tid] = mf;
-            ws[(size_t)tid * Nmax + t] = mf;
+            if (MFh) MFh[t * D + tid] = mf;
+            if (ws) ws[(size_t)tid * Nmax + t] = mf;
         }
         __syncthreads();
         if ((t & 15) == 15 && t >= 31) {                             // test every 16 steps: a block reduction costs two barriers
@@ -565,9 +565,11 @@ __global__ void __launch_bounds__(kCsThreads) k_cs_apply0(const SmConst<D>* __re
 #pragma unroll
             for (int k = 0; k < D; ++k) x[k] = t[k] + u[k];
             if (FWD) {
-                double* o = fi.MF + (i + 1) * D;
+                if (fi.MF) {                                   // nullable: the log-likelihood alone needs no stored means
+                    double* o = fi.MF + (i + 1) * D;
 #pragma unroll
-                for (int k = 0; k < D; ++k) o[k] = x[k];
+                    for (int k = 0; k < D; ++k) o[k] = x[k];
+                }
             } else {
                 const long long tt = bi.t_hi - i;
                 double mu = cst->h0;

@@ -71,3 +71,27 @@ def test_steady_posterior_marginals_falls_back_when_not_converged(pkg, handle):
     np.testing.assert_allclose(got[0], ref[0], rtol=MV_RTOL, atol=1e-7)
     np.testing.assert_allclose(got[1], ref[1], rtol=MV_RTOL)
     assert abs(got[2] - ref[2]) <= LML_RTOL * abs(ref[2])
+
+
+def test_steady_logpdf_large_state_dimension(pkg, handle):
+    """logpdf of the D = 10 config-3 kernel on a long regular grid: no register-resident steady kernel exists for D > 6, so the
+    library runs the sequential single-CTA head + ONE constant-coefficient forward scan (logpdf_steady_vec). Same answer as the
+    general scan (TGP_ALGO_SCAN) and the sequential oracle, with fewer, lighter launches."""
+    kp, ko = _cfg3_kernels(pkg)
+    T = 60_000
+    mo = O.build_lgssm(ko, O.RegularSpacing(0.0, 0.01, T), 0.1)
+    rng = np.random.default_rng(77)
+    y = np.sin(np.arange(T) * 0.004) + 0.35 * rng.standard_normal(T)
+    model = pkg.to_sde(pkg.GP(kp))(pkg.RegularSpacing(0.0, 0.01, T), 0.1).build_lgssm()
+    ref = c_oracle.logpdf(c_oracle.Model.from_lgssm(mo), y)
+    lml = pkg.lgssm.logpdf(model, y, handle)
+    assert abs(lml - ref) <= LML_RTOL * abs(ref)
+    handle.set_algo(pkg.TGP_ALGO_SCAN)
+    try:
+        lml_g = pkg.lgssm.logpdf(model, y, handle)
+    finally:
+        handle.set_algo(pkg.TGP_ALGO_AUTO)
+    assert abs(lml - lml_g) <= 1e-9 * abs(ref)
+    # per-step output requested: the general kernels (the vector scan emits the sum only)
+    lml2, steps = pkg.lgssm.logpdf(model, y, handle, per_step=True)
+    assert abs(lml2 - ref) <= LML_RTOL * abs(ref) and abs(steps.sum() - ref) <= LML_RTOL * abs(ref)
