@@ -84,19 +84,27 @@ end
 struct B200LGSSM{Tm<:LGSSM}
     model::Tm
     device::Int
+    f32::Bool          # storage tag was B200Storage{Float32}: large-state products on the tensor cores (TGP_DENSE_TF32X3)
+end
+B200LGSSM(model, device::Int) = B200LGSSM(model, device, false)
+# handle of the model's device with the dense-path arithmetic of its storage tag selected
+function handle(m::B200LGSSM)
+    h = handle(m.device)
+    set_dense_math(h, m.f32 ? Float32 : Float64)
+    h
 end
 Base.length(m::B200LGSSM) = length(m.model)
 
 lgssm_components(k, t::AbstractVector, s::B200Storage{T}) where {T} = lgssm_components(k, t, SArrayStorage(T))
 function build_lgssm(f::LTISDE{<:GP,<:B200Storage}, x::AbstractVector, Σys::AbstractVector)
     inner = build_lgssm(LTISDE(f.f, SArrayStorage(eltype(f.storage))), x, Σys)
-    B200LGSSM(inner, f.storage.device)
+    B200LGSSM(inner, f.storage.device, eltype(f.storage) === Float32)
 end
 
 # logpdf(model, y) — src/models/lgssm.jl:147-151
 function logpdf(m::B200LGSSM, y::AbstractVector{<:Real})
     length(m) == length(y) || error("Dimension mismatch. length(prior) is $(length(m)), but length(y) is $(length(y))")
-    h = handle(m.device); mm = Marshalled(m.model); yy = convert(Vector{Float64}, y); out = Ref(0.0)
+    h = handle(m); mm = Marshalled(m.model); yy = convert(Vector{Float64}, y); out = Ref(0.0)
     GC.@preserve mm yy begin
         check(h, ccall((:tgp_logpdf, LIB), Cint, (Ptr{Cvoid}, Ref{Desc}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
                        h, mm.desc, yy, out, C_NULL))
@@ -106,12 +114,12 @@ end
 # missing data: host transform, kernels see plain Σ_t (src/models/missings.jl:8-13, 25-53)
 function logpdf(m::B200LGSSM, y::AbstractVector{Union{Missing,T}}) where {T}
     model2, y2 = transform_model_and_obs(m.model, y)
-    logpdf(B200LGSSM(model2, m.device), y2) + _logpdf_volume_compensation(y, m.model)
+    logpdf(B200LGSSM(model2, m.device, m.f32), y2) + _logpdf_volume_compensation(y, m.model)
 end
 
 # _filter(model, y) — src/models/lgssm.jl:171-173: Vector{Gaussian{SVector{D},SMatrix{D,D}}} written in place
 function _filter(m::B200LGSSM, y::AbstractVector{<:Real})
-    h = handle(m.device); mm = Marshalled(m.model); yy = convert(Vector{Float64}, y)
+    h = handle(m); mm = Marshalled(m.model); yy = convert(Vector{Float64}, y)
     D = Int(mm.desc.D); T = length(m); rec = D + D * D
     buf = Vector{Float64}(undef, rec * T)
     GC.@preserve mm yy buf begin
