@@ -97,7 +97,8 @@ Base.length(m::B200LGSSM) = length(m.model)
 
 lgssm_components(k, t::AbstractVector, s::B200Storage{T}) where {T} = lgssm_components(k, t, SArrayStorage(T))
 function build_lgssm(f::LTISDE{<:GP,<:B200Storage}, x::AbstractVector, Σys::AbstractVector)
-    inner = build_lgssm(LTISDE(f.f, SArrayStorage(eltype(f.storage))), x, Σys)
+    # the ABI takes Float64 arrays; with a Float32 tag the library converts to FP32 storage on the device
+    inner = build_lgssm(LTISDE(f.f, SArrayStorage(Float64)), x, Σys)
     B200LGSSM(inner, f.storage.device, eltype(f.storage) === Float32)
 end
 
