@@ -348,8 +348,12 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
     const int D = m->D, M = m->M;
     const int64_t T = m->T;
     cudaStream_t st = h->stream;
-    static cublasHandle_t cb = nullptr;
-    if (!cb) TGP_CUBLAS(h, cublasCreate(&cb));
+    if (!h->cublas) {            // one cuBLAS handle per library handle (= per device and stream owner), not per process
+        cublasHandle_t nb = nullptr;
+        TGP_CUBLAS(h, cublasCreate(&nb));
+        h->cublas = nb;
+    }
+    cublasHandle_t cb = (cublasHandle_t)h->cublas;
     TGP_CUBLAS(h, cublasSetStream(cb, st));
     TGP_CUBLAS(h, cublasSetPointerMode(cb, CUBLAS_POINTER_MODE_HOST));
     TGP_CUBLAS(h, cublasSetMathMode(cb, CUBLAS_PEDANTIC_MATH));   // plain FP64: no down-conversion anywhere
@@ -473,6 +477,12 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
     return TGP_OK;
 }
 
+}  // namespace tgp
+
+namespace tgp {
+void dense_release(tgp_ctx* h) {
+    if (h->cublas) { cublasDestroy((cublasHandle_t)h->cublas); h->cublas = nullptr; }
+}
 }  // namespace tgp
 
 #include "tgp_dense_tc.cuh"

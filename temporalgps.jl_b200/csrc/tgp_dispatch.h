@@ -23,6 +23,8 @@ template <int D> int do_shard_prefix(int n, const double* elems, const double* m
 int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out, double* lml_steps, double* m_f, int64_t s_m,
                  double* P_f, int64_t s_P);
 
+void dense_release(tgp_ctx* h);   // frees the dense path's cuBLAS handle
+
 // Peer-memory exchange of the time-sharded path (tgp_xchg.cu).
 int xchg_create(tgp_ctx* h, int rank, int world, int slot_doubles, void* ipc_handle_out);
 int xchg_open(tgp_ctx* h, const void* handles_all);

@@ -831,10 +831,12 @@ int launch_ss_main(tgp_ctx* h, bool stage_m, const SSConst<D>* cst, const double
                    unsigned* counters, const SSOut& so, const SSShard& sh) {
     using LY = SSLayout<D, L, NS>;
     const size_t smem = LY::bytes(stage_m);
-    static size_t attr_smem = 0;   // opt in to exactly what this instantiation needs (static + dynamic must stay <= 227 KB)
-    if (smem > attr_smem) {
+    // opt in to exactly what this instantiation needs (static + dynamic must stay <= 227 KB); function attributes are per DEVICE
+    static size_t attr_smem[64] = {0};
+    const int dv = h->device & 63;
+    if (smem > attr_smem[dv]) {
         TGP_CUDA(h, cudaFuncSetAttribute(k_ss_main<D, L, NS, OUTS, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
+        attr_smem[dv] = smem;
     }
     void* args[] = {(void*)&cst, (void*)&dy, (void*)&zbuf, (void*)&zstride, (void*)&agg, (void*)&counters, (void*)&so, (void*)&sh};
     TGP_K(h, sh.phase == 1 ? "k_ss_main(phase1)" : (sh.phase == 2 ? "k_ss_main(phase2)" : (sh.phase == 3 ? "k_ss_main(fused shard step)" : "k_ss_main")));
