@@ -112,6 +112,20 @@ def cpu_reference(T, reps, seed=20261017 + 2):
     return float(np.mean(ts)), lml
 
 
+METRIC = "Kalman filter steps/s (logpdf, Matern52 d=3, T=1e7 per GPU, FP64)"
+
+
+def workload_config(T, world, algo="auto"):
+    """`config` of the JSON line — identical in both arms so the driver can pair them."""
+    Tglob = T * world
+    return {"workload": (f"cfg2: GP(Matern52) D=3 M=1 RegularSpacing(0,{DT},T) sigma2={SIGMA2} logpdf; "
+                         f"T={T} per GPU, one series of {Tglob} steps sharded over time") if world > 1 else
+                        f"cfg2: GP(Matern52) D=3 M=1 RegularSpacing(0,{DT},{T}) sigma2={SIGMA2} logpdf",
+            "T_per_gpu": T, "T_total": Tglob, "algo": algo,
+            "l2": f"{N_BUF} rotating input buffers of {8 * T / 1e6:.0f} MB (> 126 MB L2 between reuses)",
+            "parallelism": f"time-sharded x{world}" if world > 1 else "single GPU"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -122,10 +136,10 @@ def run_reference(args):
     t, _ = cpu_reference(T, args.steps)
     v = T / t
     print(json.dumps({
-        "impl": "reference", "metric": "Kalman filter steps/s (logpdf, Matern52 d=3, T=1e7, FP64)", "value": v, "unit": "steps/s",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg2: GP(Matern52) D=3 M=1 RegularSpacing(0,{DT},{T}) sigma2={SIGMA2} logpdf", "T": T},
+        "config": workload_config(T, max(int(os.environ.get("WORLD_SIZE", "1")), 1), args.algo),
         "cpu_baseline": {"value": v, "unit": "steps/s", "cores": 1, "kind": "port",
                          "sample": f"{args.steps} x full T={T} logpdf, C restatement (oracle/lgssm_ref.c, static D=3), 1 thread: the "
                                    "reference recursion is sequential and single-threaded; Julia itself is not installable here"},
@@ -319,15 +333,10 @@ def run_ours(args):
             assert rel < 1e-6, f"GPU logpdf {lml_host[0]} differs from the oracle {lml_cpu}"
 
     out = {
-        "metric": "Kalman filter steps/s (logpdf, Matern52 d=3, T=1e7 per GPU, FP64)", "value": value, "unit": "steps/s",
+        "metric": METRIC, "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": max(W, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": value / 5e7, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"cfg2: GP(Matern52) D=3 M=1 RegularSpacing(0,{DT},T) sigma2={SIGMA2} logpdf; "
-                               f"T={T} per GPU, one series of {Tglob} steps sharded over time" if world > 1 else
-                               f"cfg2: GP(Matern52) D=3 M=1 RegularSpacing(0,{DT},{T}) sigma2={SIGMA2} logpdf",
-                   "T_per_gpu": T, "T_total": Tglob, "algo": args.algo,
-                   "l2": f"{N_BUF} rotating input buffers of {8 * T / 1e6:.0f} MB (> 126 MB L2 between reuses)",
-                   "parallelism": f"time-sharded x{world}" if world > 1 else "single GPU"},
+        "config": workload_config(T, world, args.algo),
         "logpdf_per_s": 1e3 / ms_per_step,
         "vs_baseline_note": "BASELINE.md: reference static-lgssm logpdf at N=1e7 read off a plot as 2.5-5e7 steps/s on an unstated CPU; "
                             "5e7 (upper end) used as the denominator",
