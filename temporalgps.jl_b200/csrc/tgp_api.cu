@@ -134,6 +134,7 @@ void tgp_destroy(tgp_handle h) {
     cudaStreamSynchronize(h->stream);
     xchg_destroy(h);
     dense_release(h);
+    h->fir.release();
     h->arena.release();
     for (auto& sp : h->spans) { cudaEventDestroy(sp.t0); cudaEventDestroy(sp.t1); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);

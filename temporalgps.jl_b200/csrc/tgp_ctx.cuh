@@ -66,6 +66,32 @@ struct tgp_shard_state {
     alignas(8) char work[256];   // tgp::SSWork<D>: device pointers of the run's workspace
 };
 
+// Persistent state of the one-launch steady-state logpdf (tgp_fir.cuh): the cached plan of the last model and a workspace that
+// outlives calls (the tile words are tagged with a per-call epoch instead of being cleared).
+struct tgp_fir_state {
+    std::vector<unsigned char> key;      // bytes the cached plan was built from
+    std::vector<unsigned char> plan;     // tgp::FirPlan<D>
+    std::vector<double> upload;          // host copy of the device tables (kept alive for the asynchronous upload)
+    int status = 1;
+    long long bad_step = -1;
+    double* dev = nullptr;   size_t dev_cap = 0;     // transient table + lane powers
+    void* agg = nullptr;     size_t agg_cap = 0;     // tile words
+    unsigned* counters = nullptr;
+    double* partials = nullptr; size_t partials_cap = 0;
+    double* result = nullptr;
+    unsigned long long epoch = 0;
+    void release() {
+        if (dev) cudaFree(dev);
+        if (agg) cudaFree(agg);
+        if (counters) cudaFree(counters);
+        if (partials) cudaFree(partials);
+        if (result) cudaFree(result);
+        dev = nullptr; agg = nullptr; counters = nullptr; partials = nullptr; result = nullptr;
+        dev_cap = agg_cap = partials_cap = 0;
+        key.clear();
+    }
+};
+
 struct tgp_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -100,6 +126,7 @@ struct tgp_ctx {
     unsigned long long* sticky = nullptr;
     void* cublas = nullptr;                             // cublasHandle_t of the FP64 dense path (tgp_dense.cu), created on first use
     void* xchg = nullptr;                               // tgp::XchgState: peer-memory exchange of the time-sharded path (tgp_xchg.cu)
+    tgp_fir_state fir;
 };
 
 namespace tgp {

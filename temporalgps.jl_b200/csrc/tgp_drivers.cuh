@@ -6,6 +6,7 @@
 #include "tgp_dispatch.h"
 #include "tgp_scan_small.cuh"
 #include "tgp_steady.cuh"
+#include "tgp_fir.cuh"
 #include "tgp_steady_smooth.cuh"
 
 namespace tgp {
@@ -225,6 +226,15 @@ int logpdf_steady_vec(tgp_ctx* h, const tgp_lgssm& d, const double* dy, double* 
 template <int D>
 int do_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* m_f, int64_t s_m, double* P_f, int64_t s_P,
               double* lml_out, double* lml_steps) {
+    if constexpr (D <= kFirMaxD) {   // log-likelihood only, time-invariant: one launch, one pass over y (tgp_fir.cuh)
+        if (h->algo == TGP_ALGO_AUTO && m->ordering == TGP_FORWARD && time_invariant(*m) && !m_f && !P_f && !lml_steps) {
+            bool handled = false;
+            TGP_TRY(logpdf_fir<D>(h, m, y, lml_out, &handled));
+            if (handled) return TGP_OK;
+            h->pending.clear();
+            TGP_CUDA(h, h->arena.reset());
+        }
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         tgp_lgssm d;
         const double* dy;
