@@ -62,6 +62,13 @@ struct FirArgs {
 __device__ __forceinline__ void fir_ld4(const double* p, double& a, double& b, double& c, double& d) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
+__device__ __forceinline__ unsigned long long fir_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void fir_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void fir_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fir_put_word(double2* p, double v, unsigned long long tag) {
     asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(__longlong_as_double((long long)tag)) : "memory");
 }
@@ -83,23 +90,37 @@ template <int D> __device__ __forceinline__ Vec<D> fir_shfl_up(const Vec<D>& v, 
     return r;
 }
 
-// One tile. ys: observation of the tile's first step. slot: index of the tile's word group in agg. nvalid: steps of the tile that
+// ---- staging of a full, aligned tile: coalesced 16-byte cp.async into a per-warp buffer of 32 padded rows (one row = one lane's run,
+// 34 doubles apart so the lanes' 128-bit reads are conflict-free). The NEXT tile of the warp streams in while the current one is
+// being computed from registers.
+constexpr int kFirRow = kFirL + 2;                    // doubles between rows
+constexpr int kFirBufDoubles = 32 * kFirRow;          // per warp
+__device__ __forceinline__ void fir_cp16(double* smem_dst, const double* g, unsigned long long pol) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void fir_issue_tile(double* buf, const double* __restrict__ ys, int lane, unsigned long long pol) {
+#pragma unroll
+    for (int k = 0; k < kFirL / 2; ++k) {
+        const int c = k * 32 + lane;                  // 16-byte chunk of the tile: consecutive lanes, consecutive addresses
+        fir_cp16(buf + (c >> 4) * kFirRow + (c & 15) * 2, ys + 2 * c, pol);
+    }
+}
+__device__ __forceinline__ void fir_read_tile(const double* buf, int lane, double (&yv)[kFirL]) {
+    const double2* row = reinterpret_cast<const double2*>(buf + lane * kFirRow);
+#pragma unroll
+    for (int i = 0; i < kFirL / 2; ++i) {
+        const double2 t = row[i];
+        yv[2 * i] = t.x;
+        yv[2 * i + 1] = t.y;
+    }
+}
+
+// One tile from the lane's 32 observations in registers. slot: index of the tile's word group in agg. nvalid: steps of the tile that
 // exist (TAIL only). pub: publish the zero-state response. full: wait for the carry and run pass B. Returns the lane's sum of v^2.
 template <int D, bool TAIL>
-__device__ __forceinline__ double fir_tile_body(const FirPlan<D>& pl, const FirArgs& ar, const double* __restrict__ ys, long long slot,
-                                           int nvalid, bool pub, bool full, const double* __restrict__ splane, int lane) {
-    double yv[kFirL];
-    if (!TAIL) {
-        const double* p = ys + lane * kFirL;
-#pragma unroll
-        for (int i = 0; i < kFirL / 4; ++i) fir_ld4(p + 4 * i, yv[4 * i], yv[4 * i + 1], yv[4 * i + 2], yv[4 * i + 3]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < kFirL; ++j) {
-            const int e = lane * kFirL + j;
-            yv[j] = e < nvalid ? __ldg(ys + e) : 0.0;
-        }
-    }
+__device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, const FirArgs& ar, double (&yv)[kFirL], long long slot, int nvalid,
+                                                   bool pub, bool full, const double* __restrict__ splane, int lane) {
     // ---- pass A: zero-state response of the lane's run --------------------------------------------------------------
     Vec<D> u[kFirNBlk], z = vzero<D>();
     fir_pass_a<D>(pl, yv, u, z);
@@ -116,22 +137,24 @@ __device__ __forceinline__ double fir_tile_body(const FirPlan<D>& pl, const FirA
     if (!full) return 0.0;
     Vec<D> m = fir_shfl_up(z, 1);
     if (lane == 0) m = vzero<D>();
-    // ---- carry: state entering the tile from the nb tiles before it -------------------------------------------------------
-    {
-        const int npoll = pl.nb * D;
-        double val = 0.0;
-        const double2* wp = ar.agg + (slot - 1 - lane / D) * D + (lane % D);
-        if (lane < npoll) {
-            unsigned long long tag;
-            unsigned spins = 0;
-            for (;;) {
-                fir_get_word(wp, val, tag);
-                if (tag == ar.epoch) break;
-                if (++spins > (1u << 28)) __trap();    // a predecessor that never arrives (a lost peer rank): fail loudly
-                __nanosleep(64);
-            }
+    // ---- carry: state entering the tile from the nb tiles before it. First look right away (the load is in flight during the
+    // data-only half of pass B), then spin if a predecessor had not published yet.
+    const int npoll = pl.nb * D;
+    double val = 0.0;
+    unsigned long long tag = ar.epoch;
+    const double2* wp = ar.agg + (slot - 1 - lane / D) * D + (lane % D);
+    if (lane < npoll) fir_get_word(wp, val, tag);
+    fir_pass_b1<D>(pl, yv);
+    if (lane < npoll) {
+        unsigned spins = 0;
+        while (tag != ar.epoch) {
+            if (++spins > (1u << 28)) __trap();    // a predecessor that never arrives (a lost peer rank): fail loudly
+            __nanosleep(32);
+            fir_get_word(wp, val, tag);
         }
-        __syncwarp();
+    }
+    __syncwarp();
+    {
         Vec<D> c;
 #pragma unroll
         for (int i = 0; i < D; ++i) c[i] = __shfl_sync(0xffffffffu, val, i);
@@ -146,16 +169,21 @@ __device__ __forceinline__ double fir_tile_body(const FirPlan<D>& pl, const FirA
 #pragma unroll
             for (int j = 0; j < D; ++j) m[i] = fma(splane[(i * D + j) * 32 + lane], c[j], m[i]);
     }
-    // ---- pass B: innovations of the lane's run from its true start state ---------------------------------------------------
-    return fir_pass_b<D, TAIL>(pl, yv, u, m, TAIL ? nvalid - lane * kFirL : kFirL);
+    // ---- pass B, state half -------------------------------------------------------------------------------------------------
+    return fir_pass_b2<D, TAIL>(pl, yv, u, m, TAIL ? nvalid - lane * kFirL : kFirL);
 }
 
-// Full, aligned tiles are inlined into the kernel (coefficients become constant-bank operands); partial / unaligned / halo tiles
-// take one out-of-line copy of the guarded variant.
+// Partial / unaligned / halo tiles: guarded scalar loads straight from global memory, one out-of-line copy.
 template <int D>
 __device__ __noinline__ double fir_tile_guarded(const FirPlan<D>& pl, const FirArgs& ar, const double* __restrict__ ys, long long slot, int nvalid,
                                                 bool pub, bool full, const double* __restrict__ splane, int lane) {
-    return fir_tile_body<D, true>(pl, ar, ys, slot, nvalid, pub, full, splane, lane);
+    double yv[kFirL];
+#pragma unroll
+    for (int j = 0; j < kFirL; ++j) {
+        const int e = lane * kFirL + j;
+        yv[j] = e < nvalid ? __ldg(ys + e) : 0.0;
+    }
+    return fir_tile_compute<D, true>(pl, ar, yv, slot, nvalid, pub, full, splane, lane);
 }
 
 // The transient: steps [0, N0) with the tabulated gains, one warp. Lane l owns a run of ceil(N0 / 32) steps: it composes the run's
@@ -256,6 +284,7 @@ __device__ __noinline__ double fir_head(const FirPlan<D>& pl, const FirArgs& ar,
 template <int D>
 __global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm)
 k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirArgs ar) {
+    extern __shared__ __align__(16) double sbuf[];   // kFirWarps staging buffers
     __shared__ double splane[D * D * 32];
     __shared__ double sred[kFirWarps];
     __shared__ unsigned s_vb;
@@ -320,15 +349,33 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         // items of this warp: [its deferred tile, pass A only] tiles first, first + NW, ... [the deferred tile, pass B]
         const long long first = deferred ? gw + NW : gw;
         const long long n_main = ntiles > first ? (ntiles - first + NW - 1) / NW : 0;
-        for (long long it = deferred ? -1 : 0; it < n_main + (deferred ? 1 : 0); ++it) {
-            const bool main_item = it >= 0 && it < n_main;
-            const long long t = main_item ? first + it * NW : gw;
+        const long long it0 = deferred ? -1 : 0, it1 = n_main + (deferred ? 1 : 0);
+        double* buf = sbuf + wp * kFirBufDoubles;
+        const unsigned long long pol = fir_policy_evict_first();
+        auto tile_of = [&](long long it) { return (it >= 0 && it < n_main) ? first + it * NW : gw; };
+        auto staged = [&](long long it) { return it < it1 && pl.aligned && Ts - tile_of(it) * kFirTile >= kFirTile; };
+        if (staged(it0)) fir_issue_tile(buf, ys + tile_of(it0) * kFirTile, lane, pol);
+        fir_cp_commit();
+        for (long long it = it0; it < it1; ++it) {
+            const long long t = tile_of(it);
             const bool pub = it < n_main, full = it >= 0;
             const long long s0 = t * kFirTile;
-            const long long left = Ts - s0;
-            if (pl.aligned && left >= kFirTile) q += fir_tile_body<D, false>(pl, ar, ys + s0, t + kFirNbMax, kFirTile, pub, full, splane, lane);
-            else q += fir_tile_guarded<D>(pl, ar, ys + s0, t + kFirNbMax, (int)min(left, (long long)kFirTile), pub, full, splane, lane);
+            if (staged(it)) {
+                double yv[kFirL];
+                fir_cp_wait_all();
+                __syncwarp();
+                fir_read_tile(buf, lane, yv);
+                __syncwarp();
+                if (staged(it + 1)) fir_issue_tile(buf, ys + tile_of(it + 1) * kFirTile, lane, pol);
+                fir_cp_commit();
+                q += fir_tile_compute<D, false>(pl, ar, yv, t + kFirNbMax, kFirTile, pub, full, splane, lane);
+            } else {
+                if (staged(it + 1)) fir_issue_tile(buf, ys + tile_of(it + 1) * kFirTile, lane, pol);
+                fir_cp_commit();
+                q += fir_tile_guarded<D>(pl, ar, ys + s0, t + kFirNbMax, (int)min(Ts - s0, (long long)kFirTile), pub, full, splane, lane);
+            }
         }
+        fir_cp_wait_all();
     }
     // ---- fixed-order reductions; the last CTA to finish forms the log-likelihood ------------------------------------------
 #pragma unroll
@@ -462,7 +509,13 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     ar.lml_user = (lml_out && is_device_ptr(lml_out)) ? lml_out : nullptr;
     if (xc) ar.x = *xc;
     TGP_K(h, "k_fir_logpdf");
-    k_fir_logpdf<D><<<G, kFirThreads, 0, h->stream>>>(pl, ar);
+    constexpr size_t smem = (size_t)kFirWarps * kFirBufDoubles * sizeof(double);
+    static bool attr_set[64] = {false};
+    if (!attr_set[h->device & 63]) {   // ask for the shared-memory carve-out that lets kFirCtasPerSm CTAs live on one SM
+        TGP_CUDA(h, cudaFuncSetAttribute(k_fir_logpdf<D>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+        attr_set[h->device & 63] = true;
+    }
+    k_fir_logpdf<D><<<G, kFirThreads, smem, h->stream>>>(pl, ar);
     TGP_LAUNCH_CHECK(h);
     *handled = true;
     if (lml_out && !ar.lml_user) {

@@ -89,19 +89,33 @@ TGP_UNROLL
 TGP_UNROLL
         for (int j = 0; j < D; ++j) c[i] = fma(pl.PT[k][i][j], tk[j], c[i]);
 }
-// pass B: innovations of the lane's run from its true start state m; returns sum v^2 over the first nvalid steps of the run.
+// pass B, data-only half (needs no state, so it runs while the carry is in flight): y_j <- y_j - kap_j - sum_{i<j} g_{j-1-i} y_i,
+// in place, j descending inside each block.
+template <int D>
+TGP_HD void fir_pass_b1(const FirPlan<D>& pl, double (&yv)[kFirL]) {
+TGP_UNROLL
+    for (int b = 0; b < kFirNBlk; ++b) {
+TGP_UNROLL
+        for (int j = kFirB - 1; j >= 0; --j) {
+            double v = yv[b * kFirB + j] - pl.kap[j];
+TGP_UNROLL
+            for (int i = 0; i < j; ++i) v = fma(-pl.g[j - 1 - i], yv[b * kFirB + i], v);
+            yv[b * kFirB + j] = v;
+        }
+    }
+}
+// pass B, state half: v_j = (the above) - (w'Abar^j) m from the true block-start state m; m <- Abar^8 m + u_b. Returns sum v^2 over the
+// first nvalid steps of the run.
 template <int D, bool TAIL>
-TGP_HD double fir_pass_b(const FirPlan<D>& pl, const double (&yv)[kFirL], const Vec<D> (&u)[kFirNBlk], Vec<D> m, int nvalid) {
+TGP_HD double fir_pass_b2(const FirPlan<D>& pl, const double (&yv)[kFirL], const Vec<D> (&u)[kFirNBlk], Vec<D> m, int nvalid) {
     double q = 0.0;
 TGP_UNROLL
     for (int b = 0; b < kFirNBlk; ++b) {
 TGP_UNROLL
         for (int j = 0; j < kFirB; ++j) {
-            double v = yv[b * kFirB + j] - pl.kap[j];
+            double v = yv[b * kFirB + j];
 TGP_UNROLL
             for (int i = 0; i < D; ++i) v = fma(-pl.wA[j][i], m[i], v);
-TGP_UNROLL
-            for (int i = 0; i < j; ++i) v = fma(-pl.g[j - 1 - i], yv[b * kFirB + i], v);
             if (TAIL) {
                 if (b * kFirB + j < nvalid) q = fma(v, v, q);
             } else {
@@ -184,6 +198,28 @@ void fir_build_plan(const double* hA, const double* ha, const double* hQ, const 
     }
     if (N0conv < 0) return;                 // no fixed point within the budget: general scan
     P.N0conv = N0conv;
+    // The transient ends where successive P differ by tol; the steady constants come from the fixed point itself: keep iterating
+    // (data-free, a few hundred 3x3 steps) until P stops moving in double precision, so that the frozen gain carries no O(tol) bias.
+    {
+        double prev = 1e300;
+        for (long long t = 0; t < 4 * kFirMaxN0; ++t) {
+            const Sym<D> Pp = congruence(A, Pf, Q);
+            const Vec<D> V = symvec(Pp, H);
+            const double Sx = dot(V, H) + R;
+            const double is = 1.0 / sqrt(Sx);
+            double err = 0.0, nrm = 0.0;
+            Sym<D> Pn;
+            for (int j = 0; j < D; ++j)
+                for (int i = 0; i <= j; ++i) {
+                    Pn(i, j) = fma(-(V[i] * is), V[j] * is, Pp(i, j));
+                    err = fmax(err, fabs(Pn(i, j) - Pf(i, j)));
+                    nrm = fmax(nrm, fabs(Pn(i, j)));
+                }
+            Pf = Pn;
+            if (err <= 4e-16 * nrm || (err >= prev && err <= 1e-14 * nrm)) break;
+            prev = err;
+        }
+    }
     // ---- constants of the steady recursion: one more step from the converged P ---------------------------------------------
     {
         const Sym<D> Pp = congruence(A, Pf, Q);

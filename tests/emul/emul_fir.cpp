@@ -1,6 +1,6 @@
 // emul_fir.cpp — g++-compiled, single-threaded emulation of the one-launch steady-state logpdf kernel (tgp_fir.cuh), built from the
 // SAME plan builder and per-lane arithmetic (tgp_fir_plan.h: fir_build_plan, fir_pass_a, fir_scan_level, fir_carry_add,
-// fir_pass_b); the warp shuffles, the tile words and the look-back are replaced by arrays. TEST HARNESS ONLY.
+// fir_pass_b1, fir_pass_b2); the warp shuffles, the tile words and the look-back are replaced by arrays. TEST HARNESS ONLY.
 #include <cstdint>
 #include <vector>
 
@@ -74,8 +74,9 @@ static int run(const double* A, const double* a, const double* Q, const double* 
             Vec<D> m = lane ? z[lane - 1] : vzero<D>();
             for (int i = 0; i < D; ++i)
                 for (int j = 0; j < D; ++j) m[i] = fma(plane[(i * D + j) * 32 + lane], c[j], m[i]);
-            q += nvalid == kFirTile ? fir_pass_b<D, false>(pl, yv[lane], u[lane], m, kFirL)
-                                    : fir_pass_b<D, true>(pl, yv[lane], u[lane], m, nvalid - lane * kFirL);
+            fir_pass_b1<D>(pl, yv[lane]);
+            q += nvalid == kFirTile ? fir_pass_b2<D, false>(pl, yv[lane], u[lane], m, kFirL)
+                                    : fir_pass_b2<D, true>(pl, yv[lane], u[lane], m, nvalid - lane * kFirL);
         }
     }
     *lml_out = pl.c0 - 0.5 * (qh + pl.invS * q);
