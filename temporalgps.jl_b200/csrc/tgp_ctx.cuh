@@ -75,19 +75,17 @@ struct tgp_fir_state {
     int status = 1;
     long long bad_step = -1;
     double* dev = nullptr;   size_t dev_cap = 0;     // transient table + lane powers
-    void* agg = nullptr;     size_t agg_cap = 0;     // tile words
     unsigned* counters = nullptr;
     double* partials = nullptr; size_t partials_cap = 0;
     double* result = nullptr;
     unsigned long long epoch = 0;
     void release() {
         if (dev) cudaFree(dev);
-        if (agg) cudaFree(agg);
         if (counters) cudaFree(counters);
         if (partials) cudaFree(partials);
         if (result) cudaFree(result);
-        dev = nullptr; agg = nullptr; counters = nullptr; partials = nullptr; result = nullptr;
-        dev_cap = agg_cap = partials_cap = 0;
+        dev = nullptr; counters = nullptr; partials = nullptr; result = nullptr;
+        dev_cap = partials_cap = 0;
         key.clear();
     }
 };

@@ -4,24 +4,26 @@
 //
 // Past the covariance transient (host plan, tgp_fir_plan.h) the filter is the constant-coefficient recursion
 //      m_t = Abar m_{t-1} + K y_t + c,    v_t = y_t - w'm_{t-1} - hh,    lml_t = -(log 2pi + log S + v_t^2 / S) / 2.
-// The steady steps are cut into tiles of 1024 = 32 lanes x 32 steps; a lane keeps its 32 observations in registers
-// (8 x 256-bit loads) and works on blocks of 8 steps:
+// The steady steps are cut into tiles of 1024 = 32 lanes x 32 steps. One 16-warp CTA per SM owns a CONTIGUOUS chunk of tiles, its
+// warps take them round-robin. A lane keeps its 32 observations in registers and works on blocks of 8 steps:
 //   pass A   u_b = zc + sum_j (Abar^(7-j) K) y_j ;  z <- Abar^8 z + u_b          zero-state response of the lane's run
-//   scan     5 shuffle levels with Abar^(32 2^k): lane-exclusive prefix; lane 31 PUBLISHES the tile's zero-state
-//            response (3 x 16-byte {value, epoch} words, no fence)
-//   carry    the state entering the tile = sum_{k=1..nb} Abar^(1024 (k-1)) tot_{t-k}: a stable filter forgets its start,
-//            so nb (1..3, from |Abar^1024|, decided by the plan) PREDECESSOR tiles suffice to double precision. Those
-//            tiles are being processed by neighbouring warps at the same moment — there is no serial chain through the
-//            series, no second pass over y, no grid barrier and no scratch besides 48 B per tile.
-//   pass B   from the true block-start state m: v_j = y_j - kap_j - (w'Abar^j) m - sum_{i<j} g_{j-1-i} y_i (independent FMAs,
-//            coefficients are kernel parameters = constant-bank operands), q += v_j^2 ;  m <- Abar^8 m + u_b.
-// 14.4 DFMA per step instead of ~25 for the two-phase kernel (tgp_steady.cuh), the loop-carried chain is 3 DFMA per 8 steps.
-// The transient (the first N0 steps, where P_t still moves) is one warp of a service CTA running the time-varying affine
-// recursion with the gains K_t, 1/S_t tabulated by the plan. Time shards (multi-GPU) use the same kernel: a rank > 0 replaces the
-// transient by pass A over the last nb tiles of its predecessor's shard (the "halo": 8 KB per tile, pushed over NVLink by the
-// predecessor's service CTA at the START of its kernel), so shards never wait for each other's results.
-// Work assignment is static and deterministic: CTAs take a virtual index in start order (atomic), warp gw owns tiles
-// gw, gw + NW, ...; every reduction has a fixed order, so the result is bit-reproducible.
+//   scan     5 shuffle levels with Abar^(32 2^k): lane-exclusive prefix; lane 31 PUBLISHES the tile's zero-state response in a
+//            shared-memory ring
+//   pass B1  y_j <- y_j - kap_j - sum_{i<j} g_{j-1-i} y_i  (needs no state: runs while the neighbours publish)
+//   carry    the state entering the tile = sum_{k=1..nb} Abar^(1024 (k-1)) tot_{t-k}: a stable filter forgets its start, so the nb
+//            (1..3, from |Abar^1024|, decided by the plan) PREDECESSOR tiles suffice to double precision. They are being processed
+//            by the neighbouring warps of the same CTA at the same moment: no serial chain through the series, no second pass over
+//            y, no grid barrier, no global scratch. The first tiles of a chunk take theirs from pass A over the nb tiles BEFORE the
+//            chunk (re-read from HBM: 1-3 % extra traffic), so CTAs never talk to each other.
+//   pass B2  v_j = (B1) - (w'Abar^j) m from the true block-start state, q += v_j^2 ;  m <- Abar^8 m + u_b.
+// 14.4 DFMA per step (two-phase kernel of tgp_steady.cuh: ~25) with every coefficient a constant-bank operand (the plan is a kernel
+// parameter); the loop-carried chain is 3 DFMA per 8 steps. y streams through per-warp cp.async buffers (coalesced 16-byte copies
+// into padded rows), one tile ahead of the arithmetic.
+// The transient (the first N0 steps, where P_t still moves) is run by CTA 0 as a block-wide scan over the affine maps
+// x -> A x + a + K_t (y_t - hh - w'x) with the gains K_t, 1/S_t tabulated by the plan. Time shards (multi-GPU): a rank > 0 has no
+// transient; its CTA 0 takes the nb tiles before the shard (the "halo", 8 KB per tile) from a buffer its predecessor's kernel
+// fills over NVLink at the START of its run, so shards never wait for each other's results.
+// Work assignment is static and every reduction has a fixed order: the result is bit-reproducible.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -33,10 +35,16 @@
 
 namespace tgp {
 
+constexpr int kFirThreads = 512;
+constexpr int kFirWarps = kFirThreads / 32;
+constexpr int kFirRing = 64;                          // tile words kept in shared memory (>= 2 rounds of 16 warps + look-back)
+constexpr int kFirRow = kFirL + 2;                    // doubles between the rows of a staging buffer
+constexpr int kFirBufDoubles = 32 * kFirRow;          // staging buffer of one warp
+
 struct FirXchg {                  // time-sharded use (all null / 0 on a single GPU)
     const double* halo;           // nb * 1024 observations preceding this shard's first step, oldest first (rank > 0)
     const unsigned long long* halo_flag;   // wait for *halo_flag >= epoch before reading the halo (null: no wait)
-    unsigned long long* ack_out;  // predecessor's ack word (peer memory): set to epoch once the halo is in registers
+    unsigned long long* ack_out;  // predecessor's ack word (peer memory): set to epoch once the halo has been consumed
     double* push_dst;             // successor's halo buffer for this epoch (peer memory), null on the last rank
     unsigned long long* push_flag;         // successor's halo flag (peer memory)
     const unsigned long long* ack_in;      // own ack word: wait for >= epoch - ring before overwriting the ring slot
@@ -50,18 +58,24 @@ struct FirArgs {
     const double* y;              // observations of this shard, index = time
     const double* tab;            // transient table [N0][D + 1]: K_t, 1/S_t
     const double* plane;          // [D*D][32]: Abar^(32 lane), entry-major
-    double2* agg;                 // (ntiles + kFirNbMax) * D words {value, epoch bits}; slot(t) = t + kFirNbMax
-    unsigned long long epoch;     // tag of this call's words
-    unsigned* counters;           // [0] virtual CTA index claim, [1] finished CTAs (both left at 0 by the last CTA)
-    double* partials;             // gridDim.x per-CTA sums of v^2 (+ [gridDim.x]: transient's sum of v^2 / S_t)
+    unsigned long long epoch;     // call counter of the handle (exchange flags)
+    unsigned* counters;           // [0] finished CTAs (left at 0 by the last CTA)
+    double* partials;             // gridDim.x per-CTA sums of v^2, [gridDim.x]: the transient's sum of v^2 / S_t
     double* result;               // lml of this shard (device)
     double* lml_user;             // caller's device destination, nullable
     FirXchg x;
 };
 
-__device__ __forceinline__ void fir_ld4(const double* p, double& a, double& b, double& c, double& d) {
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
+template <int D>
+struct FirSmem {
+    static constexpr int o_plane = kFirWarps * kFirBufDoubles;
+    static constexpr int o_ring = o_plane + D * D * 32;
+    static constexpr int o_red = o_ring + (kFirRing + kFirNbMax) * D;
+    static constexpr int o_scan = o_red + kFirWarps + 2;                 // transient: per-warp affine maps (D*D + D each)
+    static constexpr int o_tag = o_scan + kFirWarps * (D * D + D);       // kFirRing + kFirNbMax ints
+    static constexpr size_t bytes = (size_t)o_tag * sizeof(double) + (kFirRing + kFirNbMax) * sizeof(int);
+};
+
 __device__ __forceinline__ unsigned long long fir_policy_evict_first() {
     unsigned long long p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -69,36 +83,17 @@ __device__ __forceinline__ unsigned long long fir_policy_evict_first() {
 }
 __device__ __forceinline__ void fir_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void fir_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fir_put_word(double2* p, double v, unsigned long long tag) {
-    asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(__longlong_as_double((long long)tag)) : "memory");
-}
-__device__ __forceinline__ void fir_get_word(const double2* p, double& v, unsigned long long& tag) {
-    double t;
-    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "l"(p) : "memory");
-    tag = (unsigned long long)__double_as_longlong(t);
-}
 __device__ __forceinline__ unsigned long long fir_ld_sys(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-
-template <int D> __device__ __forceinline__ Vec<D> fir_shfl_up(const Vec<D>& v, int off) {
-    Vec<D> r;
-#pragma unroll
-    for (int i = 0; i < D; ++i) r[i] = __shfl_up_sync(0xffffffffu, v[i], off);
-    return r;
-}
-
-// ---- staging of a full, aligned tile: coalesced 16-byte cp.async into a per-warp buffer of 32 padded rows (one row = one lane's run,
-// 34 doubles apart so the lanes' 128-bit reads are conflict-free). The NEXT tile of the warp streams in while the current one is
-// being computed from registers.
-constexpr int kFirRow = kFirL + 2;                    // doubles between rows
-constexpr int kFirBufDoubles = 32 * kFirRow;          // per warp
 __device__ __forceinline__ void fir_cp16(double* smem_dst, const double* g, unsigned long long pol) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sa), "l"(g), "l"(pol) : "memory");
 }
+// Staging of a full, aligned tile: coalesced 16-byte cp.async into 32 padded rows (one row = one lane's run; 34 doubles apart, so
+// the lanes' 128-bit reads are conflict-free).
 __device__ __forceinline__ void fir_issue_tile(double* buf, const double* __restrict__ ys, int lane, unsigned long long pol) {
 #pragma unroll
     for (int k = 0; k < kFirL / 2; ++k) {
@@ -116,11 +111,31 @@ __device__ __forceinline__ void fir_read_tile(const double* buf, int lane, doubl
     }
 }
 
-// One tile from the lane's 32 observations in registers. slot: index of the tile's word group in agg. nvalid: steps of the tile that
-// exist (TAIL only). pub: publish the zero-state response. full: wait for the carry and run pass B. Returns the lane's sum of v^2.
+template <int D> __device__ __forceinline__ Vec<D> fir_shfl_up(const Vec<D>& v, int off) {
+    Vec<D> r;
+#pragma unroll
+    for (int i = 0; i < D; ++i) r[i] = __shfl_up_sync(0xffffffffu, v[i], off);
+    return r;
+}
+
+// The shared-memory ring of tile words: entry r (= tile index relative to the chunk + kFirNbMax) holds the zero-state response of
+// that tile (or, for r < kFirNbMax, what precedes the chunk); tag[r % kFirRing] == r once it is there.
+// Entries r < kFirNbMax (what precedes the chunk) have fixed slots; the tiles of the chunk share the ring.
+__device__ __forceinline__ int fir_slot(int r) { return r < kFirNbMax ? r : kFirNbMax + ((r - kFirNbMax) % kFirRing); }
+template <int D>
+__device__ __forceinline__ void fir_publish(double* sring, int* stag, int r, const Vec<D>& z) {
+    volatile double* p = sring + fir_slot(r) * D;
+#pragma unroll
+    for (int i = 0; i < D; ++i) p[i] = z[i];
+    __threadfence_block();
+    *reinterpret_cast<volatile int*>(stag + fir_slot(r)) = r;
+}
+
+// One tile from the lane's 32 observations in registers. r: ring entry of the tile. nvalid: steps of the tile that exist (TAIL only).
+// pub: publish the zero-state response. full: take the carry and run pass B. Returns the lane's sum of v^2.
 template <int D, bool TAIL>
-__device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, const FirArgs& ar, double (&yv)[kFirL], long long slot, int nvalid,
-                                                   bool pub, bool full, const double* __restrict__ splane, int lane) {
+__device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double (&yv)[kFirL], int r, int nvalid, bool pub, bool full,
+                                                   const double* __restrict__ splane, double* sring, int* stag, int lane) {
     // ---- pass A: zero-state response of the lane's run --------------------------------------------------------------
     Vec<D> u[kFirNBlk], z = vzero<D>();
     fir_pass_a<D>(pl, yv, u, z);
@@ -130,38 +145,33 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, const F
         const Vec<D> zu = fir_shfl_up(z, 1 << k);
         if (lane >= (1 << k)) z = fir_scan_level<D>(pl, k, z, zu);
     }
-    if (pub && lane == 31) {
-#pragma unroll
-        for (int i = 0; i < D; ++i) fir_put_word(ar.agg + slot * D + i, z[i], ar.epoch);
-    }
+    if (pub && lane == 31) fir_publish<D>(sring, stag, r, z);
     if (!full) return 0.0;
     Vec<D> m = fir_shfl_up(z, 1);
     if (lane == 0) m = vzero<D>();
-    // ---- carry: state entering the tile from the nb tiles before it. First look right away (the load is in flight during the
-    // data-only half of pass B), then spin if a predecessor had not published yet.
-    const int npoll = pl.nb * D;
-    double val = 0.0;
-    unsigned long long tag = ar.epoch;
-    const double2* wp = ar.agg + (slot - 1 - lane / D) * D + (lane % D);
-    if (lane < npoll) fir_get_word(wp, val, tag);
+    // ---- pass B, data-only half (the neighbours publish meanwhile) ----------------------------------------------------------
     fir_pass_b1<D>(pl, yv);
-    if (lane < npoll) {
+    // ---- carry: state entering the tile from the nb entries before it ----------------------------------------------------
+    if (lane < pl.nb) {
+        const int want = r - 1 - lane;
+        const volatile int* tg = stag + fir_slot(want);
         unsigned spins = 0;
-        while (tag != ar.epoch) {
-            if (++spins > (1u << 28)) __trap();    // a predecessor that never arrives (a lost peer rank): fail loudly
-            __nanosleep(32);
-            fir_get_word(wp, val, tag);
+        while (*tg != want) {
+            if (++spins > (1u << 26)) __trap();        // cannot happen short of a lost peer rank (halo): fail loudly, do not hang
+            __nanosleep(20);
         }
     }
     __syncwarp();
     {
         Vec<D> c;
+        const volatile double* e = sring + fir_slot(r - 1) * D;
 #pragma unroll
-        for (int i = 0; i < D; ++i) c[i] = __shfl_sync(0xffffffffu, val, i);
+        for (int i = 0; i < D; ++i) c[i] = e[i];
         for (int k = 1; k < pl.nb; ++k) {
             Vec<D> tk;
+            const volatile double* ek = sring + fir_slot(r - 1 - k) * D;
 #pragma unroll
-            for (int i = 0; i < D; ++i) tk[i] = __shfl_sync(0xffffffffu, val, k * D + i);
+            for (int i = 0; i < D; ++i) tk[i] = ek[i];
             fir_carry_add<D>(pl, k, tk, c);
         }
 #pragma unroll
@@ -175,25 +185,27 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, const F
 
 // Partial / unaligned / halo tiles: guarded scalar loads straight from global memory, one out-of-line copy.
 template <int D>
-__device__ __noinline__ double fir_tile_guarded(const FirPlan<D>& pl, const FirArgs& ar, const double* __restrict__ ys, long long slot, int nvalid,
-                                                bool pub, bool full, const double* __restrict__ splane, int lane) {
+__device__ __noinline__ double fir_tile_guarded(const FirPlan<D>& pl, const double* __restrict__ ys, int r, int nvalid, bool pub, bool full,
+                                                const double* __restrict__ splane, double* sring, int* stag, int lane) {
     double yv[kFirL];
 #pragma unroll
     for (int j = 0; j < kFirL; ++j) {
         const int e = lane * kFirL + j;
         yv[j] = e < nvalid ? __ldg(ys + e) : 0.0;
     }
-    return fir_tile_compute<D, true>(pl, ar, yv, slot, nvalid, pub, full, splane, lane);
+    return fir_tile_compute<D, true>(pl, yv, r, nvalid, pub, full, splane, sring, stag, lane);
 }
 
-// The transient: steps [0, N0) with the tabulated gains, one warp. Lane l owns a run of ceil(N0 / 32) steps: it composes the run's
-// affine map, a shuffle scan over (M, b) gives its start state, a second sweep forms the innovations. Publishes m_{N0-1} as the
-// word group of "tile -1" (zeros for the tiles before it) and returns sum_t v_t^2 / S_t in lane 0.
+// The transient: steps [0, N0) with the tabulated gains, the whole CTA. Thread i owns steps [i c, (i + 1) c), c = ceil(N0 / 512): it
+// composes their affine map (M, b); shuffle scan inside the warps, the 16 warp totals through shared memory; a second sweep from the
+// thread's start state forms the innovations. Publishes the filtered mean after step N0 - 1 as ring entry kFirNbMax - 1 (zeros before
+// it) and returns the CTA's sum of v_t^2 / S_t (valid in thread 0).
 template <int D>
-__device__ __noinline__ double fir_head(const FirPlan<D>& pl, const FirArgs& ar, int lane) {
+__device__ __noinline__ double fir_head(const FirPlan<D>& pl, const FirArgs& ar, double* sscan, double* sred, double* sring, int* stag) {
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const long long N0 = pl.N0;
-    const long long c = (N0 + 31) / 32;
-    const long long t0 = min((long long)lane * c, N0), t1 = min(t0 + c, N0);
+    const long long c = (N0 + kFirThreads - 1) / kFirThreads;
+    const long long t0 = min((long long)tid * c, N0), t1 = min(t0 + c, N0);
     Mat<D> A;
     Vec<D> a, w;
 #pragma unroll
@@ -238,30 +250,49 @@ __device__ __noinline__ double fir_head(const FirPlan<D>& pl, const FirArgs& ar,
             M = matmul(M, Mu);
         }
     }
-    Vec<D> m0;
+    if (lane == 31) {       // the warp's map
+        double* e = sscan + wp * (D * D + D);
 #pragma unroll
-    for (int i = 0; i < D; ++i) m0[i] = pl.m0[i];
-    {   // lane 31's inclusive map covers [0, N0): the filtered mean after the transient enters tile 0
-        const Vec<D> t = matvec(M, m0);
-        if (lane == 31) {
+        for (int i = 0; i < D * D; ++i) e[i] = M.v[i];
 #pragma unroll
-            for (int i = 0; i < D; ++i) fir_put_word(ar.agg + (kFirNbMax - 1) * D + i, t[i] + b[i], ar.epoch);
-            for (int k = 2; k <= kFirNbMax; ++k)
-#pragma unroll
-                for (int i = 0; i < D; ++i) fir_put_word(ar.agg + (kFirNbMax - k) * D + i, 0.0, ar.epoch);
-        }
+        for (int i = 0; i < D; ++i) e[D * D + i] = b[i];
     }
-    Mat<D> Me;
-    Vec<D> be;
+    __syncthreads();
+    Vec<D> m;                // state entering the warp: the maps of the warps before it applied to m0
 #pragma unroll
-    for (int i = 0; i < D * D; ++i) Me.v[i] = __shfl_up_sync(0xffffffffu, M.v[i], 1);
+    for (int i = 0; i < D; ++i) m[i] = pl.m0[i];
+    for (int k = 0; k < wp; ++k) {
+        const double* e = sscan + k * (D * D + D);
+        Vec<D> mn;
 #pragma unroll
-    for (int i = 0; i < D; ++i) be[i] = __shfl_up_sync(0xffffffffu, b[i], 1);
-    Vec<D> m = m0;
-    if (lane > 0) {
-        const Vec<D> t = matvec(Me, m0);
+        for (int i = 0; i < D; ++i) {
+            double sacc = e[D * D + i];
 #pragma unroll
-        for (int i = 0; i < D; ++i) m[i] = t[i] + be[i];
+            for (int j = 0; j < D; ++j) sacc = fma(e[i + D * j], m[j], sacc);
+            mn[i] = sacc;
+        }
+        m = mn;
+    }
+    {   // exclusive map inside the warp
+        Mat<D> Me;
+        Vec<D> be;
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) Me.v[i] = __shfl_up_sync(0xffffffffu, M.v[i], 1);
+#pragma unroll
+        for (int i = 0; i < D; ++i) be[i] = __shfl_up_sync(0xffffffffu, b[i], 1);
+        if (tid == kFirThreads - 1) {   // the last thread's inclusive map closes the transient: the mean entering tile 0
+            const Vec<D> t = matvec(M, m);
+            Vec<D> mf, zero = vzero<D>();
+#pragma unroll
+            for (int i = 0; i < D; ++i) mf[i] = t[i] + b[i];
+            for (int k = 2; k <= kFirNbMax; ++k) fir_publish<D>(sring, stag, kFirNbMax - k, zero);
+            fir_publish<D>(sring, stag, kFirNbMax - 1, mf);
+        }
+        if (lane > 0) {
+            const Vec<D> t = matvec(Me, m);
+#pragma unroll
+            for (int i = 0; i < D; ++i) m[i] = t[i] + be[i];
+        }
     }
     double q = 0.0;
 #pragma unroll 1
@@ -278,88 +309,102 @@ __device__ __noinline__ double fir_head(const FirPlan<D>& pl, const FirArgs& ar,
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) q += __shfl_down_sync(0xffffffffu, q, off);
-    return q;
+    if (lane == 0) sred[wp] = q;
+    __syncthreads();
+    double tot = 0.0;
+    if (tid == 0)
+        for (int i = 0; i < kFirWarps; ++i) tot += sred[i];
+    __syncthreads();
+    return tot;
 }
 
 template <int D>
-__global__ void __launch_bounds__(kFirThreads, kFirCtasPerSm)
+__global__ void __launch_bounds__(kFirThreads, 1)
 k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirArgs ar) {
-    extern __shared__ __align__(16) double sbuf[];   // kFirWarps staging buffers
-    __shared__ double splane[D * D * 32];
-    __shared__ double sred[kFirWarps];
-    __shared__ unsigned s_vb;
+    using SM = FirSmem<D>;
+    extern __shared__ __align__(16) double smem[];
+    double* splane = smem + SM::o_plane;
+    double* sring = smem + SM::o_ring;
+    double* sred = smem + SM::o_red;
+    double* sscan = smem + SM::o_scan;
+    int* stag = reinterpret_cast<int*>(smem + SM::o_tag);
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    const unsigned G = gridDim.x;
-    if (tid == 0) s_vb = atomicAdd(ar.counters, 1u);
+    const long long G = gridDim.x, b = blockIdx.x;
     for (int i = tid; i < D * D * 32; i += kFirThreads) splane[i] = __ldg(ar.plane + i);
+    if (tid < kFirRing + kFirNbMax) stag[tid] = -1;
     __syncthreads();
-    const unsigned vb = s_vb;
     const double* __restrict__ ys = ar.y + pl.N0;
     const long long Ts = pl.T - pl.N0;
-    double q = 0.0;
-    if (vb == 0) {
-        // ---- service CTA: the transient (or, on a shard with rank > 0, pass A over the halo) and the halo push -------------
-        if (wp == 0) {
-            if (ar.x.halo == nullptr) {
-                const double qh = fir_head<D>(pl, ar, lane);
-                if (lane == 0) ar.partials[G] = qh;
-            } else {
-                if (ar.x.halo_flag) {
-                    if (lane == 0) {
-                        unsigned spins = 0;
-                        while (fir_ld_sys(ar.x.halo_flag) < ar.epoch) {
-                            if (++spins > (1u << 28)) __trap();
-                            __nanosleep(100);
-                        }
-                    }
-                    __syncwarp();
-                    __threadfence_system();
-                }
-                for (int k = pl.nb; k >= 1; --k)     // tile -k: its zero-state response goes to slot kFirNbMax - k
-                    fir_tile_guarded<D>(pl, ar, ar.x.halo + (size_t)(pl.nb - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, lane);
-                if (ar.x.ack_out && lane == 0) {
-                    __threadfence_system();
-                    *reinterpret_cast<volatile unsigned long long*>(ar.x.ack_out) = ar.epoch;
-                }
-                if (lane == 0) ar.partials[G] = 0.0;
-            }
-        } else if (wp == 1 && ar.x.push_dst) {
-            // the last nb tiles of this shard -> the successor's halo ring slot, then its flag
-            if (lane == 0 && ar.x.ack_in && ar.epoch > ar.x.ring) {
-                unsigned spins = 0;
-                while (fir_ld_sys(ar.x.ack_in) + ar.x.ring < ar.epoch) {
-                    if (++spins > (1u << 28)) __trap();
-                    __nanosleep(100);
-                }
-            }
-            __syncwarp();
-            const long long n = (long long)pl.nb * kFirTile;
-            const double* src = ar.y + pl.T - n;
-            for (long long e = lane; e < n; e += 32) ar.x.push_dst[e] = __ldg(src + e);
-            __threadfence_system();
-            __syncwarp();
-            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(ar.x.push_flag) = ar.epoch;
+    const long long ntiles = pl.ntiles;
+    const long long c0 = ntiles * b / G, c1 = ntiles * (b + 1) / G;    // this CTA's tiles
+    const bool exch_halo = b == 0 && ar.x.halo != nullptr;              // shard with rank > 0: what precedes tile 0 arrives over NVLink
+    // ---- what precedes the chunk --------------------------------------------------------------------------------------
+    if (b == 0 && !exch_halo) {
+        const double qh = fir_head<D>(pl, ar, sscan, sred, sring, stag);
+        if (tid == 0) ar.partials[G] = qh;
+    } else if (b > 0) {
+        if (wp >= kFirWarps - pl.nb) {       // the last warps: pass A over the nb tiles before the chunk (re-read from HBM)
+            const int k = kFirWarps - wp;    // tile c0 - k
+            fir_tile_guarded<D>(pl, ys + (c0 - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, sring, stag, lane);
         }
-    } else {
-        const long long NW = (long long)(G - 1) * kFirWarps;
-        const long long gw = (long long)(vb - 1) * kFirWarps + wp;
-        const long long ntiles = pl.ntiles;
-        const bool deferred = gw < pl.nb && gw < ntiles;   // this warp's first tile waits for the transient / halo: publish now, finish last
-        // items of this warp: [its deferred tile, pass A only] tiles first, first + NW, ... [the deferred tile, pass B]
-        const long long first = deferred ? gw + NW : gw;
-        const long long n_main = ntiles > first ? (ntiles - first + NW - 1) / NW : 0;
+    }
+    if (b == G - 1 && wp == kFirWarps - 1 && ar.x.push_dst) {
+        // the last nb tiles of this shard -> the successor's halo ring slot (NVLink stores), then its flag
+        if (lane == 0 && ar.x.ack_in && ar.epoch > ar.x.ring) {
+            unsigned spins = 0;
+            while (fir_ld_sys(ar.x.ack_in) + ar.x.ring < ar.epoch) {
+                if (++spins > (1u << 26)) __trap();
+                __nanosleep(100);
+            }
+        }
+        __syncwarp();
+        const long long n = (long long)pl.nb * kFirTile;
+        const double* src = ar.y + pl.T - n;
+        for (long long e = lane; e < n; e += 32) ar.x.push_dst[e] = __ldg(src + e);
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(ar.x.push_flag) = ar.epoch;
+    }
+    // ---- the chunk: warp wp takes tiles c0 + wp, c0 + wp + 16, ... ---------------------------------------------------------
+    double q = 0.0;
+    {
+        // On a shard with rank > 0 the first nb tiles of CTA 0 need the halo: their warps publish pass A now and run pass B last.
+        const bool deferred = exch_halo && wp < pl.nb && c0 + wp < c1;
+        const long long first = c0 + wp + (deferred ? kFirWarps : 0);
+        const long long n_main = c1 > first ? (c1 - first + kFirWarps - 1) / kFirWarps : 0;
         const long long it0 = deferred ? -1 : 0, it1 = n_main + (deferred ? 1 : 0);
-        double* buf = sbuf + wp * kFirBufDoubles;
+        double* buf = smem + wp * kFirBufDoubles;
         const unsigned long long pol = fir_policy_evict_first();
-        auto tile_of = [&](long long it) { return (it >= 0 && it < n_main) ? first + it * NW : gw; };
+        auto tile_of = [&](long long it) { return (it >= 0 && it < n_main) ? first + it * kFirWarps : c0 + wp; };
         auto staged = [&](long long it) { return it < it1 && pl.aligned && Ts - tile_of(it) * kFirTile >= kFirTile; };
         if (staged(it0)) fir_issue_tile(buf, ys + tile_of(it0) * kFirTile, lane, pol);
         fir_cp_commit();
         for (long long it = it0; it < it1; ++it) {
             const long long t = tile_of(it);
             const bool pub = it < n_main, full = it >= 0;
+            const int r = (int)(t - c0) + kFirNbMax;
             const long long s0 = t * kFirTile;
+            if (exch_halo && it == n_main && wp == 0) {
+                // the halo: wait for the predecessor's push, pass A over its nb tiles, tell the predecessor the slot is free
+                if (ar.x.halo_flag) {
+                    if (lane == 0) {
+                        unsigned spins = 0;
+                        while (fir_ld_sys(ar.x.halo_flag) < ar.epoch) {
+                            if (++spins > (1u << 26)) __trap();
+                            __nanosleep(100);
+                        }
+                    }
+                    __syncwarp();
+                    __threadfence_system();
+                }
+                for (int k = pl.nb; k >= 1; --k)
+                    fir_tile_guarded<D>(pl, ar.x.halo + (size_t)(pl.nb - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, sring, stag, lane);
+                if (ar.x.ack_out && lane == 0) {
+                    __threadfence_system();
+                    *reinterpret_cast<volatile unsigned long long*>(ar.x.ack_out) = ar.epoch;
+                }
+            }
             if (staged(it)) {
                 double yv[kFirL];
                 fir_cp_wait_all();
@@ -368,11 +413,13 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
                 __syncwarp();
                 if (staged(it + 1)) fir_issue_tile(buf, ys + tile_of(it + 1) * kFirTile, lane, pol);
                 fir_cp_commit();
-                q += fir_tile_compute<D, false>(pl, ar, yv, t + kFirNbMax, kFirTile, pub, full, splane, lane);
+                q += fir_tile_compute<D, false>(pl, yv, r, kFirTile, pub, full, splane, sring, stag, lane);
             } else {
+                fir_cp_wait_all();
+                __syncwarp();
                 if (staged(it + 1)) fir_issue_tile(buf, ys + tile_of(it + 1) * kFirTile, lane, pol);
                 fir_cp_commit();
-                q += fir_tile_guarded<D>(pl, ar, ys + s0, t + kFirNbMax, (int)min(Ts - s0, (long long)kFirTile), pub, full, splane, lane);
+                q += fir_tile_guarded<D>(pl, ys + s0, r, (int)min(Ts - s0, (long long)kFirTile), pub, full, splane, sring, stag, lane);
             }
         }
         fir_cp_wait_all();
@@ -380,21 +427,23 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     // ---- fixed-order reductions; the last CTA to finish forms the log-likelihood ------------------------------------------
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) q += __shfl_down_sync(0xffffffffu, q, off);
+    __syncthreads();
     if (lane == 0) sred[wp] = q;
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;
 #pragma unroll
         for (int i = 0; i < kFirWarps; ++i) t += sred[i];
-        __stcg(ar.partials + vb, vb == 0 ? 0.0 : t);
+        __stcg(ar.partials + b, t);
+        if (b == 0 && exch_halo) __stcg(ar.partials + G, 0.0);
         __threadfence();
-        s_last = atomicAdd(ar.counters + 1, 1u) == G - 1;
+        s_last = atomicAdd(ar.counters, 1u) == (unsigned)G - 1;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     double s = 0.0;
-    for (unsigned i = tid; i < G; i += kFirThreads) s += __ldcg(ar.partials + i);
+    for (long long i = tid; i < G; i += kFirThreads) s += __ldcg(ar.partials + i);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
     __syncthreads();
@@ -408,7 +457,6 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         *ar.result = lml;
         if (ar.lml_user) *ar.lml_user = lml;
         ar.counters[0] = 0u;
-        ar.counters[1] = 0u;
         if (ar.x.peers) {      // partial log-likelihood of this shard -> every rank's buffer, then the flags
             for (int p = 0; p < ar.x.world; ++p) *reinterpret_cast<volatile double*>(ar.x.peers[p] + ar.x.lml_off) = lml;
             __threadfence_system();
@@ -485,12 +533,7 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     memcpy(&pl, st.plan.data(), sizeof pl);
     // ---- workspace ---------------------------------------------------------------------------------------------------
     const long long ntiles = pl.ntiles;
-    const long long want_ctas = (ntiles + kFirWarps - 1) / kFirWarps;
-    const unsigned G = 1u + (unsigned)std::min<long long>(want_ctas, (long long)h->sm_count * kFirCtasPerSm - 1);
-    size_t agg_cap = st.agg_cap;
-    double2* agg = (double2*)st.agg;
-    TGP_TRY(fir_grow(h, &agg, &agg_cap, (size_t)(ntiles + kFirNbMax) * D * sizeof(double2), true));
-    st.agg = agg; st.agg_cap = agg_cap;
+    const unsigned G = (unsigned)std::max<long long>(1, std::min<long long>(h->sm_count, ntiles / 8));   // one 16-warp CTA per SM
     TGP_TRY(fir_grow(h, &st.partials, &st.partials_cap, (size_t)(G + 1) * sizeof(double), false));
     if (!st.counters) {
         TGP_CUDA(h, cudaMalloc((void**)&st.counters, 2 * sizeof(unsigned)));
@@ -501,7 +544,6 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     ar.y = dy;
     ar.tab = st.dev;
     ar.plane = st.dev + (size_t)pl.N0 * (D + 1);
-    ar.agg = agg;
     ar.epoch = ++st.epoch;
     ar.counters = st.counters;
     ar.partials = st.partials;
@@ -509,10 +551,10 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     ar.lml_user = (lml_out && is_device_ptr(lml_out)) ? lml_out : nullptr;
     if (xc) ar.x = *xc;
     TGP_K(h, "k_fir_logpdf");
-    constexpr size_t smem = (size_t)kFirWarps * kFirBufDoubles * sizeof(double);
+    constexpr size_t smem = FirSmem<D>::bytes;
     static bool attr_set[64] = {false};
-    if (!attr_set[h->device & 63]) {   // ask for the shared-memory carve-out that lets kFirCtasPerSm CTAs live on one SM
-        TGP_CUDA(h, cudaFuncSetAttribute(k_fir_logpdf<D>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    if (!attr_set[h->device & 63]) {
+        TGP_CUDA(h, cudaFuncSetAttribute(k_fir_logpdf<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[h->device & 63] = true;
     }
     k_fir_logpdf<D><<<G, kFirThreads, smem, h->stream>>>(pl, ar);

@@ -16,9 +16,6 @@ constexpr int kFirNBlk = 4;       // blocks per lane run
 constexpr int kFirL = kFirB * kFirNBlk;   // 32 steps per lane
 constexpr int kFirTile = 32 * kFirL;      // 1024 steps per warp tile
 constexpr int kFirNbMax = 3;      // look-back depth limit (tiles)
-constexpr int kFirThreads = 128;
-constexpr int kFirWarps = kFirThreads / 32;
-constexpr int kFirCtasPerSm = 4;
 constexpr int kFirMaxD = 4;        // instantiated for D <= 4 (larger states: the two-phase kernel / the vector scans)
 
 // Hot-loop constants: passed BY VALUE (kernel parameter space = constant bank, so every coefficient is a DFMA operand).
