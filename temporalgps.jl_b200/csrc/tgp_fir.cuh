@@ -27,6 +27,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -63,6 +65,7 @@ struct FirArgs {
     double* partials;             // gridDim.x per-CTA sums of v^2, [gridDim.x]: the transient's sum of v^2 / S_t
     double* result;               // lml of this shard (device)
     double* lml_user;             // caller's device destination, nullable
+    unsigned stagger_ns;          // initial delay between the four warp groups of a CTA (0: none)
     FirXchg x;
 };
 
@@ -132,25 +135,38 @@ __device__ __forceinline__ void fir_publish(double* sring, int* stag, int r, con
 }
 
 // One tile from the lane's 32 observations in registers. r: ring entry of the tile. nvalid: steps of the tile that exist (TAIL only).
-// pub: publish the zero-state response. full: take the carry and run pass B. Returns the lane's sum of v^2.
+// pub: publish the zero-state response. full: take the carry and run pass B. next: observations of this warp's next tile (or null):
+// its 16 cp.async per lane are spread over pass A instead of being issued back to back. Returns the lane's sum of v^2.
 template <int D, bool TAIL>
 __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double (&yv)[kFirL], int r, int nvalid, bool pub, bool full,
-                                                   const double* __restrict__ splane, double* sring, int* stag, int lane) {
-    // ---- pass A: zero-state response of the lane's run --------------------------------------------------------------
+                                                   const double* __restrict__ splane, double* sring, int* stag, int lane,
+                                                   double* buf = nullptr, const double* __restrict__ next = nullptr, unsigned long long pol = 0) {
+    // ---- pass A: zero-state response of the lane's run (+ the next tile's copies) -------------------------------------------
     Vec<D> u[kFirNBlk], z = vzero<D>();
-    fir_pass_a<D>(pl, yv, u, z);
-    // ---- warp scan: state at the end of every lane's run, the tile starting from zero -------------------------------------
+#pragma unroll
+    for (int b = 0; b < kFirNBlk; ++b) {
+        fir_pass_a_block<D>(pl, b, yv, u[b], z);
+        if (!TAIL && next) {
+#pragma unroll
+            for (int k = b * (kFirL / 2 / kFirNBlk); k < (b + 1) * (kFirL / 2 / kFirNBlk); ++k) {
+                const int c = k * 32 + lane;
+                fir_cp16(buf + (c >> 4) * kFirRow + (c & 15) * 2, next + 2 * c, pol);
+            }
+        }
+    }
+    if (!TAIL) fir_cp_commit();
+    // ---- warp scan (state at the end of every lane's run, the tile starting from zero), with the data-only half of pass B
+    // (y_j <- y_j - kap_j - sum_{i<j} g y_i) filling the shuffle latencies --------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const Vec<D> zu = fir_shfl_up(z, 1 << k);
+        if (full && k < kFirNBlk) fir_pass_b1_block<D>(pl, k, yv);
         if (lane >= (1 << k)) z = fir_scan_level<D>(pl, k, z, zu);
     }
     if (pub && lane == 31) fir_publish<D>(sring, stag, r, z);
     if (!full) return 0.0;
     Vec<D> m = fir_shfl_up(z, 1);
     if (lane == 0) m = vzero<D>();
-    // ---- pass B, data-only half (the neighbours publish meanwhile) ----------------------------------------------------------
-    fir_pass_b1<D>(pl, yv);
     // ---- carry: state entering the tile from the nb entries before it ----------------------------------------------------
     if (lane < pl.nb) {
         const int want = r - 1 - lane;
@@ -331,14 +347,34 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const long long G = gridDim.x, b = blockIdx.x;
-    for (int i = tid; i < D * D * 32; i += kFirThreads) splane[i] = __ldg(ar.plane + i);
-    if (tid < kFirRing + kFirNbMax) stag[tid] = -1;
-    __syncthreads();
     const double* __restrict__ ys = ar.y + pl.N0;
     const long long Ts = pl.T - pl.N0;
     const long long ntiles = pl.ntiles;
-    const long long c0 = ntiles * b / G, c1 = ntiles * (b + 1) / G;    // this CTA's tiles
+    // This CTA's tiles [c0, c1): equal chunks, except that CTA 0 (which also runs the transient) takes one round less.
+    long long c0, c1;
+    {
+        const long long base = ntiles / G;
+        const long long t0 = (G > 1 && base >= 3 * kFirWarps) ? base - kFirWarps : base;     // tiles of CTA 0
+        const long long rest = ntiles - t0;
+        c0 = b == 0 ? 0 : t0 + (G > 1 ? rest * (b - 1) / (G - 1) : 0);
+        c1 = b == 0 ? (G > 1 ? t0 : ntiles) : t0 + rest * b / (G - 1);
+    }
     const bool exch_halo = b == 0 && ar.x.halo != nullptr;              // shard with rank > 0: what precedes tile 0 arrives over NVLink
+    // On a shard with rank > 0 the first nb tiles of CTA 0 need the halo: their warps publish pass A now and run pass B last.
+    const bool deferred = exch_halo && wp < pl.nb && c0 + wp < c1;
+    const long long first = c0 + wp + (deferred ? kFirWarps : 0);       // this warp: tiles first, first + 16, ... < c1
+    int n_main = c1 > first ? (int)((c1 - first + kFirWarps - 1) / kFirWarps) : 0;
+    // all of them are full tiles except, possibly, the very last tile of the series
+    const bool last_partial = n_main > 0 && (first + (long long)(n_main - 1) * kFirWarps + 1) * kFirTile > Ts;
+    const int n_fast = pl.aligned ? n_main - (last_partial ? 1 : 0) : 0;
+    double* buf = smem + wp * kFirBufDoubles;
+    const unsigned long long pol = fir_policy_evict_first();
+    const double* __restrict__ yt = ys + first * kFirTile;              // current tile of the fast loop
+    if (n_fast > 0) fir_issue_tile(buf, yt, lane, pol);                 // first tile on its way before anything else
+    fir_cp_commit();
+    for (int i = tid; i < D * D * 32; i += kFirThreads) splane[i] = __ldg(ar.plane + i);
+    if (tid < kFirRing + kFirNbMax) stag[tid] = -1;
+    __syncthreads();
     // ---- what precedes the chunk --------------------------------------------------------------------------------------
     if (b == 0 && !exch_halo) {
         const double qh = fir_head<D>(pl, ar, sscan, sred, sring, stag);
@@ -366,64 +402,55 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         __syncwarp();
         if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(ar.x.push_flag) = ar.epoch;
     }
-    // ---- the chunk: warp wp takes tiles c0 + wp, c0 + wp + 16, ... ---------------------------------------------------------
+    if (ar.stagger_ns && (wp >> 2)) __nanosleep((unsigned)(wp >> 2) * ar.stagger_ns);   // de-phase the 4 warps of each scheduler
+    // ---- the chunk --------------------------------------------------------------------------------------------------------
     double q = 0.0;
-    {
-        // On a shard with rank > 0 the first nb tiles of CTA 0 need the halo: their warps publish pass A now and run pass B last.
-        const bool deferred = exch_halo && wp < pl.nb && c0 + wp < c1;
-        const long long first = c0 + wp + (deferred ? kFirWarps : 0);
-        const long long n_main = c1 > first ? (c1 - first + kFirWarps - 1) / kFirWarps : 0;
-        const long long it0 = deferred ? -1 : 0, it1 = n_main + (deferred ? 1 : 0);
-        double* buf = smem + wp * kFirBufDoubles;
-        const unsigned long long pol = fir_policy_evict_first();
-        auto tile_of = [&](long long it) { return (it >= 0 && it < n_main) ? first + it * kFirWarps : c0 + wp; };
-        auto staged = [&](long long it) { return it < it1 && pl.aligned && Ts - tile_of(it) * kFirTile >= kFirTile; };
-        if (staged(it0)) fir_issue_tile(buf, ys + tile_of(it0) * kFirTile, lane, pol);
-        fir_cp_commit();
-        for (long long it = it0; it < it1; ++it) {
-            const long long t = tile_of(it);
-            const bool pub = it < n_main, full = it >= 0;
-            const int r = (int)(t - c0) + kFirNbMax;
-            const long long s0 = t * kFirTile;
-            if (exch_halo && it == n_main && wp == 0) {
-                // the halo: wait for the predecessor's push, pass A over its nb tiles, tell the predecessor the slot is free
-                if (ar.x.halo_flag) {
-                    if (lane == 0) {
-                        unsigned spins = 0;
-                        while (fir_ld_sys(ar.x.halo_flag) < ar.epoch) {
-                            if (++spins > (1u << 26)) __trap();
-                            __nanosleep(100);
-                        }
-                    }
-                    __syncwarp();
-                    __threadfence_system();
-                }
-                for (int k = pl.nb; k >= 1; --k)
-                    fir_tile_guarded<D>(pl, ar.x.halo + (size_t)(pl.nb - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, sring, stag, lane);
-                if (ar.x.ack_out && lane == 0) {
-                    __threadfence_system();
-                    *reinterpret_cast<volatile unsigned long long*>(ar.x.ack_out) = ar.epoch;
-                }
-            }
-            if (staged(it)) {
-                double yv[kFirL];
-                fir_cp_wait_all();
-                __syncwarp();
-                fir_read_tile(buf, lane, yv);
-                __syncwarp();
-                if (staged(it + 1)) fir_issue_tile(buf, ys + tile_of(it + 1) * kFirTile, lane, pol);
-                fir_cp_commit();
-                q += fir_tile_compute<D, false>(pl, yv, r, kFirTile, pub, full, splane, sring, stag, lane);
-            } else {
-                fir_cp_wait_all();
-                __syncwarp();
-                if (staged(it + 1)) fir_issue_tile(buf, ys + tile_of(it + 1) * kFirTile, lane, pol);
-                fir_cp_commit();
-                q += fir_tile_guarded<D>(pl, ys + s0, r, (int)min(Ts - s0, (long long)kFirTile), pub, full, splane, sring, stag, lane);
-            }
-        }
+    int r = (int)(first - c0) + kFirNbMax;
+    if (deferred)
+        fir_tile_guarded<D>(pl, ys + (c0 + wp) * kFirTile, wp + kFirNbMax, (int)min(Ts - (c0 + wp) * kFirTile, (long long)kFirTile), true, false,
+                            splane, sring, stag, lane);
+#pragma unroll 1
+    for (int it = 0; it < n_fast; ++it) {
+        double yv[kFirL];
         fir_cp_wait_all();
+        __syncwarp();
+        fir_read_tile(buf, lane, yv);
+        __syncwarp();
+        const double* __restrict__ next = it + 1 < n_fast ? yt + kFirWarps * kFirTile : nullptr;
+        q += fir_tile_compute<D, false>(pl, yv, r, kFirTile, true, true, splane, sring, stag, lane, buf, next, pol);
+        yt += kFirWarps * kFirTile;
+        r += kFirWarps;
     }
+#pragma unroll 1
+    for (int it = n_fast; it < n_main; ++it) {      // unaligned series (all tiles) or the partial last tile
+        const long long s0 = (first + (long long)it * kFirWarps) * kFirTile;
+        q += fir_tile_guarded<D>(pl, ys + s0, (int)(first - c0) + it * kFirWarps + kFirNbMax, (int)min(Ts - s0, (long long)kFirTile), true, true,
+                                 splane, sring, stag, lane);
+    }
+    if (exch_halo && wp == 0) {
+        // the halo: wait for the predecessor's push, pass A over its nb tiles, tell the predecessor the slot is free
+        if (ar.x.halo_flag) {
+            if (lane == 0) {
+                unsigned spins = 0;
+                while (fir_ld_sys(ar.x.halo_flag) < ar.epoch) {
+                    if (++spins > (1u << 26)) __trap();
+                    __nanosleep(100);
+                }
+            }
+            __syncwarp();
+            __threadfence_system();
+        }
+        for (int k = pl.nb; k >= 1; --k)
+            fir_tile_guarded<D>(pl, ar.x.halo + (size_t)(pl.nb - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, sring, stag, lane);
+        if (ar.x.ack_out && lane == 0) {
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(ar.x.ack_out) = ar.epoch;
+        }
+    }
+    if (deferred)
+        q += fir_tile_guarded<D>(pl, ys + (c0 + wp) * kFirTile, wp + kFirNbMax, (int)min(Ts - (c0 + wp) * kFirTile, (long long)kFirTile), false, true,
+                                 splane, sring, stag, lane);
+    fir_cp_wait_all();
     // ---- fixed-order reductions; the last CTA to finish forms the log-likelihood ------------------------------------------
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) q += __shfl_down_sync(0xffffffffu, q, off);
@@ -550,6 +577,11 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     ar.result = st.result;
     ar.lml_user = (lml_out && is_device_ptr(lml_out)) ? lml_out : nullptr;
     if (xc) ar.x = *xc;
+    {
+        static int stagger = -1;
+        if (stagger < 0) { const char* e = getenv("TGP_FIR_STAGGER"); stagger = e ? atoi(e) : 0; }
+        ar.stagger_ns = (unsigned)stagger;
+    }
     TGP_K(h, "k_fir_logpdf");
     constexpr size_t smem = FirSmem<D>::bytes;
     static bool attr_set[64] = {false};
