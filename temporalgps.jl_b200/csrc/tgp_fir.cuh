@@ -72,11 +72,10 @@ struct FirArgs {
 template <int D>
 struct FirSmem {
     static constexpr int o_plane = kFirWarps * kFirBufDoubles;
-    static constexpr int o_ring = o_plane + D * D * 32;
-    static constexpr int o_red = o_ring + (kFirRing + kFirNbMax) * D;
+    static constexpr int o_ring = o_plane + D * D * 32 + ((D * D * 32) & 1);   // 16-byte words {value, tag}
+    static constexpr int o_red = o_ring + 2 * (kFirRing + kFirNbMax) * D;
     static constexpr int o_scan = o_red + kFirWarps + 2;                 // transient: per-warp affine maps (D*D + D each)
-    static constexpr int o_tag = o_scan + kFirWarps * (D * D + D);       // kFirRing + kFirNbMax ints
-    static constexpr size_t bytes = (size_t)o_tag * sizeof(double) + (kFirRing + kFirNbMax) * sizeof(int);
+    static constexpr size_t bytes = (size_t)(o_scan + kFirWarps * (D * D + D)) * sizeof(double);
 };
 
 __device__ __forceinline__ unsigned long long fir_policy_evict_first() {
@@ -123,15 +122,25 @@ template <int D> __device__ __forceinline__ Vec<D> fir_shfl_up(const Vec<D>& v, 
 
 // The shared-memory ring of tile words: entry r (= tile index relative to the chunk + kFirNbMax) holds the zero-state response of
 // that tile (or, for r < kFirNbMax, what precedes the chunk); tag[r % kFirRing] == r once it is there.
-// Entries r < kFirNbMax (what precedes the chunk) have fixed slots; the tiles of the chunk share the ring.
+// Entries r < kFirNbMax (what precedes the chunk) have fixed slots; the tiles of the chunk share the ring. An entry is D 16-byte words
+// {value, tag = r}: one 128-bit shared-memory store per word, so a reader that sees the tag sees the value — no fence (a fence here
+// would also wait for the warp's cp.async copies in flight).
 __device__ __forceinline__ int fir_slot(int r) { return r < kFirNbMax ? r : kFirNbMax + ((r - kFirNbMax) % kFirRing); }
+__device__ __forceinline__ void fir_st_word(double2* p, double v, int tag) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"(sa), "d"(v), "d"(__longlong_as_double((long long)tag)) : "memory");
+}
+__device__ __forceinline__ void fir_ld_word(const double2* p, double& v, int& tag) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
+    double t;
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "r"(sa) : "memory");
+    tag = (int)__double_as_longlong(t);
+}
 template <int D>
-__device__ __forceinline__ void fir_publish(double* sring, int* stag, int r, const Vec<D>& z) {
-    volatile double* p = sring + fir_slot(r) * D;
+__device__ __forceinline__ void fir_publish(double2* sring, int r, const Vec<D>& z) {
+    double2* p = sring + fir_slot(r) * D;
 #pragma unroll
-    for (int i = 0; i < D; ++i) p[i] = z[i];
-    __threadfence_block();
-    *reinterpret_cast<volatile int*>(stag + fir_slot(r)) = r;
+    for (int i = 0; i < D; ++i) fir_st_word(p + i, z[i], r);
 }
 
 // One tile from the lane's 32 observations in registers. r: ring entry of the tile. nvalid: steps of the tile that exist (TAIL only).
@@ -139,7 +148,7 @@ __device__ __forceinline__ void fir_publish(double* sring, int* stag, int r, con
 // its 16 cp.async per lane are spread over pass A instead of being issued back to back. Returns the lane's sum of v^2.
 template <int D, bool TAIL>
 __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double (&yv)[kFirL], int r, int nvalid, bool pub, bool full,
-                                                   const double* __restrict__ splane, double* sring, int* stag, int lane,
+                                                   const double* __restrict__ splane, double2* sring, int lane,
                                                    double* buf = nullptr, const double* __restrict__ next = nullptr, unsigned long long pol = 0) {
     // ---- pass A: zero-state response of the lane's run (+ the next tile's copies) -------------------------------------------
     Vec<D> u[kFirNBlk], z = vzero<D>();
@@ -163,16 +172,20 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double 
         if (full && k < kFirNBlk) fir_pass_b1_block<D>(pl, k, yv);
         if (lane >= (1 << k)) z = fir_scan_level<D>(pl, k, z, zu);
     }
-    if (pub && lane == 31) fir_publish<D>(sring, stag, r, z);
+    if (pub && lane == 31) fir_publish<D>(sring, r, z);
     if (!full) return 0.0;
     Vec<D> m = fir_shfl_up(z, 1);
     if (lane == 0) m = vzero<D>();
-    // ---- carry: state entering the tile from the nb entries before it ----------------------------------------------------
-    if (lane < pl.nb) {
-        const int want = r - 1 - lane;
-        const volatile int* tg = stag + fir_slot(want);
+    // ---- carry: state entering the tile from the nb entries before it (lane k D + i fetches component i of entry r - 1 - k) ---------
+    double val = 0.0;
+    if (lane < pl.nb * D) {
+        const int want = r - 1 - lane / D;
+        const double2* wptr = sring + fir_slot(want) * D + lane % D;
+        int tag;
         unsigned spins = 0;
-        while (*tg != want) {
+        for (;;) {
+            fir_ld_word(wptr, val, tag);
+            if (tag == want) break;
             if (++spins > (1u << 26)) __trap();        // cannot happen short of a lost peer rank (halo): fail loudly, do not hang
             __nanosleep(20);
         }
@@ -180,14 +193,12 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double 
     __syncwarp();
     {
         Vec<D> c;
-        const volatile double* e = sring + fir_slot(r - 1) * D;
 #pragma unroll
-        for (int i = 0; i < D; ++i) c[i] = e[i];
+        for (int i = 0; i < D; ++i) c[i] = __shfl_sync(0xffffffffu, val, i);
         for (int k = 1; k < pl.nb; ++k) {
             Vec<D> tk;
-            const volatile double* ek = sring + fir_slot(r - 1 - k) * D;
 #pragma unroll
-            for (int i = 0; i < D; ++i) tk[i] = ek[i];
+            for (int i = 0; i < D; ++i) tk[i] = __shfl_sync(0xffffffffu, val, k * D + i);
             fir_carry_add<D>(pl, k, tk, c);
         }
 #pragma unroll
@@ -202,14 +213,14 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double 
 // Partial / unaligned / halo tiles: guarded scalar loads straight from global memory, one out-of-line copy.
 template <int D>
 __device__ __noinline__ double fir_tile_guarded(const FirPlan<D>& pl, const double* __restrict__ ys, int r, int nvalid, bool pub, bool full,
-                                                const double* __restrict__ splane, double* sring, int* stag, int lane) {
+                                                const double* __restrict__ splane, double2* sring, int lane) {
     double yv[kFirL];
 #pragma unroll
     for (int j = 0; j < kFirL; ++j) {
         const int e = lane * kFirL + j;
         yv[j] = e < nvalid ? __ldg(ys + e) : 0.0;
     }
-    return fir_tile_compute<D, true>(pl, yv, r, nvalid, pub, full, splane, sring, stag, lane);
+    return fir_tile_compute<D, true>(pl, yv, r, nvalid, pub, full, splane, sring, lane);
 }
 
 // The transient: steps [0, N0) with the tabulated gains, the whole CTA. Thread i owns steps [i c, (i + 1) c), c = ceil(N0 / 512): it
@@ -217,7 +228,7 @@ __device__ __noinline__ double fir_tile_guarded(const FirPlan<D>& pl, const doub
 // thread's start state forms the innovations. Publishes the filtered mean after step N0 - 1 as ring entry kFirNbMax - 1 (zeros before
 // it) and returns the CTA's sum of v_t^2 / S_t (valid in thread 0).
 template <int D>
-__device__ __noinline__ double fir_head(const FirPlan<D>& pl, const FirArgs& ar, double* sscan, double* sred, double* sring, int* stag) {
+__device__ __noinline__ double fir_head(const FirPlan<D>& pl, const FirArgs& ar, double* sscan, double* sred, double2* sring) {
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const long long N0 = pl.N0;
     const long long c = (N0 + kFirThreads - 1) / kFirThreads;
@@ -301,8 +312,8 @@ __device__ __noinline__ double fir_head(const FirPlan<D>& pl, const FirArgs& ar,
             Vec<D> mf, zero = vzero<D>();
 #pragma unroll
             for (int i = 0; i < D; ++i) mf[i] = t[i] + b[i];
-            for (int k = 2; k <= kFirNbMax; ++k) fir_publish<D>(sring, stag, kFirNbMax - k, zero);
-            fir_publish<D>(sring, stag, kFirNbMax - 1, mf);
+            for (int k = 2; k <= kFirNbMax; ++k) fir_publish<D>(sring, kFirNbMax - k, zero);
+            fir_publish<D>(sring, kFirNbMax - 1, mf);
         }
         if (lane > 0) {
             const Vec<D> t = matvec(Me, m);
@@ -340,10 +351,9 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     using SM = FirSmem<D>;
     extern __shared__ __align__(16) double smem[];
     double* splane = smem + SM::o_plane;
-    double* sring = smem + SM::o_ring;
+    double2* sring = reinterpret_cast<double2*>(smem + SM::o_ring);
     double* sred = smem + SM::o_red;
     double* sscan = smem + SM::o_scan;
-    int* stag = reinterpret_cast<int*>(smem + SM::o_tag);
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const long long G = gridDim.x, b = blockIdx.x;
@@ -370,19 +380,30 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     double* buf = smem + wp * kFirBufDoubles;
     const unsigned long long pol = fir_policy_evict_first();
     const double* __restrict__ yt = ys + first * kFirTile;              // current tile of the fast loop
-    if (n_fast > 0) fir_issue_tile(buf, yt, lane, pol);                 // first tile on its way before anything else
+    // CTAs b > 0: the last nb warps (they have a tile less than warps 0, 1 when the chunk is not a multiple of 16) first run pass A
+    // over the nb tiles BEFORE the chunk (re-read from HBM) — staged like any other tile, and first in the queue.
+    const int halo_k = (b > 0 && wp >= kFirWarps - pl.nb) ? kFirWarps - wp : 0;      // tile c0 - halo_k
+    const bool halo_fast = halo_k > 0 && pl.aligned;
+    if (halo_fast) fir_issue_tile(buf, ys + (c0 - halo_k) * kFirTile, lane, pol);
+    else if (n_fast > 0) fir_issue_tile(buf, yt, lane, pol);            // first tile on its way before anything else
     fir_cp_commit();
     for (int i = tid; i < D * D * 32; i += kFirThreads) splane[i] = __ldg(ar.plane + i);
-    if (tid < kFirRing + kFirNbMax) stag[tid] = -1;
+    for (int i = tid; i < (kFirRing + kFirNbMax) * D; i += kFirThreads) fir_st_word(sring + i, 0.0, -1);
     __syncthreads();
     // ---- what precedes the chunk --------------------------------------------------------------------------------------
     if (b == 0 && !exch_halo) {
-        const double qh = fir_head<D>(pl, ar, sscan, sred, sring, stag);
+        const double qh = fir_head<D>(pl, ar, sscan, sred, sring);
         if (tid == 0) ar.partials[G] = qh;
-    } else if (b > 0) {
-        if (wp >= kFirWarps - pl.nb) {       // the last warps: pass A over the nb tiles before the chunk (re-read from HBM)
-            const int k = kFirWarps - wp;    // tile c0 - k
-            fir_tile_guarded<D>(pl, ys + (c0 - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, sring, stag, lane);
+    } else if (halo_k > 0) {
+        if (halo_fast) {
+            double yv[kFirL];
+            fir_cp_wait_all();
+            __syncwarp();
+            fir_read_tile(buf, lane, yv);
+            __syncwarp();
+            fir_tile_compute<D, false>(pl, yv, kFirNbMax - halo_k, kFirTile, true, false, splane, sring, lane, buf, n_fast > 0 ? yt : nullptr, pol);
+        } else {
+            fir_tile_guarded<D>(pl, ys + (c0 - halo_k) * kFirTile, kFirNbMax - halo_k, kFirTile, true, false, splane, sring, lane);
         }
     }
     if (b == G - 1 && wp == kFirWarps - 1 && ar.x.push_dst) {
@@ -408,7 +429,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     int r = (int)(first - c0) + kFirNbMax;
     if (deferred)
         fir_tile_guarded<D>(pl, ys + (c0 + wp) * kFirTile, wp + kFirNbMax, (int)min(Ts - (c0 + wp) * kFirTile, (long long)kFirTile), true, false,
-                            splane, sring, stag, lane);
+                            splane, sring, lane);
 #pragma unroll 1
     for (int it = 0; it < n_fast; ++it) {
         double yv[kFirL];
@@ -417,7 +438,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         fir_read_tile(buf, lane, yv);
         __syncwarp();
         const double* __restrict__ next = it + 1 < n_fast ? yt + kFirWarps * kFirTile : nullptr;
-        q += fir_tile_compute<D, false>(pl, yv, r, kFirTile, true, true, splane, sring, stag, lane, buf, next, pol);
+        q += fir_tile_compute<D, false>(pl, yv, r, kFirTile, true, true, splane, sring, lane, buf, next, pol);
         yt += kFirWarps * kFirTile;
         r += kFirWarps;
     }
@@ -425,7 +446,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     for (int it = n_fast; it < n_main; ++it) {      // unaligned series (all tiles) or the partial last tile
         const long long s0 = (first + (long long)it * kFirWarps) * kFirTile;
         q += fir_tile_guarded<D>(pl, ys + s0, (int)(first - c0) + it * kFirWarps + kFirNbMax, (int)min(Ts - s0, (long long)kFirTile), true, true,
-                                 splane, sring, stag, lane);
+                                 splane, sring, lane);
     }
     if (exch_halo && wp == 0) {
         // the halo: wait for the predecessor's push, pass A over its nb tiles, tell the predecessor the slot is free
@@ -441,7 +462,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
             __threadfence_system();
         }
         for (int k = pl.nb; k >= 1; --k)
-            fir_tile_guarded<D>(pl, ar.x.halo + (size_t)(pl.nb - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, sring, stag, lane);
+            fir_tile_guarded<D>(pl, ar.x.halo + (size_t)(pl.nb - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, sring, lane);
         if (ar.x.ack_out && lane == 0) {
             __threadfence_system();
             *reinterpret_cast<volatile unsigned long long*>(ar.x.ack_out) = ar.epoch;
@@ -449,7 +470,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     }
     if (deferred)
         q += fir_tile_guarded<D>(pl, ys + (c0 + wp) * kFirTile, wp + kFirNbMax, (int)min(Ts - (c0 + wp) * kFirTile, (long long)kFirTile), false, true,
-                                 splane, sring, stag, lane);
+                                 splane, sring, lane);
     fir_cp_wait_all();
     // ---- fixed-order reductions; the last CTA to finish forms the log-likelihood ------------------------------------------
 #pragma unroll
