@@ -97,11 +97,11 @@ __device__ __forceinline__ void fir_cp16(double* smem_dst, const double* g, unsi
 // Staging of a full, aligned tile: coalesced 16-byte cp.async into 32 padded rows (one row = one lane's run; 34 doubles apart, so
 // the lanes' 128-bit reads are conflict-free).
 __device__ __forceinline__ void fir_issue_tile(double* buf, const double* __restrict__ ys, int lane, unsigned long long pol) {
+    // 16-byte chunk c = 32 k + lane (consecutive lanes, consecutive addresses) -> row c >> 4, column chunk c & 15
+    double* dst = buf + (lane >> 4) * kFirRow + (lane & 15) * 2;
+    const double* src = ys + 2 * lane;
 #pragma unroll
-    for (int k = 0; k < kFirL / 2; ++k) {
-        const int c = k * 32 + lane;                  // 16-byte chunk of the tile: consecutive lanes, consecutive addresses
-        fir_cp16(buf + (c >> 4) * kFirRow + (c & 15) * 2, ys + 2 * c, pol);
-    }
+    for (int k = 0; k < kFirL / 2; ++k) fir_cp16(dst + k * 2 * kFirRow, src + 64 * k, pol);
 }
 __device__ __forceinline__ void fir_read_tile(const double* buf, int lane, double (&yv)[kFirL]) {
     const double2* row = reinterpret_cast<const double2*>(buf + lane * kFirRow);
@@ -146,7 +146,7 @@ __device__ __forceinline__ void fir_publish(double2* sring, int r, const Vec<D>&
 // One tile from the lane's 32 observations in registers. r: ring entry of the tile. nvalid: steps of the tile that exist (TAIL only).
 // pub: publish the zero-state response. full: take the carry and run pass B. next: observations of this warp's next tile (or null):
 // its 16 cp.async per lane are spread over pass A instead of being issued back to back. Returns the lane's sum of v^2.
-template <int D, bool TAIL>
+template <int D, bool TAIL, bool ZM = false>
 __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double (&yv)[kFirL], int r, int nvalid, bool pub, bool full,
                                                    const double* __restrict__ splane, double2* sring, int lane,
                                                    double* buf = nullptr, const double* __restrict__ next = nullptr, unsigned long long pol = 0) {
@@ -154,13 +154,12 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double 
     Vec<D> u[kFirNBlk], z = vzero<D>();
 #pragma unroll
     for (int b = 0; b < kFirNBlk; ++b) {
-        fir_pass_a_block<D>(pl, b, yv, u[b], z);
-        if (!TAIL && next) {
+        fir_pass_a_block<D, ZM>(pl, b, yv, u[b], z);
+        if (!TAIL && next) {      // chunk c = 32 k + lane: row 2 k + (lane >> 4), column chunk lane & 15 -> one base + constants
+            double* dst = buf + (lane >> 4) * kFirRow + (lane & 15) * 2;
+            const double* src = next + 2 * lane;
 #pragma unroll
-            for (int k = b * (kFirL / 2 / kFirNBlk); k < (b + 1) * (kFirL / 2 / kFirNBlk); ++k) {
-                const int c = k * 32 + lane;
-                fir_cp16(buf + (c >> 4) * kFirRow + (c & 15) * 2, next + 2 * c, pol);
-            }
+            for (int k = b * (kFirL / 2 / kFirNBlk); k < (b + 1) * (kFirL / 2 / kFirNBlk); ++k) fir_cp16(dst + k * 2 * kFirRow, src + 64 * k, pol);
         }
     }
     if (!TAIL) fir_cp_commit();
@@ -168,9 +167,11 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double 
     // (y_j <- y_j - kap_j - sum_{i<j} g y_i) filling the shuffle latencies --------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        const Vec<D> zu = fir_shfl_up(z, 1 << k);
-        if (full && k < kFirNBlk) fir_pass_b1_block<D>(pl, k, yv);
-        if (lane >= (1 << k)) z = fir_scan_level<D>(pl, k, z, zu);
+        Vec<D> zu = fir_shfl_up(z, 1 << k);
+        if (full && k < kFirNBlk) fir_pass_b1_block<D, ZM>(pl, k, yv);
+#pragma unroll
+        for (int i = 0; i < D; ++i) zu[i] = lane >= (1 << k) ? zu[i] : 0.0;      // branch-free: lanes without a partner add zero
+        z = fir_scan_level<D>(pl, k, z, zu);
     }
     if (pub && lane == 31) fir_publish<D>(sring, r, z);
     if (!full) return 0.0;
@@ -357,6 +358,9 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const long long G = gridDim.x, b = blockIdx.x;
+    // Programmatic dependent launch: the next call's CTAs may take an SM as soon as this call's CTA leaves it (the calls share
+    // nothing: counters / partials / result alternate by call parity).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const double* __restrict__ ys = ar.y + pl.N0;
     const long long Ts = pl.T - pl.N0;
     const long long ntiles = pl.ntiles;
@@ -438,7 +442,8 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         fir_read_tile(buf, lane, yv);
         __syncwarp();
         const double* __restrict__ next = it + 1 < n_fast ? yt + kFirWarps * kFirTile : nullptr;
-        q += fir_tile_compute<D, false>(pl, yv, r, kFirTile, true, true, splane, sring, lane, buf, next, pol);
+        q += pl.zero_mean ? fir_tile_compute<D, false, true>(pl, yv, r, kFirTile, true, true, splane, sring, lane, buf, next, pol)
+                          : fir_tile_compute<D, false, false>(pl, yv, r, kFirTile, true, true, splane, sring, lane, buf, next, pol);
         yt += kFirWarps * kFirTile;
         r += kFirWarps;
     }
@@ -582,27 +587,29 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     // ---- workspace ---------------------------------------------------------------------------------------------------
     const long long ntiles = pl.ntiles;
     const unsigned G = (unsigned)std::max<long long>(1, std::min<long long>(h->sm_count, ntiles / 8));   // one 16-warp CTA per SM
-    TGP_TRY(fir_grow(h, &st.partials, &st.partials_cap, (size_t)(G + 1) * sizeof(double), false));
+    // counters / partials / result alternate with the parity of the call, so two consecutive calls may overlap (PDL)
+    const size_t pstride = ((size_t)h->sm_count + 8) & ~size_t(7);
+    TGP_TRY(fir_grow(h, &st.partials, &st.partials_cap, 2 * pstride * sizeof(double), false));
     if (!st.counters) {
-        TGP_CUDA(h, cudaMalloc((void**)&st.counters, 2 * sizeof(unsigned)));
-        TGP_CUDA(h, cudaMemsetAsync(st.counters, 0, 2 * sizeof(unsigned), h->stream));
-        TGP_CUDA(h, cudaMalloc((void**)&st.result, 4 * sizeof(double)));
+        TGP_CUDA(h, cudaMalloc((void**)&st.counters, 64 * sizeof(unsigned)));
+        TGP_CUDA(h, cudaMemsetAsync(st.counters, 0, 64 * sizeof(unsigned), h->stream));
+        TGP_CUDA(h, cudaMalloc((void**)&st.result, 8 * sizeof(double)));
     }
     FirArgs ar{};
     ar.y = dy;
     ar.tab = st.dev;
     ar.plane = st.dev + (size_t)pl.N0 * (D + 1);
     ar.epoch = ++st.epoch;
-    ar.counters = st.counters;
-    ar.partials = st.partials;
-    ar.result = st.result;
+    const int par = (int)(ar.epoch & 1ull);
+    ar.counters = st.counters + 32 * par;
+    ar.partials = st.partials + pstride * par;
+    ar.result = st.result + 4 * par;
     ar.lml_user = (lml_out && is_device_ptr(lml_out)) ? lml_out : nullptr;
     if (xc) ar.x = *xc;
-    {
-        static int stagger = -1;
-        if (stagger < 0) { const char* e = getenv("TGP_FIR_STAGGER"); stagger = e ? atoi(e) : 0; }
-        ar.stagger_ns = (unsigned)stagger;
-    }
+    static int stagger = -1, pdl = -1;
+    if (stagger < 0) { const char* e = getenv("TGP_FIR_STAGGER"); stagger = e ? atoi(e) : 0; }
+    if (pdl < 0) { const char* e = getenv("TGP_FIR_PDL"); pdl = e ? atoi(e) : 1; }
+    ar.stagger_ns = (unsigned)stagger;
     TGP_K(h, "k_fir_logpdf");
     constexpr size_t smem = FirSmem<D>::bytes;
     static bool attr_set[64] = {false};
@@ -610,11 +617,23 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
         TGP_CUDA(h, cudaFuncSetAttribute(k_fir_logpdf<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[h->device & 63] = true;
     }
-    k_fir_logpdf<D><<<G, kFirThreads, smem, h->stream>>>(pl, ar);
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(G);
+        cfg.blockDim = dim3(kFirThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = (pdl && !h->timing) ? 1 : 0;
+        TGP_CUDA(h, cudaLaunchKernelEx(&cfg, k_fir_logpdf<D>, pl, ar));
+    }
     TGP_LAUNCH_CHECK(h);
     *handled = true;
     if (lml_out && !ar.lml_user) {
-        TGP_CUDA(h, cudaMemcpyAsync(h->pinned + 8, st.result, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        TGP_CUDA(h, cudaMemcpyAsync(h->pinned + 8, ar.result, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         TGP_CUDA(h, cudaStreamSynchronize(h->stream));
         h->d2h += 8;
         *lml_out = h->pinned[8];

@@ -37,18 +37,19 @@ struct FirPlan {
     long long T;                  // steps of this shard
     long long ntiles;             // ceil((T - N0) / 1024)
     int nb;                       // look-back depth in tiles
-    int aligned;                  // y + N0 is 32-byte aligned (256-bit loads)
+    int aligned;                  // y + N0 is 32-byte aligned (16-byte cp.async)
+    int zero_mean;                // a = 0 and h = 0: kap, zc vanish (the kernel has a variant without those terms)
 };
 
 
 // ---- per-lane arithmetic of one tile (shared by the kernel and the g++-compiled emulation in tests/emul/) ---------------------
 // pass A, one block: u_b = zc + sum_j gK[j] y_j; z <- Abar^8 z + u_b (z = zero-state response of the lane's run so far).
-template <int D>
+template <int D, bool ZM = false>
 TGP_HD void fir_pass_a_block(const FirPlan<D>& pl, int b, const double (&yv)[kFirL], Vec<D>& ub, Vec<D>& z) {
 TGP_UNROLL
-    for (int i = 0; i < D; ++i) ub[i] = pl.zc[i];
+    for (int i = 0; i < D; ++i) ub[i] = ZM ? pl.gK[0][i] * yv[b * kFirB] : fma(pl.gK[0][i], yv[b * kFirB], pl.zc[i]);
 TGP_UNROLL
-    for (int j = 0; j < kFirB; ++j)
+    for (int j = 1; j < kFirB; ++j)
 TGP_UNROLL
         for (int i = 0; i < D; ++i) ub[i] = fma(pl.gK[j][i], yv[b * kFirB + j], ub[i]);
     Vec<D> zn = ub;
@@ -88,11 +89,11 @@ TGP_UNROLL
 }
 // pass B, data-only half (needs no state, so it runs while the carry is in flight): y_j <- y_j - kap_j - sum_{i<j} g_{j-1-i} y_i,
 // in place, j descending inside each block.
-template <int D>
+template <int D, bool ZM = false>
 TGP_HD void fir_pass_b1_block(const FirPlan<D>& pl, int b, double (&yv)[kFirL]) {
 TGP_UNROLL
     for (int j = kFirB - 1; j >= 0; --j) {
-        double v = yv[b * kFirB + j] - pl.kap[j];
+        double v = ZM ? yv[b * kFirB + j] : yv[b * kFirB + j] - pl.kap[j];
 TGP_UNROLL
         for (int i = 0; i < j; ++i) v = fma(-pl.g[j - 1 - i], yv[b * kFirB + i], v);
         yv[b * kFirB + j] = v;
@@ -278,6 +279,9 @@ void fir_build_plan(const double* hA, const double* ha, const double* hQ, const 
     }
     d.hh = hh;
     d.invS = 1.0 / S;
+    d.zero_mean = 1;
+    for (int i = 0; i < D; ++i) if (d.zc[i] != 0.0) d.zero_mean = 0;
+    for (int j = 0; j < kFirB; ++j) if (d.kap[j] != 0.0) d.zero_mean = 0;
     // ---- extent of the transient: converged, and the first steady step 32-byte aligned ------------------------------------
     long long N0 = 0;
     if (first_shard) {
