@@ -15,8 +15,10 @@ log marginal likelihood), i.e. the reference's headline benchmark (README "logpd
   cpu_baseline  the C restatement of the reference's sequential SArrayStorage path (oracle/), 1 thread
   filter_emit   (extra) tgp_filter emitting (m_f, P_f): 104 B/step algorithmic
 
-N > 1 (torchrun): ONE series of N*T steps sharded over time, one rank per GPU ("weak" scaling: T per
-GPU fixed); exchange = one all-gather of a scan element per rank over NCCL.
+N > 1 (torchrun): ONE series of N*T steps sharded over time, one rank per GPU ("weak" scaling: T per GPU fixed = `value`), and
+BASELINE config 4 beside it on every line (`strong_scaling`: the same 8e7-step series at every N). One kernel launch per shard and
+step; the <= 3072 observations that precede a shard travel over NVLink inside the kernels (tgp_fir.cuh).
+Both series are checked against the sequential oracle at every N (`lml_rel_err_vs_oracle`).
 --impl reference: the oracle port of the reference's CPU path on the host (rank 0 only).
 """
 from __future__ import annotations
@@ -149,6 +151,28 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+STRONG_T = 80_000_000      # BASELINE config 4: one series of 8e7 steps, time-sharded over the GPUs (fixed total = strong scaling)
+STRONG_CHUNK = 10_000_000
+
+
+def strong_chunk(c, buf):
+    """Chunk c (1e7 steps) of the config-4 series, buffer set `buf`: the same for every world size."""
+    return synth_y(STRONG_CHUNK, 20261017 + 4 + 131 * c + 7919 * buf)
+
+
+def cpu_all_cores(T, nthreads, seed=20261017 + 2):
+    """`nthreads` independent logpdf evaluations, one host thread each (oracle/lgssm_ref.c: the only way the single-threaded
+    reference can use all cores for this path; labelled "replicas" — NOT what it does for one series)."""
+    from oracle import c_oracle, tgp_oracle as O
+    cm = c_oracle.Model.from_lgssm(O.build_lgssm(O.Matern52(), O.RegularSpacing(0.0, DT, T), SIGMA2))
+    ys = np.stack([synth_y(T, seed + 17 * k) for k in range(nthreads)])
+    c_oracle.logpdf_replicas(cm, ys[:, : T])      # warm
+    t0 = time.perf_counter()
+    _, n = c_oracle.logpdf_replicas(cm, ys)
+    dt = time.perf_counter() - t0
+    return nthreads * T / dt, n
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -163,7 +187,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     T = args.T
-    K, W = args.steps, args.warmup
+    K, W = args.steps, max(args.warmup, 3)
     h = pkg.default_handle(local)
     # One real stream for the library's kernels, torch's copies / collectives and the timing events (torch's default stream has
     # handle 0, which the library would read as "use the handle's own stream").
@@ -172,66 +196,79 @@ def run_ours(args):
     h.set_stream(stream.cuda_stream)
     if args.algo == "scan":
         h.set_algo(pkg.TGP_ALGO_SCAN)
-
-    # model: the public API builds it (host, O(1) for RegularSpacing)
     f = pkg.to_sde(pkg.GP(pkg.Matern52Kernel()), pkg.B200Storage(local))
-    Tglob = T * world
-    fx = f(pkg.RegularSpacing(0.0, DT, T), SIGMA2)
-    model = fx.build_lgssm()
-    mm = pkg.lgssm._Marshalled(model)
-
-    # inputs: N_BUF distinct series resident in HBM (rotated so no step finds its y in L2)
-    ys_host = [synth_y(T, 20261017 + 2 + 97 * i + 1000 * rank) for i in range(N_BUF)]
-    ys_dev = [torch.from_numpy(v).to(dev) for v in ys_host]
-    lml_dev = torch.zeros(1, dtype=torch.float64, device=dev)
-    lml_host = np.zeros(1)
-
-    if world == 1:
-        # device-resident inputs AND outputs: the calls are only enqueued (TGP_OPT_DEFER_STATUS), their status accumulates on the
-        # device and is checked by h.synchronize() after the timed loop — no host round trip between steps
-        h.set_option(pkg._lib.TGP_OPT_DEFER_STATUS, 1)
-
-        def step(i):
-            h.logpdf(mm.desc, ys_dev[i % N_BUF], lml_dev)
-    else:
-        from temporalgps_jl_b200 import sharded
-        sh = sharded.ShardedLogpdf(h, mm, rank, world, dev)
-
-        def step(i):
-            sh.logpdf(ys_dev[i % N_BUF], lml_dev, sync=False)   # enqueued; status accumulates on the device, checked after the loop
+    from temporalgps_jl_b200 import sharded
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(W, 3)):
-        step(i)
-    barrier()
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step, finish):
+        """W warm-up steps, then exactly K steps between two events on the launching stream, barrier + synchronize on both sides;
+        `finish` (inside the timed region) makes the last step's result available. -> ms per step, max over ranks."""
+        for i in range(W):
+            step(i)
+        finish()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for i in range(K):
+            step(i)
+        finish()
+        e1.record(stream)
+        barrier()
+        h.synchronize()
+        return max_over_ranks(e0.elapsed_time(e1)) / K
+
+    # ================= weak series (the headline `value`): config 2 per GPU, T = 1e7 each, ONE series of world * T steps ==========
+    Tglob = T * world
+    fx = f(pkg.RegularSpacing(0.0, DT, T), SIGMA2)
+    mm = pkg.lgssm._Marshalled(fx.build_lgssm())
+    seed_of = lambda r, i: 20261017 + 2 + 97 * i + 1000 * r      # noqa: E731
+    ys_host = [synth_y(T, seed_of(rank, i)) for i in range(N_BUF)]
+    ys_dev = [torch.from_numpy(v).to(dev) for v in ys_host]
+    lml_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+    lml_host = np.zeros(1)
+    sh = None
+    if world == 1:
+        # device-resident inputs AND output: each call is ONE kernel launch, only enqueued (nothing to report back: the plan checked
+        # positive-definiteness on the host); consecutive calls may overlap at their edges (programmatic dependent launch)
+        def step(i):
+            h.logpdf(mm.desc, ys_dev[i % N_BUF], lml_dev)
+
+        def finish():
+            pass
+    else:
+        sh = sharded.ShardedLogpdf(h, mm, rank, world, dev)
+
+        def step(i):
+            sh.logpdf(ys_dev[i % N_BUF], None, sync=False)      # one launch per shard; the partial lmls land in every rank's buffer
+
+        def finish():
+            sh.result(lml_dev)                                  # fixed-order sum over ranks of the LAST step
     c0 = h.counters()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for i in range(K):
-        step(i)
-    e1.record(stream)
-    barrier()
-    if world > 1:
-        sh.check()
-    else:
-        h.synchronize()       # raises if any of the enqueued calls failed (not positive definite / steady state not reached)
-    dev_ms = e0.elapsed_time(e1)
+    ms_per_step = timed(step, finish)
     c1 = h.counters()
-    if world > 1:
-        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
-    ms_per_step = dev_ms / K
     value = Tglob / (ms_per_step * 1e-3)
-    launches = c1["launches"] - c0["launches"]
+    launches = (c1["launches"] - c0["launches"]) * K // (K + W)
+    route = sh.route if sh else "single launch (k_fir_logpdf)"
+    # parity of the benchmarked computation at THIS world size: buffer 0 of every rank, concatenated, against the sequential oracle
+    step(0)
+    finish()
+    h.synchronize()
+    lml_weak = float(lml_dev.item())
 
     # ---- e2e: public API, pinned host y, H2D + D2H inside the timed region -------------------------
     pin = [torch.from_numpy(v).pin_memory() for v in ys_host[:2]]
@@ -250,24 +287,19 @@ def run_ours(args):
     for i in range(K):
         lml_e2e = e2e_step(i)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
     ce1 = h.counters()
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
     e2e_value = Tglob * K / e2e_s
+    e2e_h2d = (ce1["h2d_bytes"] - ce0["h2d_bytes"]) / K + (sh.h2d_bytes_per_host_call if sh else 0)
+    e2e_d2h = (ce1["d2h_bytes"] - ce0["d2h_bytes"]) / K + (8 if sh else 0)      # sharded: the .item() of the total
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- roofline leg: per-kernel device time with the library's event timers (separate pass) ------
+    # ---- roofline leg: per-kernel device time with the library's event timers (separate pass, calls do not overlap) ------
     h.set_timing(True)
     for i in range(K):
         step(i)
     tim = h.timing()
     h.set_timing(False)
-    if os.environ.get("TGP_BENCH_DEBUG"):
-        with open(os.path.join(ROOT, "gpurun_out", f"kernels_rank{rank}.txt"), "w") as fh:
-            fh.write(repr([(n, round(ms / c * 1e3, 1)) for n, ms, c in tim]) + "\n")
     tot = sum(t[1] for t in tim) or 1.0
     top = tim[0]
     hbm, peak_src = peaks()
@@ -282,14 +314,52 @@ def run_ours(args):
             traffic = rec["dram_bytes_per_launch"]
     roof = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
             "traffic": traffic, "peak_source": peak_src, "kernel_ms": top_ms, "kernel_share_of_step": top[1] / tot,
-            "algorithmic_bytes_per_step": bytes_per_step,
+            "algorithmic_bytes_per_step": bytes_per_step, "whole_call_frac": bytes_per_step * T / (ms_per_step * 1e-3) / 1e9 / hbm,
+            "note": "kernel_ms: one launch timed alone (CUDA events around it, no overlap with its neighbours); whole_call_frac: "
+                    "8 B x T / ms_per_step of the back-to-back timed loop",
             "kernels": [{"name": n, "ms_per_launch": ms / c, "launches_per_step": c / K} for n, ms, c in tim]}
+
+    # ================= strong series (BASELINE config 4): T_total = 8e7 FIXED, sharded over the GPUs ==============================
+    strong = None
+    if not args.no_strong and STRONG_T % (world * STRONG_CHUNK) == 0:
+        del ys_dev
+        torch.cuda.empty_cache()
+        per = STRONG_T // world
+        cpr = per // STRONG_CHUNK                                   # chunks per rank
+        mm4 = pkg.lgssm._Marshalled(f(pkg.RegularSpacing(0.0, DT, per), SIGMA2).build_lgssm())
+        ys4 = [torch.cat([torch.from_numpy(strong_chunk(rank * cpr + c, b)) for c in range(cpr)]).to(dev) for b in range(2)]
+        if world == 1:
+            def step4(i):
+                h.logpdf(mm4.desc, ys4[i % 2], lml_dev)
+
+            def finish4():
+                pass
+        else:
+            sh4 = sharded.ShardedLogpdf(h, mm4, rank, world, dev)
+
+            def step4(i):
+                sh4.logpdf(ys4[i % 2], None, sync=False)
+
+            def finish4():
+                sh4.result(lml_dev)
+        ms4 = timed(step4, finish4)
+        step4(0)
+        finish4()
+        h.synchronize()
+        strong = {"T_total": STRONG_T, "T_per_gpu": per, "value": STRONG_T / (ms4 * 1e-3), "unit": "steps/s", "ms_per_step": ms4,
+                  "scaling": "strong", "hbm_frac_per_gpu": 8.0 * per / (ms4 * 1e-3) / 1e9 / hbm, "lml": float(lml_dev.item()),
+                  "note": "BASELINE config 4: the SAME series of 8e7 steps at every world size (2 rotating buffer sets); "
+                          "scaling = value(N) / value(1) across the lines of a --gpus sweep"}
+        del ys4
+        torch.cuda.empty_cache()
+        ys_dev = [torch.from_numpy(v).to(dev) for v in ys_host]
 
     # ---- extra: tgp_filter emitting (m_f, P_f) — 104 B/step algorithmic (single GPU only) --------------
     extra = None
     if world == 1 and not args.no_filter:
         mf = torch.empty((T, 3), dtype=torch.float64, device=dev)
         Pf = torch.empty((T, 9), dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for i in range(3):
             h.filter(mm.desc, ys_dev[i % N_BUF], mf, 3, Pf, 9, lml_dev)
         torch.cuda.synchronize()
@@ -318,38 +388,57 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- cpu baseline (rank 0, bounded sample) -----------------------------------------------------
+    # ---- cpu baseline + parity (rank 0, bounded sample) -----------------------------------------------------
     cpu = None
+    parity = {}
     if not args.no_cpu:
-        reps = 10
-        t_cpu, lml_cpu = cpu_reference(T, reps)
+        from oracle import c_oracle, tgp_oracle as O
+        reps = 5
+        t_cpu, _ = cpu_reference(T, reps)
+        ncores = os.cpu_count() or 1
+        all_v, all_n = cpu_all_cores(min(T, 4_000_000), ncores)
         cpu = {"value": T / t_cpu, "unit": "steps/s", "cores": 1, "kind": "port",
                "sample": f"{reps} x full T={T} logpdf with the C restatement of the reference's sequential SArrayStorage path "
-                         f"(oracle/lgssm_ref.c, gcc -O3), 1 thread of {os.cpu_count()} host cores"}
-        if world == 1:  # parity of the benchmarked call itself (same y as buffer 0)
-            h.logpdf(mm.desc, ys_dev[0], lml_host)
-            rel = abs(lml_host[0] - lml_cpu) / abs(lml_cpu)
-            cpu["lml_rel_err_vs_gpu"] = rel
-            assert rel < 1e-6, f"GPU logpdf {lml_host[0]} differs from the oracle {lml_cpu}"
+                         f"(oracle/lgssm_ref.c, gcc -O3), 1 thread of {ncores} host cores",
+               "all_cores": {"value": all_v, "unit": "steps/s", "cores": all_n,
+                             "sample": f"{all_n} independent logpdf evaluations of T={min(T, 4_000_000)} each, one POSIX thread per "
+                                       "evaluation ('replicas': the only way the single-threaded reference uses every core; NOT "
+                                       "what it does for one series)"}}
+        # parity at THIS world size, on the benchmarked inputs (buffer 0 of every rank = one series of world * T steps)
+        y_all = np.concatenate([synth_y(T, seed_of(r, 0)) for r in range(world)])
+        ref = c_oracle.logpdf(c_oracle.Model.from_lgssm(O.build_lgssm(O.Matern52(), O.RegularSpacing(0.0, DT, Tglob), SIGMA2)), y_all)
+        parity["lml_rel_err_vs_oracle"] = abs(lml_weak - ref) / abs(ref)
+        assert parity["lml_rel_err_vs_oracle"] < 1e-6, f"GPU logpdf {lml_weak} differs from the oracle {ref} at world {world}"
+        cpu["lml_rel_err_vs_gpu"] = parity["lml_rel_err_vs_oracle"]
+        if strong is not None:
+            y4 = np.concatenate([strong_chunk(c, 0) for c in range(STRONG_T // STRONG_CHUNK)])
+            ref4 = c_oracle.logpdf(c_oracle.Model.from_lgssm(O.build_lgssm(O.Matern52(), O.RegularSpacing(0.0, DT, STRONG_T), SIGMA2)), y4)
+            strong["lml_rel_err_vs_oracle"] = abs(strong["lml"] - ref4) / abs(ref4)
+            assert strong["lml_rel_err_vs_oracle"] < 1e-6, f"config 4: GPU logpdf {strong['lml']} differs from the oracle {ref4}"
 
+    cfg = workload_config(T, world, args.algo)
+    cfg["route"] = route
     out = {
         "metric": METRIC, "value": value, "unit": "steps/s",
-        "n_gpus": world, "steps": K, "warmup": max(W, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": value / 5e7, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(T, world, args.algo),
+        "config": cfg,
         "logpdf_per_s": 1e3 / ms_per_step,
         "vs_baseline_note": "BASELINE.md: reference static-lgssm logpdf at N=1e7 read off a plot as 2.5-5e7 steps/s on an unstated CPU; "
                             "5e7 (upper end) used as the denominator",
         "e2e": {"value": e2e_value, "unit": "steps/s", "ms_per_step": e2e_s / K * 1e3,
-                "h2d_bytes_per_step": (ce1["h2d_bytes"] - ce0["h2d_bytes"]) / K, "d2h_bytes_per_step": (ce1["d2h_bytes"] - ce0["d2h_bytes"]) / K,
-                "api": "gp.logpdf(to_sde(GP(Matern52Kernel()))(RegularSpacing, sigma2), y_pinned_host)"},
+                "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h,
+                "api": "gp.logpdf(to_sde(GP(Matern52Kernel()))(RegularSpacing, sigma2), y_pinned_host)" if world == 1 else
+                       "ShardedLogpdf.logpdf_host(y_pinned_host): torch H2D copy of the shard + tgp_shard_logpdf + tgp_shard_result + .item()"},
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "lml_rel_err_vs_oracle": parity.get("lml_rel_err_vs_oracle"),
+        "strong_scaling": strong,
         "filter_emit": extra,
         "secondary": secondary,
         "clocks": clk,
-        "lml": float(lml_e2e),
+        "lml": lml_weak,
     }
     print(json.dumps(out))
     if world > 1:
@@ -418,6 +507,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-filter", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the configs 3 / 5 extras")
+    ap.add_argument("--no-strong", action="store_true", help="skip the fixed-T = 8e7 (config 4) series")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

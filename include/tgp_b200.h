@@ -181,28 +181,29 @@ int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial);
  * (tgp_shard_phase2: TGP_ENOTPD / TGP_EUNSUPPORTED "not converged"). The next call on the handle does the same. */
 int tgp_synchronize(tgp_handle h);
 
-/* Peer-memory exchange for the sharded path (one process per GPU, NVLink / NVSwitch P2P): replaces the all-gather of the
- * records and the all-reduce of the partial log-likelihoods by direct stores into every peer's buffer + a flag, all
- * stream-ordered on the handle's stream (no NCCL call, no host round trip):
- *     tgp_shard_phase1 -> tgp_xchg_put(0, rec) -> tgp_xchg_wait(0, n, recs, 0) -> tgp_shard_phase2 -> tgp_xchg_put(1, lml)
- *     -> tgp_xchg_wait(1, 1, lml_total, 1)
+/* Peer-memory exchange for the sharded path (one process per GPU, NVLink / NVSwitch P2P): direct stores into every peer's buffer
+ * + a flag, all stream-ordered on the handle's stream (no NCCL call, no host round trip).
  * tgp_xchg_create allocates this rank's buffer and returns its 64-byte CUDA IPC handle; the caller gathers the handles of
  * all ranks (any transport) and passes them, rank-ordered, to tgp_xchg_open. put copies n doubles (n <= slot_doubles) into
  * this rank's slot of `channel` (0 or 1) on EVERY rank and raises the slot's flag; wait mode 0 waits for the ranks before
  * this one and copies their slots to dst[p*n ..]; mode 1 waits for all ranks and writes the sum over ranks to dst[0..n).
- * src / dst are device pointers. Every rank must issue the same sequence of put / wait calls.
- * FUSED FORM: once tgp_xchg_open has succeeded, tgp_shard_phase1 / tgp_shard_phase2 do the channel-0 put / wait and the
- * channel-1 put INSIDE their kernels (the sequence is then phase1 -> phase2 -> tgp_xchg_wait(1, 1, total, 1)); the caller must
- * not put on those channels itself. xchg_all of tgp_shard_phase2 is then unused (the records are read from the exchange buffer). */
+ * src / dst are device pointers. Every rank must issue the same sequence of put / wait calls. */
 int tgp_xchg_create(tgp_handle h, int rank, int world, int slot_doubles, void* ipc_handle_out);
-/* ONE-LAUNCH FORM (needs an opened exchange): phase 1, the record exchange and phase 2 inside a single cooperative kernel — the
- * grid barrier between the two phases doubles as the exchange point (the CTA arriving last ships the record over NVLink before
- * releasing the grid; ranks > 0 then wait for their predecessors' flags). Writes the shard's partial log-likelihood to
- * lml_partial (DEVICE) and ships it on channel 1; the caller follows with tgp_xchg_wait(1, 1, total, 1). Un-synchronised. */
-int tgp_shard_step(tgp_handle h, const tgp_lgssm* shard, const double* y, int rank, int world, double* lml_partial);
 int tgp_xchg_open(tgp_handle h, const void* ipc_handles_all);
 int tgp_xchg_put(tgp_handle h, int channel, const double* src, int n);
 int tgp_xchg_wait(tgp_handle h, int channel, int n, double* dst, int mode);
+
+/* ONE-LAUNCH SHARDED LOGPDF (the path BASELINE config 4 runs; needs an opened exchange when world > 1). `shard` describes this
+ * rank's steps [rank*T, ...) of ONE Forward, time-invariant, scalar-observation series (D <= 4); its (m0, P0) is the prior of the
+ * whole series. The call ENQUEUES one kernel and returns: rank 0 runs the covariance transient, every other rank starts from pass A
+ * over the <= 3072 observations that precede its shard, which its predecessor's kernel stores into this rank's exchange buffer over
+ * NVLink at the START of its own run — shards never wait for each other's results. Each kernel ships its shard's log-likelihood
+ * into every rank's buffer. tgp_shard_result enqueues the fixed-order sum over ranks for the LAST tgp_shard_logpdf into lml_total
+ * (device pointer: stream-ordered; host pointer: synchronises) — call it when the value is wanted, not necessarily per step.
+ * Every rank must issue the same sequence of tgp_shard_logpdf calls. Returns TGP_EUNSUPPORTED (nothing enqueued, the same
+ * decision on every rank) for models outside the path's range: use tgp_shard_phase1/2 or tgp_shard_reduce/prefix then. */
+int tgp_shard_logpdf(tgp_handle h, const tgp_lgssm* shard, const double* y, int rank, int world);
+int tgp_shard_result(tgp_handle h, double* lml_total);
 
 #ifdef __cplusplus
 }

@@ -158,6 +158,17 @@ def logpdf(model: Model, y):
     return filter(model, y, want_mp=False, want_steps=False)["lml"]
 
 
+def logpdf_replicas(model: Model, ys):
+    """`len(ys)` independent logpdf evaluations (rows of the C-contiguous 2-D array ys), one POSIX thread each.
+    -> (lml per row, threads used)."""
+    ys = np.ascontiguousarray(ys, dtype=np.float64)
+    n, T = ys.shape
+    assert T == model.T
+    out = np.empty(n)
+    nth = lib().oracle_logpdf_replicas(C.byref(model.desc), _p(ys), C.c_int64(T), C.c_int(n), _p(out))
+    return out, int(nth)
+
+
 def posterior(model: Model, y):
     T, D = model.T, model.D
     y = np.ascontiguousarray(y, dtype=np.float64)

@@ -25,6 +25,7 @@
  * tests/test_oracle_pins.py against both this file and the NumPy restatement.
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -198,6 +199,27 @@ int oracle_filter(const tgp_lgssm* md, const double* y, double* m_f, int64_t s_m
 
 int oracle_logpdf(const tgp_lgssm* md, const double* y, double* lml_out, double* lml_per_step) {
     return oracle_filter(md, y, 0, 0, 0, 0, lml_out, lml_per_step, 0);
+}
+
+/* All host cores, the only way the single-threaded reference can use them for this path: `n` independent logpdf evaluations of the
+ * same model on `n` series (y + r * ystride), one POSIX thread each (this toolchain ships no libgomp). NOT what the reference does
+ * for one series — reported beside the 1-thread number as "replicas" (BASELINE.md section 2). lml_out[n]. Returns the threads used. */
+typedef struct { const tgp_lgssm* md; const double* y; double* out; } replica_arg;
+static void* replica_main(void* p) {
+    replica_arg* a = (replica_arg*)p;
+    oracle_logpdf(a->md, a->y, a->out, NULL);
+    return NULL;
+}
+int oracle_logpdf_replicas(const tgp_lgssm* md, const double* y, int64_t ystride, int n, double* lml_out) {
+    if (n < 1 || n > 1024) return 0;
+    pthread_t th[1024];
+    replica_arg args[1024];
+    for (int r = 0; r < n; ++r) {
+        args[r].md = md; args[r].y = y + (int64_t)r * ystride; args[r].out = lml_out + r;
+        if (pthread_create(&th[r], NULL, replica_main, &args[r]) != 0) { replica_main(&args[r]); th[r] = 0; }
+    }
+    for (int r = 0; r < n; ++r) if (th[r]) pthread_join(th[r], NULL);
+    return n;
 }
 
 int oracle_posterior(const tgp_lgssm* md, const double* y, double* G, double* g, double* Sig,

@@ -78,7 +78,8 @@ _SIGS = {
     "tgp_shard_phase1": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tgp_shard_phase2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tgp_synchronize": (C.c_int, [C.c_void_p]),
-    "tgp_shard_step": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "tgp_shard_logpdf": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_int, C.c_int]),
+    "tgp_shard_result": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tgp_xchg_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tgp_xchg_open": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tgp_xchg_put": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -227,8 +228,12 @@ class Handle:
     def shard_phase1(self, desc, y, rank, world, xchg_out):
         self.check(lib().tgp_shard_phase1(self._h, C.byref(desc), ptr(y), int(rank), int(world), ptr(xchg_out)))
 
-    def shard_step(self, desc, y, rank, world, lml_partial):
-        self.check(lib().tgp_shard_step(self._h, C.byref(desc), ptr(y), int(rank), int(world), ptr(lml_partial)))
+    def shard_logpdf(self, desc, y, rank, world):
+        """One-launch sharded logpdf (enqueued, not synchronised). Raises TGPError(TGP_EUNSUPPORTED) if the model is outside its range."""
+        self.check(lib().tgp_shard_logpdf(self._h, C.byref(desc), ptr(y), int(rank), int(world)))
+
+    def shard_result(self, lml_total):
+        self.check(lib().tgp_shard_result(self._h, ptr(lml_total)))
 
     def synchronize(self):
         self.check(lib().tgp_synchronize(self._h))

@@ -312,14 +312,47 @@ int tgp_shard_phase1(tgp_handle h, const tgp_lgssm* shard, const double* y, int 
 #undef CALL
 }
 
-int tgp_shard_step(tgp_handle h, const tgp_lgssm* shard, const double* y, int rank, int world, double* lml_partial) {
+int tgp_shard_logpdf(tgp_handle h, const tgp_lgssm* shard, const double* y, int rank, int world) {
     TGP_TRY(validate(h, shard, true, y));
     TGP_TRY(require_scalar_obs(h, shard));
-    if (rank < 0 || world < 1 || rank >= world || !lml_partial) return fail(h, TGP_EINVAL, "bad rank / world / lml_partial");
+    if (rank < 0 || world < 1 || rank >= world) return fail(h, TGP_EINVAL, "bad rank / world");
     TGP_TRY(begin_call(h));
-#define CALL(Dv) do_shard_step<Dv>(h, shard, y, rank, world, lml_partial)
-    TGP_DISPATCH_D(h, shard->D)
-#undef CALL
+    bool handled = false;
+    int rc = TGP_EUNSUPPORTED;
+    switch (shard->D) {
+#define TGP_SL_CASE(Dv) case Dv: rc = do_shard_logpdf<Dv>(h, shard, y, rank, world, &handled); break;
+        TGP_FOR_EACH_D(TGP_SL_CASE)
+#undef TGP_SL_CASE
+        default: break;
+    }
+    if (rc != TGP_OK) return rc;
+    if (!handled)
+        return fail(h, TGP_EUNSUPPORTED, "tgp_shard_logpdf runs Forward, time-invariant, scalar-observation models with D <= 4 whose filter reaches its "
+                                         "fixed point and forgets its start within 3072 steps; use tgp_shard_phase1/2 or tgp_shard_reduce/prefix");
+    h->shard_world = world;
+    return TGP_OK;
+}
+
+int tgp_shard_result(tgp_handle h, double* lml_total) {
+    if (!h || !lml_total) return TGP_EINVAL;
+    TGP_CUDA(h, cudaSetDevice(h->device));
+    if (!h->fir.result || h->fir.epoch == 0) return fail(h, TGP_EINVAL, "tgp_shard_result without a tgp_shard_logpdf");
+    const bool dev = is_device_ptr(lml_total);
+    double* dst = dev ? lml_total : h->fir.result + 2;
+    if (h->shard_world > 1) {
+        XchgFirView v;
+        if (!xchg_fir_view(h, &v)) return fail(h, TGP_EINVAL, "exchange not opened");
+        TGP_TRY(xchg_fir_total(h, *v.epoch, dst));
+    } else {
+        TGP_CUDA(h, cudaMemcpyAsync(dst, h->fir.result + 4 * (h->fir.epoch & 1ull), sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (!dev) {
+        TGP_CUDA(h, cudaMemcpyAsync(h->pinned + 8, dst, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        TGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->d2h += 8;
+        *lml_total = h->pinned[8];
+    }
+    return TGP_OK;
 }
 
 int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial) {

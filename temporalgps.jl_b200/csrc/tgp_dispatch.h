@@ -15,7 +15,7 @@ template <int D> int do_marginals(tgp_ctx* h, const tgp_lgssm* m, double* mean_o
 template <int D> int do_shard_reduce(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* elem_out);
 template <int D> int do_shard_phase1(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, int world, double* xchg_out);
 template <int D> int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double* lml_partial);
-template <int D> int do_shard_step(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, int world, double* lml_partial);
+template <int D> int do_shard_logpdf(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, int world, bool* handled);
 template <int D> int do_shard_prefix(int n, const double* elems, const double* m0, const double* P0, double* m_in,
                                      double* P_in);
 
@@ -37,6 +37,23 @@ bool xchg_view(tgp_ctx* h, XchgView* v);
 unsigned long long xchg_next_epoch(tgp_ctx* h, int ch);
 unsigned long long xchg_epoch(tgp_ctx* h, int ch);
 
+// Region of the exchange buffer used by the one-launch sharded logpdf (tgp_fir.cuh), identical on every rank:
+//   halo[4][3 * 1024] doubles   ring (by call epoch & 3) of the observations that precede this rank's shard, written by rank - 1
+//   halo_flag, ack              u64: epoch of the last halo written here by rank - 1 / of the last halo rank + 1 has consumed
+//   lml[4][world] doubles       ring of the shards' log-likelihoods, lml_flag[world] u64: epoch of the last one written by each rank
+struct FirXchgLayout {
+    static constexpr int kRing = 4, kHaloDoubles = 3 * 1024;
+    static __host__ __device__ constexpr size_t halo_off(unsigned long long epoch) { return (size_t)(epoch & 3ull) * kHaloDoubles * sizeof(double); }
+    static __host__ __device__ constexpr size_t halo_flag_off() { return (size_t)kRing * kHaloDoubles * sizeof(double); }
+    static __host__ __device__ constexpr size_t ack_off() { return halo_flag_off() + 64; }
+    static __host__ __device__ constexpr size_t lml_off(int world, unsigned long long epoch, int rank) { return ack_off() + 64 + ((size_t)(epoch & 3ull) * world + rank) * sizeof(double); }
+    static __host__ __device__ constexpr size_t lml_flag_off(int world) { return ack_off() + 64 + (size_t)kRing * world * sizeof(double); }
+    static __host__ __device__ constexpr size_t bytes(int world) { return lml_flag_off(world) + (size_t)world * sizeof(unsigned long long) + 256; }
+};
+struct XchgFirView { char* const* peers; char* self; char* prev; char* next; size_t fir_off; int world, rank; unsigned long long* epoch; };
+bool xchg_fir_view(tgp_ctx* h, XchgFirView* v);
+int xchg_fir_total(tgp_ctx* h, unsigned long long epoch, double* dst_dev);
+
 // Test hook for the tcgen05 contraction kernel alone (tgp_dense_tc.cuh).
 int tc_gemm_selftest(tgp_ctx* h, int K, int Mx, int N, const float* X, const float* Y, float* C, int symmetric);
 
@@ -51,7 +68,7 @@ int tc_gemm_selftest(tgp_ctx* h, int K, int Mx, int N, const float* X, const flo
     extern template int do_shard_reduce<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, double*);                     \
     extern template int do_shard_phase1<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, int, int, double*);           \
     extern template int do_shard_phase2<Dv>(tgp_ctx*, const double*, double*);                                       \
-    extern template int do_shard_step<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, int, int, double*);             \
+    extern template int do_shard_logpdf<Dv>(tgp_ctx*, const tgp_lgssm*, const double*, int, int, bool*);             \
     extern template int do_shard_prefix<Dv>(int, const double*, const double*, const double*, double*, double*);
 
 // The set of latent dimensions with kernel instantiations (keep in step with build.py's TGP_DIMS).

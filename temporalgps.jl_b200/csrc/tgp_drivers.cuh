@@ -45,16 +45,6 @@ inline int end_call(tgp_ctx* h, const unsigned long long* err_step, int64_t T, b
     int* pflag = (int*)(h->pinned + 2);
     *perr = ~0ull;
     *pflag = 1;
-    if (h->defer_status && h->sticky && packed && packed->packed_result && h->pending.empty() &&
-        (!packed->lml_out || is_device_ptr(packed->lml_out))) {
-        // TGP_OPT_DEFER_STATUS and nothing to bring back to the host: the call stays un-synchronised, its status (failing step,
-        // steady-state convergence) is folded into the sticky block that tgp_synchronize reports. No general-scan fallback here.
-        TGP_K(h, "k_sticky_status");
-        k_sticky_status<<<1, 1, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(packed->err), h->sticky);
-        TGP_LAUNCH_CHECK(h);
-        if (ss_converged) *ss_converged = true;
-        return TGP_OK;
-    }
     if (packed && packed->packed_result) {   // {err, lml, flag} contiguous on the device: one copy
         TGP_CUDA(h, cudaMemcpyAsync(perr, packed->err, 24, cudaMemcpyDeviceToHost, h->stream));
         h->d2h += 24;
@@ -567,12 +557,7 @@ int do_shard_phase1(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, i
         tgp_lgssm d;
         const double* dy;
         TGP_TRY(stage_model(h, m, y, &d, &dy));
-        // An opened peer-memory exchange (tgp_xchg_open) of matching shape: the kernels ship / await the records themselves.
-        SSXchg xd{};
-        XchgView xv;
-        h->shard.fused_xchg = xchg_view(h, &xv) && xv.world == world && xv.rank == rank && xv.slot >= D * D + D;
-        if (h->shard.fused_xchg) xd = SSXchg{xv.peers, xv.self, xv.slot, xv.flag_off, xchg_next_epoch(h, 0), 0ull};
-        return shard_phase1<D>(h, &h->shard, d, dy, rank, world, xchg_out, xd);
+        return shard_phase1<D>(h, &h->shard, d, dy, rank, world, xchg_out);
     } else {
         return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path is instantiated for D <= %d", TGP_REG_D);
     }
@@ -585,10 +570,7 @@ int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double* lml_partial) {
     if constexpr (D <= TGP_REG_D) {
         const int64_t T = h->shard.T;
         SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(h->shard.work);
-        SSXchg xd{};
-        XchgView xv;
-        if (h->shard.fused_xchg && xchg_view(h, &xv)) xd = SSXchg{xv.peers, xv.self, xv.slot, xv.flag_off, xchg_epoch(h, 0), xchg_next_epoch(h, 1)};
-        TGP_TRY(shard_phase2<D>(h, &h->shard, xchg_all, lml_partial, xd));
+        TGP_TRY(shard_phase2<D>(h, &h->shard, xchg_all, lml_partial));
         // no synchronisation here: the caller enqueues its all-reduce right behind this kernel; status (convergence,
         // positive-definiteness) is collected by tgp_synchronize() or by the next call on this handle.
         if (h->defer_status && h->sticky) {
@@ -605,35 +587,45 @@ int do_shard_phase2(tgp_ctx* h, const double* xchg_all, double* lml_partial) {
     }
 }
 
-// One-launch sharded step (needs an opened peer-memory exchange of matching shape): phase 1 -> record to the peers -> wait for
-// the predecessors -> phase 2 -> partial log-likelihood to the peers, all inside k_ss_main. Returns WITHOUT synchronising; the
-// caller follows with tgp_xchg_wait(1, 1, total, 1). Status: as tgp_shard_phase2 (tgp_synchronize / TGP_OPT_DEFER_STATUS).
+// One-launch sharded logpdf (tgp_fir.cuh): this rank's shard of a Forward, time-invariant series in ONE un-synchronised launch.
+// Shards never wait for each other's results: rank r > 0 takes the observations that precede its shard (the halo) from the ring its
+// predecessor's kernel fills over NVLink at the start of its run, and every rank ships its shard's log-likelihood to all peers'
+// buffers; tgp_shard_result forms the total when somebody wants it. *handled = false: the plan declined (see logpdf_fir).
 template <int D>
-int do_shard_step(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, int world, double* lml_partial) {
-    if (m->ordering != TGP_FORWARD || !time_invariant(*m))
-        return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path runs Forward, time-invariant models (use tgp_shard_reduce otherwise)");
-    if (!is_device_ptr(lml_partial)) return fail(h, TGP_EINVAL, "lml_partial must be a device pointer");
-    if constexpr (D <= TGP_REG_D) {
-        XchgView xv;
-        if (!xchg_view(h, &xv) || xv.world != world || xv.rank != rank || xv.slot < D * D + D)
-            return fail(h, TGP_EINVAL, "tgp_shard_step needs an opened exchange (tgp_xchg_open) of matching rank / world / slot size");
-        tgp_lgssm d;
-        const double* dy;
-        TGP_TRY(stage_model(h, m, y, &d, &dy));
-        const SSXchg xd{xv.peers, xv.self, xv.slot, xv.flag_off, xchg_next_epoch(h, 0), xchg_next_epoch(h, 1)};
-        SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(h->shard.work);
-        TGP_TRY(shard_step_fused<D>(h, d, dy, rank, world, lml_partial, xd, &w));
-        if (h->defer_status && h->sticky) {
-            TGP_K(h, "k_sticky_status");
-            k_sticky_status<<<1, 1, 0, h->stream>>>(w.resblk, h->sticky);
-            TGP_LAUNCH_CHECK(h);
-        } else {
-            h->deferred_res = w.resblk;
-            h->deferred_T = m->T;
+int do_shard_logpdf(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, int world, bool* handled) {
+    *handled = false;
+    if (m->ordering != TGP_FORWARD || !time_invariant(*m)) return TGP_OK;
+    if constexpr (D <= kFirMaxD) {
+        if (world == 1) return logpdf_fir<D>(h, m, y, nullptr, handled, true, nullptr);
+        XchgFirView v;
+        if (!xchg_fir_view(h, &v) || v.world != world || v.rank != rank)
+            return fail(h, TGP_EINVAL, "tgp_shard_logpdf needs an opened exchange (tgp_xchg_create / tgp_xchg_open) of matching rank / world");
+        using L = FirXchgLayout;
+        const unsigned long long ep = *v.epoch + 1;
+        FirXchg x{};
+        char* mine = v.self + v.fir_off;
+        if (rank > 0) {
+            x.halo = reinterpret_cast<const double*>(mine + L::halo_off(ep));
+            x.halo_flag = reinterpret_cast<const unsigned long long*>(mine + L::halo_flag_off());
+            x.ack_out = reinterpret_cast<unsigned long long*>(v.prev + v.fir_off + L::ack_off());
         }
+        if (v.next) {
+            x.push_dst = reinterpret_cast<double*>(v.next + v.fir_off + L::halo_off(ep));
+            x.push_flag = reinterpret_cast<unsigned long long*>(v.next + v.fir_off + L::halo_flag_off());
+            x.ack_in = reinterpret_cast<const unsigned long long*>(mine + L::ack_off());
+            x.ring = L::kRing;
+        }
+        x.peers = v.peers;
+        x.lml_off = v.fir_off + L::lml_off(world, ep, rank);
+        x.lml_flag_off = v.fir_off + L::lml_flag_off(world) + (size_t)rank * sizeof(unsigned long long);
+        x.epoch = ep;
+        x.rank = rank;
+        x.world = world;
+        TGP_TRY(logpdf_fir<D>(h, m, y, nullptr, handled, rank == 0, &x));
+        if (*handled) *v.epoch = ep;
         return TGP_OK;
     } else {
-        return fail(h, TGP_EUNSUPPORTED, "the steady-state sharded path is instantiated for D <= %d", TGP_REG_D);
+        return TGP_OK;
     }
 }
 

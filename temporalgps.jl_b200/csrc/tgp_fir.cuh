@@ -53,6 +53,7 @@ struct FirXchg {                  // time-sharded use (all null / 0 on a single 
     unsigned long long ring;      // halo ring depth
     char* const* peers;           // mapped exchange buffers of all ranks: the partial log-likelihood goes to every peer
     unsigned long long lml_off, lml_flag_off;   // byte offsets of this rank's lml slot (for this epoch) / flag inside a peer buffer
+    unsigned long long epoch;     // exchange epoch of this call (the same on every rank)
     int rank, world;
 };
 
@@ -605,7 +606,7 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     ar.partials = st.partials + pstride * par;
     ar.result = st.result + 4 * par;
     ar.lml_user = (lml_out && is_device_ptr(lml_out)) ? lml_out : nullptr;
-    if (xc) ar.x = *xc;
+    if (xc) { ar.x = *xc; ar.epoch = xc->epoch; }
     static int stagger = -1, pdl = -1;
     if (stagger < 0) { const char* e = getenv("TGP_FIR_STAGGER"); stagger = e ? atoi(e) : 0; }
     if (pdl < 0) { const char* e = getenv("TGP_FIR_PDL"); pdl = e ? atoi(e) : 1; }

@@ -14,6 +14,6 @@ template int do_marginals<TGP_D>(tgp_ctx*, const tgp_lgssm*, double*, double*);
 template int do_shard_reduce<TGP_D>(tgp_ctx*, const tgp_lgssm*, const double*, double*);
 template int do_shard_phase1<TGP_D>(tgp_ctx*, const tgp_lgssm*, const double*, int, int, double*);
 template int do_shard_phase2<TGP_D>(tgp_ctx*, const double*, double*);
-template int do_shard_step<TGP_D>(tgp_ctx*, const tgp_lgssm*, const double*, int, int, double*);
+template int do_shard_logpdf<TGP_D>(tgp_ctx*, const tgp_lgssm*, const double*, int, int, bool*);
 template int do_shard_prefix<TGP_D>(int, const double*, const double*, const double*, double*, double*);
 }  // namespace tgp

@@ -81,48 +81,13 @@ struct SSOut {
 
 // Time-sharded (multi-GPU) use of the steady kernel: phase 0 = whole filter in one launch (single GPU);
 // phase 1 = zero-state pass only, ending with the shard record (Phi_shard, Z_shard) in xchg_out; phase 2 = the
-// per-step pass, starting from the mean folded out of the gathered records of the ranks before this one.
-// Peer-memory exchange fused into the shard kernels (tgp_xchg.cu owns the buffers): phase 1 stores this rank's record straight
-// into every peer's slot over NVLink and raises a flag; phase 2 waits for the flags of the ranks before it and reads the records
-// from its own buffer; its last CTA ships the partial log-likelihood the same way. No collective, no extra launch.
-struct SSXchg {
-    char* const* peers;       // mapped buffers of all ranks (device array), nullptr = exchange through xchg_out / xchg_all
-    char* self;
-    int slot;                 // doubles per slot
-    unsigned long long flag_off;
-    unsigned long long ep_rec, ep_lml;
-};
-__device__ __forceinline__ size_t ssx_data_off(int ch, unsigned long long ep, int world, int slot, int r) {
-    return ((size_t)((ch * 2 + (int)(ep & 1ull)) * world + r) * slot) * sizeof(double);
-}
-__device__ __forceinline__ void ssx_put(const SSXchg& x, int ch, unsigned long long ep, int world, int rank, const double* v, int n) {
-    const size_t off = ssx_data_off(ch, ep, world, x.slot, rank);
-    for (int p = 0; p < world; ++p) {
-        double* d = reinterpret_cast<double*>(x.peers[p] + off);
-        for (int i = 0; i < n; ++i) d[i] = v[i];
-    }
-    __threadfence_system();
-    for (int p = 0; p < world; ++p)
-        *(reinterpret_cast<volatile unsigned long long*>(x.peers[p] + x.flag_off) + (size_t)ch * world + rank) = ep;
-}
-__device__ __forceinline__ void ssx_wait(const SSXchg& x, int ch, unsigned long long ep, int world, int upto) {
-    for (int p = 0; p < upto; ++p) {
-        const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(x.self + x.flag_off) + (size_t)ch * world + p;
-        unsigned long long spins = 0;
-        while (*f < ep) {
-            if (++spins > (1ull << 31)) __trap();     // a lost peer: fail loudly instead of hanging the GPU
-            __nanosleep(20);
-        }
-    }
-    __threadfence_system();
-}
-
+// per-step pass, starting from the mean folded out of the records of the ranks before this one (all-gathered by the caller).
+// (The log-likelihood-only sharded path of choice is tgp_fir.cuh; this one serves the models its plan declines.)
 struct SSShard {
     int phase, rank, world;
     double* xchg_out;         // D*D + D doubles (phase 1)
     const double* xchg_all;   // world x (D*D + D) doubles (phase 2)
     const void* sq;           // Mat<D>[kSqN]: squares table Abar^(2^k) (global memory)
-    SSXchg xd;
 };
 
 template <int D> __device__ __forceinline__ Vec<D> shfl_up_vec(const Vec<D>& v, int off) {
@@ -492,7 +457,7 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             if (it + NS - 1 < ntiles) issue_tile(ts + (NS - 1) * WT, (int)((it + NS - 1) % NS), pol);
             cp_async_commit();
             const double* yc = ybuf + (int)(it % NS) * LY::YB + lane * LY::YS;
-            const bool tail = (phase == 1 || phase == 3) && ts + WT > Ts;   // the shard's last, partial tile: its aggregate is consumed
+            const bool tail = phase == 1 && ts + WT > Ts;   // the shard's last, partial tile: its aggregate is consumed
             Vec<D> z = vzero<D>();                             // by the next rank, so it must be aligned at step Ts-1 exactly
             if (!tail) {      // full chunk: z = sum_j Abar^(L-1-j) (K y_j + c) through the precomputed coefficient table
                 z = c.zc;
@@ -581,14 +546,6 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
 #pragma unroll
                 for (int i = 0; i < D; ++i) sh.xchg_out[D * D + i] = Z[i];
             }
-            if (sh.xd.peers) {
-                double rec[D * D + D];
-#pragma unroll
-                for (int i = 0; i < D * D; ++i) rec[i] = Phi.v[i];
-#pragma unroll
-                for (int i = 0; i < D; ++i) rec[D * D + i] = Z[i];
-                ssx_put(sh.xd, 0, sh.xd.ep_rec, sh.world, sh.rank, rec, D * D + D);
-            }
         }
     };
     if (phase == 1) {   // the last CTA to finish builds the record
@@ -614,23 +571,6 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             __threadfence();
         }
         __syncthreads();
-    } else if (phase == 3) {
-        // Fused sharded step (one launch per shard and call): the grid barrier between the two phases doubles as the exchange point.
-        // The CTA that arrives last holds the complete set of warp aggregates: it builds the shard record, stores it into every
-        // peer's buffer over NVLink, and only then releases the grid (counter G + 1). Ranks > 0 wait below for their predecessors.
-        __syncthreads();
-        if (tid == 0) *s_last = (atomicAdd(counters, 1u) == (unsigned)G - 1) ? 1 : 0;
-        __syncthreads();
-        if (*s_last) {
-            emit_record();
-            __syncthreads();
-            if (tid == 0) { __threadfence(); atomicAdd(counters, 1u); }
-        }
-        if (tid == 0) {
-            while (*reinterpret_cast<volatile unsigned*>(counters) < (unsigned)G + 1u) { __nanosleep(32); }
-            __threadfence();
-        }
-        __syncthreads();
     }
     // this CTA's warp aggregates -> shared memory (phase 2 of a sharded run reads what phase 1 left in agg)
     if (lane == 0) {
@@ -638,15 +578,10 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
         for (int i = 0; i < D; ++i) red[(kSSWarps + 2 + wp) * D + i] = __ldcg(agg + (size_t)gw * D + i);
     }
     Vec<D> x_in = c.x_in;
-    if ((phase == 2 || phase == 3) && sh.rank > 0) {   // fold the records of the ranks before this one: x <- Phi_r x + Z_r
-        if (sh.xd.peers) {                  // peer-memory exchange: the records arrive in this GPU's own buffer
-            if (tid == 0) ssx_wait(sh.xd, 0, sh.xd.ep_rec, sh.world, sh.rank);
-            __syncthreads();
-        }
+    if (phase == 2 && sh.rank > 0) {   // fold the records of the ranks before this one: x <- Phi_r x + Z_r
         Vec<D> x = vzero<D>();
         for (int r = 0; r < sh.rank; ++r) {
-            const double* rec = sh.xd.peers ? reinterpret_cast<const double*>(sh.xd.self + ssx_data_off(0, sh.xd.ep_rec, sh.world, sh.xd.slot, r))
-                                            : sh.xchg_all + (size_t)r * (D * D + D);
+            const double* rec = sh.xchg_all + (size_t)r * (D * D + D);
             Mat<D> Ph;
             Vec<D> Zr;
 #pragma unroll
@@ -818,7 +753,6 @@ k_ss_main(const SSConst<D>* __restrict__ cg, const double* __restrict__ y_all, d
             const double lml = *out.lml_prefix + (double)Ts * (-0.5 * (kLog2Pi + c.logS)) - 0.5 * c.invS * s;
             *out.lml_out = lml;
             if (out.lml_user) *out.lml_user = lml;
-            if ((phase == 2 || phase == 3) && sh.xd.peers) ssx_put(sh.xd, 1, sh.xd.ep_lml, sh.world, sh.rank, &lml, 1);
         }
     }
 }
@@ -839,7 +773,7 @@ int launch_ss_main(tgp_ctx* h, bool stage_m, const SSConst<D>* cst, const double
         attr_smem[dv] = smem;
     }
     void* args[] = {(void*)&cst, (void*)&dy, (void*)&zbuf, (void*)&zstride, (void*)&agg, (void*)&counters, (void*)&so, (void*)&sh};
-    TGP_K(h, sh.phase == 1 ? "k_ss_main(phase1)" : (sh.phase == 2 ? "k_ss_main(phase2)" : (sh.phase == 3 ? "k_ss_main(fused shard step)" : "k_ss_main")));
+    TGP_K(h, sh.phase == 1 ? "k_ss_main(phase1)" : (sh.phase == 2 ? "k_ss_main(phase2)" : "k_ss_main"));
     TGP_CUDA(h, cudaLaunchCooperativeKernel((const void*)k_ss_main<D, L, NS, OUTS, SHARDED>, dim3((unsigned)G), dim3(kSSThreads), args, smem,
                                             h->stream));
     TGP_LAUNCH_CHECK(h);
@@ -943,7 +877,7 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
     so.lml_out = rq.lml_dev;
     so.lml_user = (rq.lml_out && is_device_ptr(rq.lml_out)) ? rq.lml_out : nullptr;   // device destination: written by the kernel
     so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
-    const SSShard sh{0, 0, 1, nullptr, nullptr, w.sq, SSXchg{}};
+    const SSShard sh{0, 0, 1, nullptr, nullptr, w.sq};
     const bool outs = rq.lml_steps || rq.m_f || rq.P_f;
     TGP_TRY(dispatch_ss_main<D>(h, small_L, outs, stage_m, w.cst, dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh));
     rq.xT = w.xT;
@@ -956,8 +890,7 @@ int filter_steady(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& r
 
 // ---- time-sharded steady-state logpdf: two stream-ordered phases around the caller's all-gather -------------------
 template <int D>
-int shard_phase1(tgp_ctx* h, tgp_shard_state* st, const tgp_lgssm& d, const double* dy, int rank, int world, double* xchg_out,
-                 const SSXchg& xd = SSXchg{}) {
+int shard_phase1(tgp_ctx* h, tgp_shard_state* st, const tgp_lgssm& d, const double* dy, int rank, int world, double* xchg_out) {
     static_assert(sizeof(SSWork<D>) <= sizeof(st->work), "SSWork must fit tgp_shard_state::work");
     const int64_t T = d.T;
     const int64_t max_blocks = std::max<int64_t>(1, std::min<int64_t>(h->ss_prefix > 0 ? (h->ss_prefix + kTrBlock - 1) / kTrBlock : 8,
@@ -973,37 +906,14 @@ int shard_phase1(tgp_ctx* h, tgp_shard_state* st, const tgp_lgssm& d, const doub
     so.lml_prefix = w.lml_prefix;
     so.lml_out = reinterpret_cast<double*>(w.resblk + 1);
     so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
-    const SSShard sh{1, rank, world, xchg_out, nullptr, w.sq, xd};
+    const SSShard sh{1, rank, world, xchg_out, nullptr, w.sq};
     TGP_TRY(dispatch_ss_main<D>(h, false, false, false, w.cst, dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh));
     st->active = true; st->D = D; st->rank = rank; st->world = world; st->T = T; st->dy = dy;
     return TGP_OK;
 }
 
-// Fused form (needs an opened peer-memory exchange): phase 1, the exchange and phase 2 in ONE cooperative launch.
 template <int D>
-int shard_step_fused(tgp_ctx* h, const tgp_lgssm& d, const double* dy, int rank, int world, double* lml_partial_dev, const SSXchg& xd,
-                     SSWork<D>* wout) {
-    const int64_t T = d.T;
-    const int64_t max_blocks = std::max<int64_t>(1, std::min<int64_t>(h->ss_prefix > 0 ? (h->ss_prefix + kTrBlock - 1) / kTrBlock : 8,
-                                                                      T / (2 * kTrBlock)));
-    if (T < 65536) return fail(h, TGP_EUNSUPPORTED, "time shards must hold at least 65536 steps for the steady-state sharded path");
-    SSWork<D>& w = *wout;
-    TGP_TRY(ss_alloc<D>(h, T, false, &w));
-    FilterReq rq;
-    TGP_TRY(ss_transient<D>(h, d, dy, rq, w, max_blocks, (rank > 0 ? 1 : 0) | 2));   // bit 1: also the shard record's powers
-    SSOut so{};
-    so.xT = w.xT;
-    so.partials = w.partials;
-    so.lml_prefix = w.lml_prefix;
-    so.lml_out = reinterpret_cast<double*>(w.resblk + 1);
-    so.lml_user = lml_partial_dev;
-    so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
-    const SSShard sh{3, rank, world, nullptr, nullptr, w.sq, xd};
-    return dispatch_ss_main<D>(h, false, false, false, w.cst, dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh);
-}
-
-template <int D>
-int shard_phase2(tgp_ctx* h, tgp_shard_state* st, const double* xchg_all, double* lml_partial_dev, const SSXchg& xd = SSXchg{}) {
+int shard_phase2(tgp_ctx* h, tgp_shard_state* st, const double* xchg_all, double* lml_partial_dev) {
     SSWork<D>& w = *reinterpret_cast<SSWork<D>*>(st->work);
     SSOut so{};
     so.xT = w.xT;
@@ -1012,7 +922,7 @@ int shard_phase2(tgp_ctx* h, tgp_shard_state* st, const double* xchg_all, double
     so.lml_out = reinterpret_cast<double*>(w.resblk + 1);
     so.lml_user = lml_partial_dev;
     so.flag_out = reinterpret_cast<int*>(w.resblk + 2);
-    const SSShard sh{2, st->rank, st->world, nullptr, xchg_all, w.sq, xd};
+    const SSShard sh{2, st->rank, st->world, nullptr, xchg_all, w.sq};
     TGP_TRY(dispatch_ss_main<D>(h, false, false, false, w.cst, st->dy, w.zbuf, w.zstride, w.G, w.agg, w.counters, so, sh));
     st->active = false;
     return TGP_OK;

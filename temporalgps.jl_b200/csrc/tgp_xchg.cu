@@ -19,6 +19,8 @@ struct XchgState {
     char** d_peers = nullptr;                   // the same on the device
     unsigned long long epoch[kXchgChannels] = {0, 0};
     size_t flag_off = 0, bytes = 0;
+    size_t fir_off = 0;                         // region of the one-launch sharded logpdf (tgp_fir.cuh), see FirXchgLayout
+    unsigned long long fir_epoch = 0;
 };
 
 __device__ __forceinline__ size_t xchg_data_off(int ch, int parity, int world, int slot, int r) {
@@ -76,7 +78,8 @@ int xchg_create(tgp_ctx* h, int rank, int world, int slot_doubles, void* ipc_han
     XchgState* x = new XchgState();
     x->rank = rank; x->world = world; x->slot = slot_doubles;
     x->flag_off = (size_t)kXchgChannels * 2 * world * slot_doubles * sizeof(double);
-    x->bytes = x->flag_off + (size_t)kXchgChannels * world * sizeof(unsigned long long);
+    x->fir_off = (x->flag_off + (size_t)kXchgChannels * world * sizeof(unsigned long long) + 255) & ~size_t(255);
+    x->bytes = x->fir_off + FirXchgLayout::bytes(world);
     if (cudaMalloc((void**)&x->self, x->bytes) != cudaSuccess || cudaMemset(x->self, 0, x->bytes) != cudaSuccess) {
         delete x;
         return fail(h, TGP_ENOMEM, "exchange buffer allocation failed");
@@ -132,6 +135,51 @@ int xchg_wait(tgp_ctx* h, int ch, int n, double* dst, int mode) {
     k_xchg_wait<<<1, 128, 0, h->stream>>>(x->self, x->world, x->rank, ch, (int)(ep & 1), x->slot, n, ep, x->flag_off, dst, mode);
     TGP_LAUNCH_CHECK(h);
     return TGP_OK;
+}
+
+// Sum of the shards' log-likelihoods of the sharded call with epoch `epoch` (ring slot epoch & 3): waits for every rank's flag.
+__global__ void __launch_bounds__(128) k_fir_lml_total(const char* __restrict__ self, size_t fir_off, int world, unsigned long long epoch,
+                                                       double* __restrict__ dst) {
+    const char* base = self + fir_off;
+    if (threadIdx.x < world) {
+        const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(base + FirXchgLayout::lml_flag_off(world)) + threadIdx.x;
+        unsigned long long spins = 0;
+        while (*f < epoch) {
+            if (++spins > (1ull << 31)) __trap();
+            __nanosleep(50);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double* v = reinterpret_cast<const double*>(base + FirXchgLayout::lml_off(world, epoch, 0));
+        double s = 0.0;
+        for (int p = 0; p < world; ++p) s += __ldcg(v + p);     // fixed order: the same bits on every rank
+        *dst = s;
+    }
+}
+
+int xchg_fir_total(tgp_ctx* h, unsigned long long epoch, double* dst_dev) {
+    XchgState* x = (XchgState*)h->xchg;
+    if (!x || !x->d_peers) return fail(h, TGP_EINVAL, "exchange not opened");
+    TGP_K(h, "k_fir_lml_total");
+    k_fir_lml_total<<<1, 128, 0, h->stream>>>(x->self, x->fir_off, x->world, epoch, dst_dev);
+    TGP_LAUNCH_CHECK(h);
+    return TGP_OK;
+}
+
+bool xchg_fir_view(tgp_ctx* h, XchgFirView* v) {
+    XchgState* x = (XchgState*)h->xchg;
+    if (!x || !x->d_peers) return false;
+    v->peers = x->d_peers;
+    v->self = x->self;
+    v->prev = x->rank > 0 ? x->peers[x->rank - 1] : nullptr;
+    v->next = x->rank + 1 < x->world ? x->peers[x->rank + 1] : nullptr;
+    v->fir_off = x->fir_off;
+    v->world = x->world;
+    v->rank = x->rank;
+    v->epoch = &x->fir_epoch;
+    return true;
 }
 
 bool xchg_view(tgp_ctx* h, XchgView* v) {

@@ -1,21 +1,21 @@
 """
 sharded.py — time-sharded logpdf over several GPUs, one process per GPU.
 
-Rank r owns steps [r*T, (r+1)*T) of ONE series. Phase 1 folds the shard into one scan element
-(tgp_shard_reduce); the elements are all-gathered (`world` x (3D^2+2D) doubles: 264 B per rank at
-D = 3) over NCCL/NVLink; every rank folds the elements of the ranks before it into x0
-(tgp_shard_prefix) to obtain the filtering distribution entering its shard; phase 2 is the ordinary
-tgp_logpdf on the shard from that state; the partial log-likelihoods are summed with one all-reduce.
-The reference has no analogue (single-threaded); host logic only here — arithmetic is in the library.
+Rank r owns steps [b[r], b[r+1]) of ONE series. Three routes, chosen COLLECTIVELY (every rank runs the same one):
 
-Time-invariant models (RegularSpacing + homoscedastic noise) take the steady-state route instead: the exchange is one
-affine record (Phi, Z) of D*D + D doubles per rank, produced and consumed on the device, so a step is
-[tgp_shard_phase1] -> all_gather -> [tgp_shard_phase2] -> all_reduce on ONE stream with no host round trip in between.
+  "fir"      time-invariant models within the range of tgp_shard_logpdf (the path BASELINE config 4 runs): one kernel launch per
+             shard and call, nothing else. Rank 0 runs the covariance transient; rank r > 0 starts from the <= 3072 observations
+             that precede its shard, which rank r - 1's kernel stores into r's exchange buffer over NVLink when it STARTS, so no
+             shard ever waits for another shard's result. The partial log-likelihoods land in every rank's buffer; `result()`
+             sums them (fixed order) when the caller wants the number.
+  "steady"   time-invariant models the first route declines (filters with a long memory): tgp_shard_phase1 -> all_gather of one
+             affine record (D*D + D doubles) per rank -> tgp_shard_phase2 -> all_reduce, on ONE stream, no host round trip.
+  "general"  everything else: tgp_shard_reduce folds the shard into one scan element (3D^2 + 2D doubles), all_gather, every rank
+             folds the elements before it into x0 (tgp_shard_prefix), ordinary tgp_logpdf from that state, all_reduce.
+
+The reference has no analogue (single-threaded); host logic only here — arithmetic is in the library.
 """
 from __future__ import annotations
-
-import copy
-import ctypes as C
 
 import numpy as np
 
@@ -34,8 +34,17 @@ def incoming_state(prefix_fn, D, elems, rank, m0, P0):
     return prefix_fn(D, elems[:rank] if rank else None, m0, P0)
 
 
+def agree(dist, world, flag: bool) -> bool:
+    """True iff `flag` is true on every rank (the route must be the same everywhere, or the collectives mismatch)."""
+    if world == 1 or dist is None:
+        return bool(flag)
+    flags = [None] * world
+    dist.all_gather_object(flags, bool(flag))
+    return all(flags)
+
+
 class ShardedLogpdf:
-    def __init__(self, handle, marshalled, rank, world, device, dist=None):
+    def __init__(self, handle, marshalled, rank, world, device, dist=None, route=None):
         import torch
         self.torch = torch
         if dist is None:
@@ -53,71 +62,85 @@ class ShardedLogpdf:
             handle.set_stream(st.cuda_stream)
         self.D = marshalled.D
         self.ES = 3 * self.D * self.D + 2 * self.D
+        self.XS = self.D * self.D + self.D
         self.elem = torch.zeros(self.ES, dtype=torch.float64, device=device)
         self.all = torch.zeros(world * self.ES, dtype=torch.float64, device=device)
         self.part = torch.zeros(1, dtype=torch.float64, device=device)
+        self.rec = torch.zeros(self.XS, dtype=torch.float64, device=device)
+        self.recs = torch.zeros(world * self.XS, dtype=torch.float64, device=device)
         self.m0 = np.array(marshalled.keep[-2])
         self.P0 = np.array(marshalled.keep[-1])
         self.desc2 = type(marshalled.desc).from_buffer_copy(marshalled.desc)   # ctypes structs with pointers cannot be copy.copy'd
         self._ybuf = None
+        self._deferred_on = False
         d = marshalled.desc
-        self.time_invariant = not (d.sA or d.sa or d.sQ or d.sH or d.sh or d.sR) and d.ordering == 0 and d.T >= 65536
-        XS = self.D * self.D + self.D
-        self.XS = XS
-        if self.time_invariant:
-            from ._lib import TGP_OPT_DEFER_STATUS
-            handle.set_option(TGP_OPT_DEFER_STATUS, 1)
-        self.rec = torch.zeros(XS, dtype=torch.float64, device=device)
-        self.recs = torch.zeros(world * XS, dtype=torch.float64, device=device)
-        # Exchange transport of the steady route: "p2p" = the library's peer-memory kernels (NVLink / NVSwitch stores + flags,
-        # tgp_xchg_*), "nccl" = all_gather + all_reduce. p2p needs CUDA IPC between the ranks' GPUs; fall back if it is unavailable.
-        import os
-        self.transport = "nccl"
-        self.fused = os.environ.get("TGP_SHARD_FUSED", "1") == "1"     # one-launch form of the p2p step (tgp_shard_step)
-        if self.time_invariant and world > 1 and device.type == "cuda" and os.environ.get("TGP_XCHG", "p2p") == "p2p":
-            mine, err = None, None
-            try:
-                mine = handle.xchg_create(rank, world, max(XS, 16))
-            except Exception as exc:      # noqa: BLE001 — reported below, NCCL is used instead
-                err = str(exc)
-            handles = [None] * world
-            dist.all_gather_object(handles, mine)          # once per run: 64-byte CUDA IPC handles, any backend
-            ok = False
-            if all(hd is not None for hd in handles):
-                try:
-                    handle.xchg_open(b"".join(handles))
-                    ok = True
-                except Exception as exc:  # noqa: BLE001
-                    err = str(exc)
-            oks = [None] * world
-            dist.all_gather_object(oks, ok)                # every rank must agree on the transport
-            self.transport_error = err
-            if all(oks):
-                self.transport = "p2p"
+        ti = not (d.sA or d.sa or d.sQ or d.sH or d.sh or d.sR) and d.ordering == 0
+        # ---- route, decided collectively --------------------------------------------------------------------------------
+        self.transport_error = None
+        self.route = "general"
+        cuda = getattr(device, "type", "cpu") == "cuda"
+        if route in (None, "fir") and cuda and agree(dist, world, ti and self.D <= 4 and d.M == 1 and d.T >= 4096):
+            ok = True
+            if world > 1:
+                ok = self._open_exchange()
+            if ok:
+                self.route = "fir"
+        if self.route != "fir" and route in (None, "fir", "steady") and agree(dist, world, ti and d.T >= 65536 and self.D <= 6):
+            self.route = "steady"
+        if route == "general":
+            self.route = "general"
 
-    def logpdf(self, y_dev, lml_out_dev, sync=True):
-        """y_dev: this rank's shard, resident on its GPU. lml_out_dev: 1-element CUDA tensor (all ranks get the total).
-        sync=False (steady route): nothing waits on the host — the call is only ENQUEUED on the stream, consecutive calls queue
-        back to back, and the shard's status (convergence, positive-definiteness) accumulates on the device until check()."""
+    def _open_exchange(self) -> bool:
+        """CUDA IPC handles of the ranks' exchange buffers, gathered once. False (on every rank) if peer memory is unavailable."""
+        h, dist, world = self.h, self.dist, self.world
+        mine, err = None, None
+        try:
+            mine = h.xchg_create(self.rank, world, 16)
+        except Exception as exc:      # noqa: BLE001 — reported in transport_error, another route is used instead
+            err = str(exc)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)          # once per run: 64-byte CUDA IPC handles, any backend
+        ok = False
+        if all(hd is not None for hd in handles):
+            try:
+                h.xchg_open(b"".join(handles))
+                ok = True
+            except Exception as exc:  # noqa: BLE001
+                err = str(exc)
+        self.transport_error = err
+        return agree(dist, world, ok)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def logpdf(self, y_dev, lml_out_dev=None, sync=True):
+        """y_dev: this rank's shard, resident on its GPU. lml_out_dev: 1-element CUDA tensor receiving the total (all ranks), or
+        None to leave the total to a later result() call (route "fir": the step is then exactly one kernel launch).
+        sync=False: nothing waits on the host; failures surface at check()."""
         h, dist = self.h, self.dist
-        if self.time_invariant and self.transport == "p2p" and self.fused:
-            # ONE cooperative launch per shard: phase 1 -> record over NVLink -> wait for the predecessors -> phase 2 -> partial lml
-            h.shard_step(self.mm.desc, y_dev, self.rank, self.world, self.part)
-            h.xchg_wait(1, 1, lml_out_dev, 1)               # sum of the partial log-likelihoods, on every rank
+        if self.route == "fir":
+            try:
+                h.shard_logpdf(self.mm.desc, y_dev, self.rank, self.world)
+            except Exception as exc:                     # the plan declined this model (the same decision on every rank)
+                if getattr(exc, "code", None) != 5:      # TGP_EUNSUPPORTED
+                    raise
+                d = self.mm.desc
+                self.route = "steady" if (d.T >= 65536 and self.D <= 6) else "general"
+                return self.logpdf(y_dev, lml_out_dev, sync)
+            if lml_out_dev is not None:
+                h.shard_result(lml_out_dev)
             if sync:
                 h.synchronize()
             return
-        if self.time_invariant:
+        if lml_out_dev is None:
+            lml_out_dev = self.part
+        if self.route == "steady":
+            if not self._deferred_on:
+                from ._lib import TGP_OPT_DEFER_STATUS
+                h.set_option(TGP_OPT_DEFER_STATUS, 1)
+                self._deferred_on = True
             h.shard_phase1(self.mm.desc, y_dev, self.rank, self.world, self.rec)
-            if self.transport == "p2p":
-                # with an exchange open the shard kernels ship / await the records themselves (NVLink stores + flags inside
-                # k_ss_main): phase 1 puts, phase 2 waits for the ranks before it and puts its partial log-likelihood
-                h.shard_phase2(self.recs, self.part)        # enqueued, not synchronised
-                h.xchg_wait(1, 1, lml_out_dev, 1)           # sum of the partial log-likelihoods, on every rank
-            else:
-                dist.all_gather_into_tensor(self.recs, self.rec)
-                h.shard_phase2(self.recs, lml_out_dev)     # enqueued, not synchronised
-                dist.all_reduce(lml_out_dev)
+            dist.all_gather_into_tensor(self.recs, self.rec)
+            h.shard_phase2(self.recs, lml_out_dev)     # enqueued, not synchronised
+            dist.all_reduce(lml_out_dev)
             if sync:
                 h.synchronize()                         # status of the shard (convergence, positive-definiteness)
             return
@@ -128,20 +151,39 @@ class ShardedLogpdf:
         self._keep = (np.ascontiguousarray(m_in), np.ascontiguousarray(P_in))
         self.desc2.m0 = self._keep[0].ctypes.data
         self.desc2.P0 = self._keep[1].ctypes.data
-        h.logpdf(self.desc2, y_dev, self.part)
-        dist.all_reduce(self.part)
-        lml_out_dev.copy_(self.part)
+        part = self.torch.zeros(1, dtype=self.torch.float64, device=self.dev)
+        h.logpdf(self.desc2, y_dev, part)
+        dist.all_reduce(part)
+        lml_out_dev.copy_(part)
+
+    def result(self, lml_out_dev):
+        """Total log-likelihood of the LAST logpdf() call into a 1-element CUDA tensor (stream-ordered)."""
+        if self.route == "fir":
+            self.h.shard_result(lml_out_dev)
+        else:
+            lml_out_dev.copy_(self.part)
 
     def check(self):
         """Wait for the stream and raise if any un-synchronised call since the last check failed."""
         self.h.synchronize()
+
+    def close(self):
+        if self._deferred_on:
+            from ._lib import TGP_OPT_DEFER_STATUS
+            self.h.set_option(TGP_OPT_DEFER_STATUS, 0)
+            self._deferred_on = False
 
     def logpdf_host(self, y_host_pinned):
         """End-to-end variant: the shard's observations start in pinned host memory."""
         torch = self.torch
         if self._ybuf is None or self._ybuf.numel() != len(y_host_pinned):
             self._ybuf = torch.empty(len(y_host_pinned), dtype=torch.float64, device=self.dev)
+            self._out = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._ybuf.copy_(torch.from_numpy(y_host_pinned), non_blocking=True)
-        out = torch.zeros(1, dtype=torch.float64, device=self.dev)
-        self.logpdf(self._ybuf, out)
-        return float(out.item())
+        self.logpdf(self._ybuf, self._out)
+        return float(self._out.item())
+
+    @property
+    def h2d_bytes_per_host_call(self):
+        """Bytes logpdf_host moves to the device per call through torch (not counted by the library's own counters)."""
+        return 0 if self._ybuf is None else self._ybuf.numel() * 8
