@@ -220,7 +220,7 @@ __device__ __noinline__ double fir_tile_guarded(const FirPlan<D>& pl, const doub
 #pragma unroll
     for (int j = 0; j < kFirL; ++j) {
         const int e = lane * kFirL + j;
-        yv[j] = e < nvalid ? __ldg(ys + e) : 0.0;
+        yv[j] = e < nvalid ? __ldcg(ys + e) : 0.0;      // L2 (the halo ring is rewritten by a PEER between calls: never through L1)
     }
     return fir_tile_compute<D, true>(pl, yv, r, nvalid, pub, full, splane, sring, lane);
 }

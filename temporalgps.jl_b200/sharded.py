@@ -93,6 +93,8 @@ class ShardedLogpdf:
     def _open_exchange(self) -> bool:
         """CUDA IPC handles of the ranks' exchange buffers, gathered once. False (on every rank) if peer memory is unavailable."""
         h, dist, world = self.h, self.dist, self.world
+        if getattr(h, "_xchg_opened", None) == (self.rank, world):   # one exchange per handle, shared by every ShardedLogpdf on it
+            return agree(dist, world, True)
         mine, err = None, None
         try:
             mine = h.xchg_create(self.rank, world, 16)
@@ -108,7 +110,10 @@ class ShardedLogpdf:
             except Exception as exc:  # noqa: BLE001
                 err = str(exc)
         self.transport_error = err
-        return agree(dist, world, ok)
+        ok = agree(dist, world, ok)
+        if ok:
+            h._xchg_opened = (self.rank, world)
+        return ok
 
     # ------------------------------------------------------------------------------------------------------------------
     def logpdf(self, y_dev, lml_out_dev=None, sync=True):
