@@ -204,6 +204,8 @@ int tgp_xchg_wait(tgp_handle h, int channel, int n, double* dst, int mode);
  * decision on every rank) for models outside the path's range: use tgp_shard_phase1/2 or tgp_shard_reduce/prefix then. */
 int tgp_shard_logpdf(tgp_handle h, const tgp_lgssm* shard, const double* y, int rank, int world);
 int tgp_shard_result(tgp_handle h, double* lml_total);
+/* This rank's own term of that sum: log p(y_shard | everything before the shard) of the LAST tgp_shard_logpdf (device or host pointer). */
+int tgp_shard_partial(tgp_handle h, double* lml_shard);
 
 #ifdef __cplusplus
 }

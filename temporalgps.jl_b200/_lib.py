@@ -80,6 +80,7 @@ _SIGS = {
     "tgp_synchronize": (C.c_int, [C.c_void_p]),
     "tgp_shard_logpdf": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_int, C.c_int]),
     "tgp_shard_result": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tgp_shard_partial": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tgp_xchg_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tgp_xchg_open": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tgp_xchg_put": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -234,6 +235,9 @@ class Handle:
 
     def shard_result(self, lml_total):
         self.check(lib().tgp_shard_result(self._h, ptr(lml_total)))
+
+    def shard_partial(self, lml_shard):
+        self.check(lib().tgp_shard_partial(self._h, ptr(lml_shard)))
 
     def synchronize(self):
         self.check(lib().tgp_synchronize(self._h))

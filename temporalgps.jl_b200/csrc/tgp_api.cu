@@ -333,6 +333,22 @@ int tgp_shard_logpdf(tgp_handle h, const tgp_lgssm* shard, const double* y, int 
     return TGP_OK;
 }
 
+int tgp_shard_partial(tgp_handle h, double* lml_shard) {
+    if (!h || !lml_shard) return TGP_EINVAL;
+    TGP_CUDA(h, cudaSetDevice(h->device));
+    if (!h->fir.result || h->fir.epoch == 0) return fail(h, TGP_EINVAL, "tgp_shard_partial without a tgp_shard_logpdf");
+    const double* src = h->fir.result + 4 * (h->fir.epoch & 1ull);
+    if (is_device_ptr(lml_shard)) {
+        TGP_CUDA(h, cudaMemcpyAsync(lml_shard, src, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        TGP_CUDA(h, cudaMemcpyAsync(h->pinned + 8, src, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        TGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->d2h += 8;
+        *lml_shard = h->pinned[8];
+    }
+    return TGP_OK;
+}
+
 int tgp_shard_result(tgp_handle h, double* lml_total) {
     if (!h || !lml_total) return TGP_EINVAL;
     TGP_CUDA(h, cudaSetDevice(h->device));

@@ -606,12 +606,12 @@ int do_shard_logpdf(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, i
         char* mine = v.self + v.fir_off;
         if (rank > 0) {
             x.halo = reinterpret_cast<const double*>(mine + L::halo_off(ep));
-            x.halo_flag = reinterpret_cast<const unsigned long long*>(mine + L::halo_flag_off());
+            x.halo_flag = reinterpret_cast<const unsigned long long*>(mine + L::halo_flag_off(ep));
             x.ack_out = reinterpret_cast<unsigned long long*>(v.prev + v.fir_off + L::ack_off());
         }
         if (v.next) {
             x.push_dst = reinterpret_cast<double*>(v.next + v.fir_off + L::halo_off(ep));
-            x.push_flag = reinterpret_cast<unsigned long long*>(v.next + v.fir_off + L::halo_flag_off());
+            x.push_flag = reinterpret_cast<unsigned long long*>(v.next + v.fir_off + L::halo_flag_off(ep));
             x.ack_in = reinterpret_cast<const unsigned long long*>(mine + L::ack_off());
             x.ring = L::kRing;
         }

@@ -67,6 +67,8 @@ struct FirArgs {
     double* result;               // lml of this shard (device)
     double* lml_user;             // caller's device destination, nullable
     unsigned stagger_ns;          // initial delay between the four warp groups of a CTA (0: none)
+    int early_trigger;            // let the next call's CTAs in as this call's CTAs leave (only when a call fills every SM: then at most
+                                  // two calls are ever in flight, which is what the parity-indexed workspace allows)
     FirXchg x;
 };
 
@@ -74,7 +76,7 @@ template <int D>
 struct FirSmem {
     static constexpr int o_plane = kFirWarps * kFirBufDoubles;
     static constexpr int o_ring = o_plane + D * D * 32 + ((D * D * 32) & 1);   // 16-byte words {value, tag}
-    static constexpr int o_red = o_ring + 2 * (kFirRing + kFirNbMax) * D;
+    static constexpr int o_red = o_ring + 2 * (kFirRing + 2 * kFirNbMax) * D;
     static constexpr int o_scan = o_red + kFirWarps + 2;                 // transient: per-warp affine maps (D*D + D each)
     static constexpr size_t bytes = (size_t)(o_scan + kFirWarps * (D * D + D)) * sizeof(double);
 };
@@ -86,6 +88,20 @@ __device__ __forceinline__ unsigned long long fir_policy_evict_first() {
 }
 __device__ __forceinline__ void fir_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void fir_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// Waits on another warp / another GPU give up (trap: the caller sees a CUDA error instead of a hung device) only after kFirGiveUpNs.
+constexpr unsigned long long kFirGiveUpNs = 120ull * 1000000000ull;
+__device__ __forceinline__ unsigned long long fir_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void fir_spin_check(unsigned& spins, unsigned long long& t0) {
+    if ((++spins & 4095u) == 0u) {
+        const unsigned long long now = fir_now_ns();
+        if (t0 == 0ull) t0 = now;
+        else if (now - t0 > kFirGiveUpNs) __trap();
+    }
+}
 __device__ __forceinline__ unsigned long long fir_ld_sys(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -123,10 +139,11 @@ template <int D> __device__ __forceinline__ Vec<D> fir_shfl_up(const Vec<D>& v, 
 
 // The shared-memory ring of tile words: entry r (= tile index relative to the chunk + kFirNbMax) holds the zero-state response of
 // that tile (or, for r < kFirNbMax, what precedes the chunk); tag[r % kFirRing] == r once it is there.
-// Entries r < kFirNbMax (what precedes the chunk) have fixed slots; the tiles of the chunk share the ring. An entry is D 16-byte words
+// Entries r < 2 kFirNbMax (what precedes the chunk, and the chunk's first tiles: on a shard with rank > 0 their pass B runs last)
+// have fixed slots; the other tiles of the chunk share the ring. An entry is D 16-byte words
 // {value, tag = r}: one 128-bit shared-memory store per word, so a reader that sees the tag sees the value — no fence (a fence here
 // would also wait for the warp's cp.async copies in flight).
-__device__ __forceinline__ int fir_slot(int r) { return r < kFirNbMax ? r : kFirNbMax + ((r - kFirNbMax) % kFirRing); }
+__device__ __forceinline__ int fir_slot(int r) { return r < 2 * kFirNbMax ? r : 2 * kFirNbMax + ((r - 2 * kFirNbMax) % kFirRing); }
 __device__ __forceinline__ void fir_st_word(double2* p, double v, int tag) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(p);
     asm volatile("st.volatile.shared.v2.f64 [%0], {%1, %2};" ::"r"(sa), "d"(v), "d"(__longlong_as_double((long long)tag)) : "memory");
@@ -185,10 +202,11 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double 
         const double2* wptr = sring + fir_slot(want) * D + lane % D;
         int tag;
         unsigned spins = 0;
+        unsigned long long t0 = 0ull;
         for (;;) {
             fir_ld_word(wptr, val, tag);
             if (tag == want) break;
-            if (++spins > (1u << 26)) __trap();        // cannot happen short of a lost peer rank (halo): fail loudly, do not hang
+            fir_spin_check(spins, t0);                 // cannot end short of a lost peer rank (halo): fail loudly, do not hang
             __nanosleep(20);
         }
     }
@@ -361,7 +379,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     const long long G = gridDim.x, b = blockIdx.x;
     // Programmatic dependent launch: the next call's CTAs may take an SM as soon as this call's CTA leaves it (the calls share
     // nothing: counters / partials / result alternate by call parity).
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (ar.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const double* __restrict__ ys = ar.y + pl.N0;
     const long long Ts = pl.T - pl.N0;
     const long long ntiles = pl.ntiles;
@@ -393,7 +411,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     else if (n_fast > 0) fir_issue_tile(buf, yt, lane, pol);            // first tile on its way before anything else
     fir_cp_commit();
     for (int i = tid; i < D * D * 32; i += kFirThreads) splane[i] = __ldg(ar.plane + i);
-    for (int i = tid; i < (kFirRing + kFirNbMax) * D; i += kFirThreads) fir_st_word(sring + i, 0.0, -1);
+    for (int i = tid; i < (kFirRing + 2 * kFirNbMax) * D; i += kFirThreads) fir_st_word(sring + i, 0.0, -1);
     __syncthreads();
     // ---- what precedes the chunk --------------------------------------------------------------------------------------
     if (b == 0 && !exch_halo) {
@@ -415,8 +433,9 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         // the last nb tiles of this shard -> the successor's halo ring slot (NVLink stores), then its flag
         if (lane == 0 && ar.x.ack_in && ar.epoch > ar.x.ring) {
             unsigned spins = 0;
+            unsigned long long t0 = 0ull;
             while (fir_ld_sys(ar.x.ack_in) + ar.x.ring < ar.epoch) {
-                if (++spins > (1u << 26)) __trap();
+                fir_spin_check(spins, t0);
                 __nanosleep(100);
             }
         }
@@ -457,10 +476,11 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     if (exch_halo && wp == 0) {
         // the halo: wait for the predecessor's push, pass A over its nb tiles, tell the predecessor the slot is free
         if (ar.x.halo_flag) {
-            if (lane == 0) {
+            if (lane == 0) {      // the flag of THIS epoch's ring slot
                 unsigned spins = 0;
-                while (fir_ld_sys(ar.x.halo_flag) < ar.epoch) {
-                    if (++spins > (1u << 26)) __trap();
+                unsigned long long t0 = 0ull;
+                while (fir_ld_sys(ar.x.halo_flag) != ar.epoch) {
+                    fir_spin_check(spins, t0);
                     __nanosleep(100);
                 }
             }
@@ -469,10 +489,6 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         }
         for (int k = pl.nb; k >= 1; --k)
             fir_tile_guarded<D>(pl, ar.x.halo + (size_t)(pl.nb - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, sring, lane);
-        if (ar.x.ack_out && lane == 0) {
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned long long*>(ar.x.ack_out) = ar.epoch;
-        }
     }
     if (deferred)
         q += fir_tile_guarded<D>(pl, ys + (c0 + wp) * kFirTile, wp + kFirNbMax, (int)min(Ts - (c0 + wp) * kFirTile, (long long)kFirTile), false, true,
@@ -488,6 +504,11 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         double t = 0.0;
 #pragma unroll
         for (int i = 0; i < kFirWarps; ++i) t += sred[i];
+        // No CTA of this call leaves before the PREVIOUS call on the stream has completed (a no-op without programmatic dependent
+        // launch): with that, the call after this one — which can only start once every CTA of this one has started, i.e. once SMs
+        // have been vacated — never overlaps the previous one, so at most two calls are in flight and the parity-indexed
+        // counters / partials / result below (and the exchange ring) are never shared by two live calls.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         __stcg(ar.partials + b, t);
         if (b == 0 && exch_halo) __stcg(ar.partials + G, 0.0);
         __threadfence();
@@ -511,6 +532,10 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         *ar.result = lml;
         if (ar.lml_user) *ar.lml_user = lml;
         ar.counters[0] = 0u;
+        if (ar.x.ack_out) {    // the halo of this call has been consumed (and so have those of all earlier calls: see the wait above)
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long*>(ar.x.ack_out) = ar.epoch;
+        }
         if (ar.x.peers) {      // partial log-likelihood of this shard -> every rank's buffer, then the flags
             for (int p = 0; p < ar.x.world; ++p) *reinterpret_cast<volatile double*>(ar.x.peers[p] + ar.x.lml_off) = lml;
             __threadfence_system();
@@ -611,6 +636,7 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     if (stagger < 0) { const char* e = getenv("TGP_FIR_STAGGER"); stagger = e ? atoi(e) : 0; }
     if (pdl < 0) { const char* e = getenv("TGP_FIR_PDL"); pdl = e ? atoi(e) : 1; }
     ar.stagger_ns = (unsigned)stagger;
+    ar.early_trigger = (pdl && (int)G == h->sm_count) ? 1 : 0;
     TGP_K(h, "k_fir_logpdf");
     constexpr size_t smem = FirSmem<D>::bytes;
     static bool attr_set[64] = {false};

@@ -31,4 +31,4 @@ sh.result(out); sh.check(); torch.cuda.synchronize()
 print("rank", rank, "pipelined rel", abs(float(out.item()) - ref) / abs(ref), flush=True)
 dist.barrier(); dist.destroy_process_group()
 PY
-for T in 4000000 20000000; do TGP_ROOT=/root/repo TGP_T=$T OMP_NUM_THREADS=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29541 /tmp/worker2.py 2>&1 | grep -v Warning | grep "rel\|Error\|error" | head -12; done
+for T in ${TS:-4000000 20000000}; do TGP_ROOT=/root/repo TGP_T=$T OMP_NUM_THREADS=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node=${NP:-2} --master-addr 127.0.0.1 --master-port 29541 /tmp/worker2.py 2>&1 | grep -v Warning | grep "rel\|Error\|error" | head -12; done
