@@ -387,7 +387,9 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     long long c0, c1;
     {
         const long long base = ntiles / G;
-        const long long t0 = (G > 1 && base >= 3 * kFirWarps) ? base - kFirWarps : base;     // tiles of CTA 0
+        // CTA 0 also runs the transient (rank 0: one round less) or, last, the halo and its first tiles' pass B (rank > 0: two less)
+        const long long less = (ar.x.halo ? 2 : 1) * kFirWarps;
+        const long long t0 = (G > 1 && base >= less + 2 * kFirWarps) ? base - less : base;   // tiles of CTA 0
         const long long rest = ntiles - t0;
         c0 = b == 0 ? 0 : t0 + (G > 1 ? rest * (b - 1) / (G - 1) : 0);
         c1 = b == 0 ? (G > 1 ? t0 : ntiles) : t0 + rest * b / (G - 1);
@@ -402,13 +404,39 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     const int n_fast = pl.aligned ? n_main - (last_partial ? 1 : 0) : 0;
     double* buf = smem + wp * kFirBufDoubles;
     const unsigned long long pol = fir_policy_evict_first();
-    const double* __restrict__ yt = ys + first * kFirTile;              // current tile of the fast loop
+    // ---- this warp's staged items, in order: [A] its deferred tile, pass A only; [B] its full tiles first, first + 16, ...;
+    // [C] (warp 0 of CTA 0 on a shard with rank > 0) the nb halo tiles, pass A only; [D] the deferred tile, pass B. ------------------
+    const int nA = (deferred && pl.aligned) ? 1 : 0, nC = (exch_halo && wp == 0 && pl.aligned) ? pl.nb : 0, nD = nA;
+    const int n_items = nA + n_fast + nC + nD;
+    struct Item { const double* src; int r; bool pub, full; };
+    auto item = [&](int it) -> Item {
+        if (it < nA) return Item{ys + (c0 + wp) * kFirTile, wp + kFirNbMax, true, false};
+        it -= nA;
+        if (it < n_fast) return Item{ys + (first + (long long)it * kFirWarps) * kFirTile, (int)(first - c0) + it * kFirWarps + kFirNbMax, true, true};
+        it -= n_fast;
+        if (it < nC) return Item{ar.x.halo + (size_t)it * kFirTile, kFirNbMax - (pl.nb - it), true, false};      // tile -(nb - it)
+        return Item{ys + (c0 + wp) * kFirTile, wp + kFirNbMax, false, true};
+    };
+    auto wait_halo = [&]() {      // the predecessor's push of THIS epoch's ring slot
+        if (ar.x.halo_flag) {
+            if (lane == 0) {
+                unsigned spins = 0;
+                unsigned long long t0 = 0ull;
+                while (fir_ld_sys(ar.x.halo_flag) != ar.epoch) {
+                    fir_spin_check(spins, t0);
+                    __nanosleep(100);
+                }
+            }
+            __syncwarp();
+            __threadfence_system();
+        }
+    };
     // CTAs b > 0: the last nb warps (they have a tile less than warps 0, 1 when the chunk is not a multiple of 16) first run pass A
     // over the nb tiles BEFORE the chunk (re-read from HBM) — staged like any other tile, and first in the queue.
     const int halo_k = (b > 0 && wp >= kFirWarps - pl.nb) ? kFirWarps - wp : 0;      // tile c0 - halo_k
     const bool halo_fast = halo_k > 0 && pl.aligned;
     if (halo_fast) fir_issue_tile(buf, ys + (c0 - halo_k) * kFirTile, lane, pol);
-    else if (n_fast > 0) fir_issue_tile(buf, yt, lane, pol);            // first tile on its way before anything else
+    else if (n_items > 0 && !(nA + n_fast == 0 && nC > 0)) fir_issue_tile(buf, item(0).src, lane, pol);   // first tile on its way before anything else
     fir_cp_commit();
     for (int i = tid; i < D * D * 32; i += kFirThreads) splane[i] = __ldg(ar.plane + i);
     for (int i = tid; i < (kFirRing + 2 * kFirNbMax) * D; i += kFirThreads) fir_st_word(sring + i, 0.0, -1);
@@ -424,7 +452,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
             __syncwarp();
             fir_read_tile(buf, lane, yv);
             __syncwarp();
-            fir_tile_compute<D, false>(pl, yv, kFirNbMax - halo_k, kFirTile, true, false, splane, sring, lane, buf, n_fast > 0 ? yt : nullptr, pol);
+            fir_tile_compute<D, false>(pl, yv, kFirNbMax - halo_k, kFirTile, true, false, splane, sring, lane, buf, n_items > 0 ? item(0).src : nullptr, pol);
         } else {
             fir_tile_guarded<D>(pl, ys + (c0 - halo_k) * kFirTile, kFirNbMax - halo_k, kFirTile, true, false, splane, sring, lane);
         }
@@ -450,22 +478,29 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     if (ar.stagger_ns && (wp >> 2)) __nanosleep((unsigned)(wp >> 2) * ar.stagger_ns);   // de-phase the 4 warps of each scheduler
     // ---- the chunk --------------------------------------------------------------------------------------------------------
     double q = 0.0;
-    int r = (int)(first - c0) + kFirNbMax;
-    if (deferred)
+    if (deferred && !pl.aligned)
         fir_tile_guarded<D>(pl, ys + (c0 + wp) * kFirTile, wp + kFirNbMax, (int)min(Ts - (c0 + wp) * kFirTile, (long long)kFirTile), true, false,
                             splane, sring, lane);
+    if (nA + n_fast == 0 && nC > 0) {      // nothing staged before the halo: its first tile could not be prefetched above
+        wait_halo();
+        fir_issue_tile(buf, item(0).src, lane, pol);
+        fir_cp_commit();
+    }
 #pragma unroll 1
-    for (int it = 0; it < n_fast; ++it) {
+    for (int it = 0; it < n_items; ++it) {
         double yv[kFirL];
+        const Item cur = item(it);
         fir_cp_wait_all();
         __syncwarp();
         fir_read_tile(buf, lane, yv);
         __syncwarp();
-        const double* __restrict__ next = it + 1 < n_fast ? yt + kFirWarps * kFirTile : nullptr;
-        q += pl.zero_mean ? fir_tile_compute<D, false, true>(pl, yv, r, kFirTile, true, true, splane, sring, lane, buf, next, pol)
-                          : fir_tile_compute<D, false, false>(pl, yv, r, kFirTile, true, true, splane, sring, lane, buf, next, pol);
-        yt += kFirWarps * kFirTile;
-        r += kFirWarps;
+        const double* __restrict__ next = nullptr;
+        if (it + 1 < n_items) {
+            if (nC > 0 && it + 1 == nA + n_fast) wait_halo();      // the next item is the first halo tile: its data must have arrived
+            next = item(it + 1).src;
+        }
+        q += pl.zero_mean ? fir_tile_compute<D, false, true>(pl, yv, cur.r, kFirTile, cur.pub, cur.full, splane, sring, lane, buf, next, pol)
+                          : fir_tile_compute<D, false, false>(pl, yv, cur.r, kFirTile, cur.pub, cur.full, splane, sring, lane, buf, next, pol);
     }
 #pragma unroll 1
     for (int it = n_fast; it < n_main; ++it) {      // unaligned series (all tiles) or the partial last tile
@@ -473,26 +508,16 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         q += fir_tile_guarded<D>(pl, ys + s0, (int)(first - c0) + it * kFirWarps + kFirNbMax, (int)min(Ts - s0, (long long)kFirTile), true, true,
                                  splane, sring, lane);
     }
-    if (exch_halo && wp == 0) {
-        // the halo: wait for the predecessor's push, pass A over its nb tiles, tell the predecessor the slot is free
-        if (ar.x.halo_flag) {
-            if (lane == 0) {      // the flag of THIS epoch's ring slot
-                unsigned spins = 0;
-                unsigned long long t0 = 0ull;
-                while (fir_ld_sys(ar.x.halo_flag) != ar.epoch) {
-                    fir_spin_check(spins, t0);
-                    __nanosleep(100);
-                }
-            }
-            __syncwarp();
-            __threadfence_system();
+    if (!pl.aligned) {
+        if (exch_halo && wp == 0) {
+            wait_halo();
+            for (int k = pl.nb; k >= 1; --k)
+                fir_tile_guarded<D>(pl, ar.x.halo + (size_t)(pl.nb - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, sring, lane);
         }
-        for (int k = pl.nb; k >= 1; --k)
-            fir_tile_guarded<D>(pl, ar.x.halo + (size_t)(pl.nb - k) * kFirTile, kFirNbMax - k, kFirTile, true, false, splane, sring, lane);
+        if (deferred)
+            q += fir_tile_guarded<D>(pl, ys + (c0 + wp) * kFirTile, wp + kFirNbMax, (int)min(Ts - (c0 + wp) * kFirTile, (long long)kFirTile), false,
+                                     true, splane, sring, lane);
     }
-    if (deferred)
-        q += fir_tile_guarded<D>(pl, ys + (c0 + wp) * kFirTile, wp + kFirNbMax, (int)min(Ts - (c0 + wp) * kFirTile, (long long)kFirTile), false, true,
-                                 splane, sring, lane);
     fir_cp_wait_all();
     // ---- fixed-order reductions; the last CTA to finish forms the log-likelihood ------------------------------------------
 #pragma unroll
