@@ -40,15 +40,14 @@ unsigned long long xchg_epoch(tgp_ctx* h, int ch);
 // Region of the exchange buffer used by the one-launch sharded logpdf (tgp_fir.cuh), identical on every rank:
 //   halo[4][3 * 1024] doubles   ring (by call epoch & 3) of the observations that precede this rank's shard, written by rank - 1
 //   halo_flag[4], ack           u64: epoch of the halo in each ring slot (written by rank - 1) / of the last halo rank + 1 has consumed
-//   lml[4][world] doubles       ring of the shards' log-likelihoods, lml_flag[world] u64: epoch of the last one written by each rank
+//   lml[4][world] 16-byte words ring of the shards' log-likelihoods: {value, epoch}, one 128-bit store each
 struct FirXchgLayout {
     static constexpr int kRing = 4, kHaloDoubles = 3 * 1024;
     static __host__ __device__ constexpr size_t halo_off(unsigned long long epoch) { return (size_t)(epoch & 3ull) * kHaloDoubles * sizeof(double); }
     static __host__ __device__ constexpr size_t halo_flag_off(unsigned long long epoch) { return (size_t)kRing * kHaloDoubles * sizeof(double) + (size_t)(epoch & 3ull) * 8; }
     static __host__ __device__ constexpr size_t ack_off() { return halo_flag_off(0) + 64; }
-    static __host__ __device__ constexpr size_t lml_off(int world, unsigned long long epoch, int rank) { return ack_off() + 64 + ((size_t)(epoch & 3ull) * world + rank) * sizeof(double); }
-    static __host__ __device__ constexpr size_t lml_flag_off(int world) { return ack_off() + 64 + (size_t)kRing * world * sizeof(double); }
-    static __host__ __device__ constexpr size_t bytes(int world) { return lml_flag_off(world) + (size_t)world * sizeof(unsigned long long) + 256; }
+    static __host__ __device__ constexpr size_t lml_off(int world, unsigned long long epoch, int rank) { return ack_off() + 64 + ((size_t)(epoch & 3ull) * world + rank) * 16; }
+    static __host__ __device__ constexpr size_t bytes(int world) { return lml_off(world, 3, world) + 256; }
 };
 struct XchgFirView { char* const* peers; char* self; char* prev; char* next; size_t fir_off; int world, rank; unsigned long long* epoch; };
 bool xchg_fir_view(tgp_ctx* h, XchgFirView* v);

@@ -617,7 +617,6 @@ int do_shard_logpdf(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, i
         }
         x.peers = v.peers;
         x.lml_off = v.fir_off + L::lml_off(world, ep, rank);
-        x.lml_flag_off = v.fir_off + L::lml_flag_off(world) + (size_t)rank * sizeof(unsigned long long);
         x.epoch = ep;
         x.rank = rank;
         x.world = world;

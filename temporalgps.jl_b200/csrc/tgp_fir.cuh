@@ -39,6 +39,7 @@ namespace tgp {
 
 constexpr int kFirThreads = 512;
 constexpr int kFirWarps = kFirThreads / 32;
+constexpr int kFirPushWarps = 4;                     // warps of the last CTA that copy the halo to the successor rank
 constexpr int kFirRing = 64;                          // tile words kept in shared memory (>= 2 rounds of 16 warps + look-back)
 constexpr int kFirRow = kFirL + 2;                    // doubles between the rows of a staging buffer
 constexpr int kFirBufDoubles = 32 * kFirRow;          // staging buffer of one warp
@@ -52,7 +53,7 @@ struct FirXchg {                  // time-sharded use (all null / 0 on a single 
     const unsigned long long* ack_in;      // own ack word: wait for >= epoch - ring before overwriting the ring slot
     unsigned long long ring;      // halo ring depth
     char* const* peers;           // mapped exchange buffers of all ranks: the partial log-likelihood goes to every peer
-    unsigned long long lml_off, lml_flag_off;   // byte offsets of this rank's lml slot (for this epoch) / flag inside a peer buffer
+    unsigned long long lml_off;   // byte offset of this rank's {lml, epoch} word (ring slot of this epoch) inside a peer buffer
     unsigned long long epoch;     // exchange epoch of this call (the same on every rank)
     int rank, world;
 };
@@ -374,8 +375,10 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     double2* sring = reinterpret_cast<double2*>(smem + SM::o_ring);
     double* sred = smem + SM::o_red;
     double* sscan = smem + SM::o_scan;
-    __shared__ int s_last;
+    __shared__ int s_last, s_push_cnt;
+    int* s_push = &s_push_cnt;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    if (tid == 0) s_push_cnt = 0;
     const long long G = gridDim.x, b = blockIdx.x;
     // Programmatic dependent launch: the next call's CTAs may take an SM as soon as this call's CTA leaves it (the calls share
     // nothing: counters / partials / result alternate by call parity).
@@ -457,9 +460,12 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
             fir_tile_guarded<D>(pl, ys + (c0 - halo_k) * kFirTile, kFirNbMax - halo_k, kFirTile, true, false, splane, sring, lane);
         }
     }
-    if (b == G - 1 && wp == kFirWarps - 1 && ar.x.push_dst) {
-        // the last nb tiles of this shard -> the successor's halo ring slot (NVLink stores), then its flag
-        if (lane == 0 && ar.x.ack_in && ar.epoch > ar.x.ring) {
+    // The last nb tiles of this shard -> the successor's halo ring slot: NVLink stores by the last kFirPushWarps warps of the last CTA at
+    // the START of the run; each of them fences after its first tile (the stores have landed by then: the fence is cheap) and the last
+    // one to do so raises the successor's flag — early in this kernel's life, long before the successor needs the halo.
+    const bool pusher = b == G - 1 && ar.x.push_dst != nullptr && wp >= kFirWarps - kFirPushWarps;
+    if (pusher) {
+        if (lane == 0 && ar.x.ack_in && ar.epoch > ar.x.ring) {      // the ring slot must have been consumed
             unsigned spins = 0;
             unsigned long long t0 = 0ull;
             while (fir_ld_sys(ar.x.ack_in) + ar.x.ring < ar.epoch) {
@@ -468,13 +474,16 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
             }
         }
         __syncwarp();
-        const long long n = (long long)pl.nb * kFirTile;
+        const int n = pl.nb * kFirTile;
         const double* src = ar.y + pl.T - n;
-        for (long long e = lane; e < n; e += 32) ar.x.push_dst[e] = __ldg(src + e);
+#pragma unroll 8
+        for (int e = (wp - (kFirWarps - kFirPushWarps)) * 32 + lane; e < n; e += kFirPushWarps * 32) ar.x.push_dst[e] = __ldg(src + e);
+    }
+    auto push_done = [&]() {
         __threadfence_system();
         __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(ar.x.push_flag) = ar.epoch;
-    }
+        if (lane == 0 && atomicAdd(s_push, 1) == kFirPushWarps - 1) *reinterpret_cast<volatile unsigned long long*>(ar.x.push_flag) = ar.epoch;
+    };
     if (ar.stagger_ns && (wp >> 2)) __nanosleep((unsigned)(wp >> 2) * ar.stagger_ns);   // de-phase the 4 warps of each scheduler
     // ---- the chunk --------------------------------------------------------------------------------------------------------
     double q = 0.0;
@@ -501,7 +510,9 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         }
         q += pl.zero_mean ? fir_tile_compute<D, false, true>(pl, yv, cur.r, kFirTile, cur.pub, cur.full, splane, sring, lane, buf, next, pol)
                           : fir_tile_compute<D, false, false>(pl, yv, cur.r, kFirTile, cur.pub, cur.full, splane, sring, lane, buf, next, pol);
+        if (pusher && it == 0) push_done();
     }
+    if (pusher && n_items == 0) push_done();
 #pragma unroll 1
     for (int it = n_fast; it < n_main; ++it) {      // unaligned series (all tiles) or the partial last tile
         const long long s0 = (first + (long long)it * kFirWarps) * kFirTile;
@@ -557,14 +568,13 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         *ar.result = lml;
         if (ar.lml_user) *ar.lml_user = lml;
         ar.counters[0] = 0u;
-        if (ar.x.ack_out) {    // the halo of this call has been consumed (and so have those of all earlier calls: see the wait above)
-            __threadfence_system();
+        if (ar.x.ack_out)      // the halo of this call has been consumed (and so have those of all earlier calls: see the wait above)
             *reinterpret_cast<volatile unsigned long long*>(ar.x.ack_out) = ar.epoch;
-        }
-        if (ar.x.peers) {      // partial log-likelihood of this shard -> every rank's buffer, then the flags
-            for (int p = 0; p < ar.x.world; ++p) *reinterpret_cast<volatile double*>(ar.x.peers[p] + ar.x.lml_off) = lml;
-            __threadfence_system();
-            for (int p = 0; p < ar.x.world; ++p) *reinterpret_cast<volatile unsigned long long*>(ar.x.peers[p] + ar.x.lml_flag_off) = ar.epoch;
+        if (ar.x.peers) {      // this shard's log-likelihood -> every rank's buffer: ONE 16-byte {value, epoch} store per peer, no fence
+            for (int p = 0; p < ar.x.world; ++p) {
+                double2* w = reinterpret_cast<double2*>(ar.x.peers[p] + ar.x.lml_off);
+                asm volatile("st.volatile.global.v2.f64 [%0], {%1, %2};" ::"l"(w), "d"(lml), "d"(__longlong_as_double((long long)ar.epoch)) : "memory");
+            }
         }
     }
 }

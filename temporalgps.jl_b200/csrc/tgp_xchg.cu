@@ -140,21 +140,24 @@ int xchg_wait(tgp_ctx* h, int ch, int n, double* dst, int mode) {
 // Sum of the shards' log-likelihoods of the sharded call with epoch `epoch` (ring slot epoch & 3): waits for every rank's flag.
 __global__ void __launch_bounds__(128) k_fir_lml_total(const char* __restrict__ self, size_t fir_off, int world, unsigned long long epoch,
                                                        double* __restrict__ dst) {
+    __shared__ double part[128];
     const char* base = self + fir_off;
-    if (threadIdx.x < world) {
-        const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(base + FirXchgLayout::lml_flag_off(world)) + threadIdx.x;
+    if (threadIdx.x < world) {      // {value, epoch}: written with one 128-bit store by rank threadIdx.x's kernel
+        const double2* w = reinterpret_cast<const double2*>(base + FirXchgLayout::lml_off(world, epoch, threadIdx.x));
+        double v, t;
         unsigned long long spins = 0;
-        while (*f < epoch) {
+        for (;;) {
+            asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "l"(w) : "memory");
+            if ((unsigned long long)__double_as_longlong(t) == epoch) break;
             if (++spins > (1ull << 31)) __trap();
             __nanosleep(50);
         }
+        part[threadIdx.x] = v;
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const double* v = reinterpret_cast<const double*>(base + FirXchgLayout::lml_off(world, epoch, 0));
         double s = 0.0;
-        for (int p = 0; p < world; ++p) s += __ldcg(v + p);     // fixed order: the same bits on every rank
+        for (int p = 0; p < world; ++p) s += part[p];     // fixed order: the same bits on every rank
         *dst = s;
     }
 }
