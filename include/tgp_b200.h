@@ -138,10 +138,16 @@ int tgp_posterior(tgp_handle h, const tgp_lgssm* model, const double* y,
  */
 int tgp_marginals(tgp_handle h, const tgp_lgssm* model, double* mean_out, double* cov_out);
 
+/* tgp_marginals_diag replaces marginals_diag(::LGSSM)  src/models/lgssm.jl:125-141
+ *              (step_marginals_diag with predict_marginals, LGC:63-68): the same recursion emitting only the diagonal of the
+ *              emission-space covariance: mean_out, var_out are T x M.
+ */
+int tgp_marginals_diag(tgp_handle h, const tgp_lgssm* model, double* mean_out, double* var_out);
+
 /* tgp_posterior_marginals fuses the chain used by marginals(::FinitePosteriorLTISDE) at the
  *              training inputs (src/gp/posterior_lti_sde.jl:27-36):
  *              posterior(model, y) -> replace_observation_noise_cov(., R_new) -> marginals(.)
- *              -> diagonal. The (G,g,Sig) dynamics are never materialised. R_new is per step with
+ *              -> diagonal. The (G,g,Sig) dynamics are never materialised (scalar observations). R_new is per step with
  *              stride sRnew (0 = constant) and the model's R_kind. Outputs mean_out, var_out: T x M.
  *              lml_out (nullable) receives logpdf(model, y) as a by-product of the forward pass.
  */

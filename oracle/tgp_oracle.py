@@ -533,6 +533,15 @@ def marginals(model: LGSSM):
     return means, covs
 
 
+def marginals_diag(model: LGSSM):
+    """marginals_diag(::LGSSM), lgssm.jl:125-141 with predict_marginals (linear_gaussian_conditionals.jl:63-68): the same recursion
+    as marginals(), emitting Gaussian(H m + h, Diagonal(diag(H P H') + diag(R)))."""
+    means, covs = marginals(model)
+    if model.scalar:
+        return means, covs
+    return means, np.einsum("tii->ti", covs).copy()
+
+
 def replace_observation_noise_cov(model: LGSSM, Rs_new) -> LGSSM:
     """missings.jl:35-41."""
     Rs_new = np.asarray(Rs_new, dtype=float)
@@ -554,12 +563,21 @@ def transform_model_and_obs(model: LGSSM, y):
         y[miss] = 0.0
         n_missing_dims = int(miss.sum())
     else:
-        miss = np.isnan(y).all(axis=1)
+        nan = np.isnan(y)
+        miss = nan.all(axis=1)
         M = y.shape[1]
-        Rs = np.array(model.Rs, copy=True)
+        Rs = np.array(np.broadcast_to(model.Rs, (model.T, M, M)), copy=True)
         Rs[miss] = LARGE_VAR * np.eye(M)
-        y[miss] = 0.0
         n_missing_dims = int(miss.sum()) * M
+        # element-wise missing (linear_gaussian_conditionals.jl:143-151 + missings.jl:76-79): Diagonal R only; the
+        # missing entries get variance 1e15 and observation 0, each adds log(2 pi 1e15) / 2
+        for t in np.nonzero(nan.any(axis=1) & ~miss)[0]:
+            if np.abs(Rs[t] - np.diag(np.diag(Rs[t]))).max() != 0.0:
+                raise TypeError("MethodError: element-wise missing observations need a Diagonal observation covariance")
+            for i in np.nonzero(nan[t])[0]:
+                Rs[t, i, i] = LARGE_VAR
+                n_missing_dims += 1
+        y[nan] = 0.0
     return replace_observation_noise_cov(model, Rs), y, n_missing_dims
 
 
@@ -722,6 +740,21 @@ def build_lgssm_separable(k_space: Kernel, k_time: Kernel, r, t, sigma2) -> LGSS
     Rs = np.stack([np.diag(v) for v in s2]) if not regular or np.ndim(sigma2) else np.broadcast_to(
         np.diag(s2[0]), (T, Nr, Nr))
     return LGSSM("forward", As, as_, Qs, m0, P0, Hs, hs, Rs)
+
+
+def dense_separable_posterior(k_space, k_time, r, t, sigma2, y, t_pr, sigma2_pr):
+    """Dense-GP posterior of a Separable(k_space, k_time) GP observed on RectilinearGrid(r, t) at RectilinearGrid(r, t_pr):
+    -> (mean, covariance incl. sigma2_pr), points ordered space-fastest (the naive side of test/space_time/to_gauss_markov.jl:68-87)."""
+    r = np.asarray(r, dtype=float)
+    tt, tp = _as_times(t), _as_times(t_pr)
+    Kr = kernelmatrix(k_space, r)
+    K = np.kron(kernelmatrix(k_time, tt), Kr) + sigma2 * np.eye(len(tt) * len(r))
+    Ks = np.kron(kernelmatrix(k_time, tp, tt), Kr)
+    Kss = np.kron(kernelmatrix(k_time, tp), Kr)
+    Lc = np.linalg.cholesky(K)
+    alpha = np.linalg.solve(Lc.T, np.linalg.solve(Lc, np.asarray(y, dtype=float).reshape(-1)))
+    V = np.linalg.solve(Lc, Ks.T)
+    return Ks @ alpha, Kss - V.T @ V + sigma2_pr * np.eye(len(tp) * len(r))
 
 
 def dense_separable_logpdf(k_space, k_time, r, t, sigma2, y):

@@ -69,6 +69,7 @@ _SIGS = {
     "tgp_posterior": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
     "tgp_marginals": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p]),
+    "tgp_marginals_diag": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p]),
     "tgp_posterior_marginals": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
     "tgp_debug_tc_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -215,6 +216,9 @@ class Handle:
 
     def marginals(self, desc, mean_out, cov_out):
         self.check(lib().tgp_marginals(self._h, C.byref(desc), ptr(mean_out), ptr(cov_out)))
+
+    def marginals_diag(self, desc, mean_out, var_out):
+        self.check(lib().tgp_marginals_diag(self._h, C.byref(desc), ptr(mean_out), ptr(var_out)))
 
     def posterior_marginals(self, desc, y, R_new, sRnew, mean_out, var_out, lml_out=None):
         self.check(lib().tgp_posterior_marginals(self._h, C.byref(desc), ptr(y), ptr(R_new), int(sRnew), ptr(mean_out),

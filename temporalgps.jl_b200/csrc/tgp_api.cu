@@ -255,8 +255,8 @@ int tgp_filter(tgp_handle h, const tgp_lgssm* model, const double* y, double* m_
 int tgp_posterior(tgp_handle h, const tgp_lgssm* model, const double* y, double* G, double* g, double* Sig, double* m_T,
                   double* P_T) {
     TGP_TRY(validate(h, model, true, y));
-    TGP_TRY(require_scalar_obs(h, model));
     TGP_TRY(begin_call(h));
+    if (!scan_shape(model) || model->ordering != TGP_FORWARD) return seq_posterior(h, model, y, G, g, Sig, m_T, P_T, nullptr);
 #define CALL(Dv) do_posterior<Dv>(h, model, y, G, g, Sig, m_T, P_T)
     TGP_DISPATCH_D(h, model->D)
 #undef CALL
@@ -264,10 +264,20 @@ int tgp_posterior(tgp_handle h, const tgp_lgssm* model, const double* y, double*
 
 int tgp_marginals(tgp_handle h, const tgp_lgssm* model, double* mean_out, double* cov_out) {
     TGP_TRY(validate(h, model, false, nullptr));
-    TGP_TRY(require_scalar_obs(h, model));
     if (!mean_out || !cov_out) return fail(h, TGP_EINVAL, "mean_out and cov_out must be non-NULL");
     TGP_TRY(begin_call(h));
+    if (!scan_shape(model)) return seq_marginals(h, model, mean_out, cov_out, 0);
 #define CALL(Dv) do_marginals<Dv>(h, model, mean_out, cov_out)
+    TGP_DISPATCH_D(h, model->D)
+#undef CALL
+}
+
+int tgp_marginals_diag(tgp_handle h, const tgp_lgssm* model, double* mean_out, double* var_out) {
+    TGP_TRY(validate(h, model, false, nullptr));
+    if (!mean_out || !var_out) return fail(h, TGP_EINVAL, "mean_out and var_out must be non-NULL");
+    TGP_TRY(begin_call(h));
+    if (!scan_shape(model)) return seq_marginals(h, model, mean_out, var_out, 1);
+#define CALL(Dv) do_marginals<Dv>(h, model, mean_out, var_out)      /* M == 1: the marginal covariance IS its diagonal */
     TGP_DISPATCH_D(h, model->D)
 #undef CALL
 }
@@ -275,10 +285,11 @@ int tgp_marginals(tgp_handle h, const tgp_lgssm* model, double* mean_out, double
 int tgp_posterior_marginals(tgp_handle h, const tgp_lgssm* model, const double* y, const double* R_new, int64_t sRnew,
                             double* mean_out, double* var_out, double* lml_out) {
     TGP_TRY(validate(h, model, true, y));
-    TGP_TRY(require_scalar_obs(h, model));
     if (!R_new || !mean_out || !var_out) return fail(h, TGP_EINVAL, "R_new, mean_out and var_out must be non-NULL");
     if (sRnew != 0 && sRnew < 1) return fail(h, TGP_EINVAL, "sRnew must be 0 or >= 1");
     TGP_TRY(begin_call(h));
+    if (!scan_shape(model) || model->ordering != TGP_FORWARD)
+        return seq_posterior_marginals(h, model, y, R_new, sRnew, mean_out, var_out, lml_out);
 #define CALL(Dv) do_posterior_marginals<Dv>(h, model, y, R_new, sRnew, mean_out, var_out, lml_out)
     TGP_DISPATCH_D(h, model->D)
 #undef CALL

@@ -25,6 +25,12 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
 
 void dense_release(tgp_ctx* h);   // frees the dense path's cuBLAS handle
 
+// Step-by-step smoother-side path for the shapes the scan kernels do not cover (tgp_seq.cu): vector observations, Reverse models.
+int seq_posterior(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* G, double* g, double* Sig, double* m_T, double* P_T, double* lml_out);
+int seq_marginals(tgp_ctx* h, const tgp_lgssm* m, double* mean_out, double* cov_out, int diag);
+int seq_posterior_marginals(tgp_ctx* h, const tgp_lgssm* m, const double* y, const double* R_new, int64_t sRnew, double* mean_out,
+                            double* var_out, double* lml_out);
+
 // Peer-memory exchange of the time-sharded path (tgp_xchg.cu).
 int xchg_create(tgp_ctx* h, int rank, int world, int slot_doubles, void* ipc_handle_out);
 int xchg_open(tgp_ctx* h, const void* handles_all);

@@ -184,9 +184,7 @@ __device__ bool seq_update(const SeqModel& md, long long t, const SeqSmem& w, do
     for (int e = seq_tid(); e < M * D; e += kSeqThreads) w.B[e] = w.V[e];
     __syncthreads();
     seq_trsm(w.S, M, w.B, M, D, true);                                   // B = U' \ V
-    if (seq_tid() == kSeqThreads - 1) seq_trsm_one:
-    {
-        // alpha = U' \ r by the last thread (a single right-hand side)
+    if (seq_tid() == kSeqThreads - 1) {      // alpha = U' \ r by the last thread (a single right-hand side)
         for (int i = 0; i < M; ++i) {
             double s = w.al[i];
             for (int k = 0; k < i; ++k) s = fma(-w.S[k + (size_t)M * i], w.al[k], s);

@@ -388,6 +388,9 @@ def marginals(fx):
     """-> (mean, var) of the marginals (lti_sde.jl:33-44, posterior_lti_sde.jl:18-37)."""
     if isinstance(fx, FinitePosteriorLTISDE):
         return _posterior_marginals(fx)
+    if _is_grid(fx.x):        # marginals_diag (lti_sde.jl:39-44): the diagonal of every time step's emission covariance
+        mu, v = L.marginals_diag(fx.build_lgssm(), fx._handle())
+        return mu.reshape(-1), v.reshape(-1)
     return L.marginals(fx.build_lgssm(), fx._handle())
 
 
@@ -428,7 +431,13 @@ def posterior(fx: FiniteLTISDE, y) -> PosteriorLTISDE:
     return PosteriorLTISDE(fx.f, y if isinstance(y, np.ma.MaskedArray) else np.asarray(y, dtype=np.float64), fx.x, fx.noise)
 
 
+def _is_grid(x):
+    return isinstance(x, RectilinearGrid)
+
+
 def _same_inputs(a, b):
+    if _is_grid(a) or _is_grid(b):
+        return (_is_grid(a) and _is_grid(b) and np.array_equal(np.asarray(a.xl), np.asarray(b.xl)) and _same_inputs(a.xr, b.xr))
     if isinstance(a, RegularSpacing) and isinstance(b, RegularSpacing):
         return a == b
     ta, tb = _times(a), _times(b)
@@ -441,45 +450,85 @@ def _nan_missing(y):
     return np.asarray(y, dtype=np.float64)
 
 
+def _time_axis(x):
+    """get_times (rectilinear_grid.jl:20)."""
+    return x.xr if _is_grid(x) else x
+
+
+def _obs_rows(x, y):
+    """observations_to_time_form (rectilinear_grid.jl:78-80): one row per time step; space varies fastest on a grid."""
+    y = _nan_missing(y)
+    return y.reshape(len(x.xr), len(x.xl)) if _is_grid(x) else y
+
+
+def _noise_rows(x, noise):
+    """noise_var_to_time_form (lti_sde.jl:82-86, rectilinear_grid.jl:90-93) as a dense per-time-step array."""
+    if not _is_grid(x):
+        return _dense(_noise_to_time_form(x, noise), len(x))
+    T, Nr = len(x.xr), len(x.xl)
+    if np.ndim(noise) == 0:
+        return np.full((T, Nr), float(noise))
+    noise = np.asarray(noise, dtype=np.float64)
+    if noise.ndim == 2:
+        noise = np.diag(noise)
+    return noise.reshape(T, Nr)
+
+
 def merge_datasets(x1, x2, S1, S2, y1, y2):
-    """posterior_lti_sde.jl:97-123 — stable sort in time. NaN marks missing internally; the result
-    is handed to the LGSSM layer as a masked array."""
-    x_raw = np.concatenate([_times(x1), _times(x2)])
+    """posterior_lti_sde.jl:97-123 (+ rectilinear_grid.jl:66-75 for grids) — stable sort in time. S1, S2, y1, y2 are per-time-step
+    rows (_noise_rows / _obs_rows). NaN marks missing internally; the result is handed to the LGSSM layer as a masked array."""
+    x_raw = np.concatenate([_times(_time_axis(x1)), _times(_time_axis(x2))])
     idx = np.argsort(x_raw, kind="stable")
     inv = np.argsort(idx, kind="stable")
-    n1 = len(x1)
-    S = np.concatenate([_dense(S1, n1), _dense(S2, len(x2))])[idx]
-    ys = np.concatenate([_nan_missing(y1), _nan_missing(y2)])[idx]
-    return x_raw[idx], S, np.ma.masked_invalid(ys), inv[:n1], inv[n1:]
+    n1 = len(_time_axis(x1))
+    S = np.concatenate([S1, S2])[idx]
+    ys = np.concatenate([y1, y2])[idx]
+    x = RectilinearGrid(x1.xl, x_raw[idx]) if _is_grid(x1) else x_raw[idx]
+    return x, S, np.ma.masked_invalid(ys), inv[:n1], inv[n1:]
+
+
+def _lgssm_noise(x, rows):
+    """Per-step noise rows -> what build_lgssm takes for x."""
+    return rows.reshape(-1) if _is_grid(x) else rows
 
 
 def _posterior_marginals(fx: FinitePosteriorLTISDE):
     post = fx.f
     h = post.prior.storage.handle()
+    flat = (lambda a: a.reshape(-1)) if _is_grid(fx.x) else (lambda a: a)
     if _same_inputs(fx.x, post.x):                       # posterior_lti_sde.jl:27-36
         model = build_lgssm(post.prior, post.x, post.noise)
-        return L.posterior_marginals(model, post.y, _noise_to_time_form(fx.x, fx.noise), h)
-    n_pr = len(fx.x)                                      # posterior_lti_sde.jl:19-26
-    x, S, ys, _tr, pr = merge_datasets(post.x, fx.x, _noise_to_time_form(post.x, post.noise), Fill(L.LARGE_VAR, n_pr),
-                                       post.y, np.full(n_pr, np.nan))
-    model = build_lgssm(post.prior, x, S)
-    R_pr = np.zeros(len(x))
-    R_pr[pr] = _dense(_noise_to_time_form(fx.x, fx.noise), n_pr)
+        Rn = _noise_rows(fx.x, fx.noise) if _is_grid(fx.x) else _noise_to_time_form(fx.x, fx.noise)     # a Fill stays a Fill
+        mu, v = L.posterior_marginals(model, post.y if not _is_grid(fx.x) else _masked_rows(post.x, post.y), Rn, h)
+        return flat(mu), flat(v)
+    n_pr = len(_time_axis(fx.x))                          # posterior_lti_sde.jl:19-26
+    S_tr = _noise_rows(post.x, post.noise)
+    x, S, ys, _tr, pr = merge_datasets(post.x, fx.x, S_tr, np.full((n_pr,) + S_tr.shape[1:], L.LARGE_VAR),
+                                       _obs_rows(post.x, post.y), np.full((n_pr,) + S_tr.shape[1:], np.nan))
+    model = build_lgssm(post.prior, x, _lgssm_noise(x, S))
+    R_pr = np.zeros(S.shape)
+    R_pr[pr] = _noise_rows(fx.x, fx.noise)
     mu, v = L.posterior_marginals(model, ys, R_pr, h)
-    return mu[pr], v[pr]
+    return flat(mu[pr]), flat(v[pr])
+
+
+def _masked_rows(x, y):
+    rows = _obs_rows(x, y)
+    return np.ma.masked_invalid(rows) if np.isnan(rows).any() else rows
 
 
 def _posterior_logpdf(fx: FinitePosteriorLTISDE, y_pr):
     """posterior_lti_sde.jl:62-78."""
     post = fx.f
     h = post.prior.storage.handle()
-    n_pr = len(fx.x)
-    S_pr = _noise_to_time_form(fx.x, fx.noise)
-    x, S, ys, tr, pr = merge_datasets(post.x, fx.x, _noise_to_time_form(post.x, post.noise), S_pr, post.y, np.full(n_pr, np.nan))
-    R_pr = np.zeros(len(x))
-    R_pr[pr] = _dense(S_pr, n_pr)
-    y_full = np.full(len(x), np.nan)
-    y_full[pr] = np.asarray(y_pr, dtype=np.float64)
-    model = build_lgssm(post.prior, x, S)
+    n_pr = len(_time_axis(fx.x))
+    S_pr = _noise_rows(fx.x, fx.noise)
+    x, S, ys, tr, pr = merge_datasets(post.x, fx.x, _noise_rows(post.x, post.noise), S_pr, _obs_rows(post.x, post.y),
+                                      np.full((n_pr,) + S_pr.shape[1:], np.nan))
+    R_pr = np.zeros(S.shape)
+    R_pr[pr] = S_pr
+    y_full = np.full(S.shape, np.nan)
+    y_full[pr] = _obs_rows(fx.x, y_pr)
+    model = build_lgssm(post.prior, x, _lgssm_noise(x, S))
     model_post = L.replace_observation_noise_cov(L.posterior(model, ys, h), R_pr)
     return L.logpdf(model_post, np.ma.masked_invalid(y_full), h)

@@ -179,23 +179,44 @@ def _host_y(y):
     return np.ascontiguousarray(y, dtype=np.float64)
 
 
-# ---- missing data (missings.jl:25-74): stays on the host, kernels see plain R_t ------------------
+# ---- missing data (missings.jl:25-74, LGC:143-151): stays on the host, kernels see plain R_t ------------------
 def transform_model_and_obs(model: LGSSM, y):
+    """-> (model with R := 1e15 where y is missing, y with 0 there, number of missing observation DIMENSIONS).
+    Scalar observations: masked == missing. Vector observations (T, M): a fully masked row is a missing observation (any R:
+    R_t := 1e15 I, missings.jl:59-74, 97); a partially masked row needs diagonal R (R_t[i] := 1e15 for the masked entries,
+    LGC:143-151 with missings.jl:76-79 — the reference raises a MethodError for dense R there)."""
     miss = np.ma.getmaskarray(y)
     y = np.array(np.ma.getdata(y), dtype=np.float64, copy=True)
     T = len(model)
-    Rs = model.emissions.Rs
-    Rs = np.full(T, float(Rs.value)) if isinstance(Rs, Fill) else np.array(Rs, dtype=np.float64, copy=True)
-    Rs[miss] = LARGE_VAR
+    em = model.emissions
+    Rs = em.Rs
+    if not isinstance(em, SmallOutputEmissions):
+        Rs = np.full(T, float(Rs.value)) if isinstance(Rs, Fill) else np.array(Rs, dtype=np.float64, copy=True)
+        Rs[miss] = LARGE_VAR
+        y[miss] = 0.0
+        return replace(model, emissions=replace(em, Rs=Rs)), y, int(miss.sum())
+    M = em.M
+    if miss.shape != (T, M):
+        raise DimensionMismatch(_lib.TGP_EINVAL, f"Dimension mismatch. y has shape {miss.shape}, the model emits {(T, M)}")
+    whole = miss.all(axis=1)
+    partial = miss.any(axis=1) & ~whole
+    dense = em.r_dense
+    if partial.any() and dense:
+        raise TGPError(_lib.TGP_EUNSUPPORTED, "element-wise missing observations need a Diagonal observation covariance "
+                                              "(linear_gaussian_conditionals.jl:143-151)")
+    Rv = Rs.value if isinstance(Rs, Fill) else None
+    if dense:
+        Rs = np.broadcast_to(Rv, (T, M, M)).copy() if Rv is not None else np.array(Rs, dtype=np.float64, copy=True)
+        Rs[whole] = LARGE_VAR * np.eye(M)
+    else:
+        Rs = np.broadcast_to(Rv, (T, M)).copy() if Rv is not None else np.array(Rs, dtype=np.float64, copy=True)
+        Rs[miss] = LARGE_VAR
     y[miss] = 0.0
-    new = replace(model, emissions=replace(model.emissions, Rs=Rs))
-    return new, y, int(miss.sum())
+    return replace(model, emissions=replace(em, Rs=Rs)), y, int(miss.sum())
 
 
 def _maybe_missing(model, y):
     if isinstance(y, np.ma.MaskedArray):          # dispatch on type, as missings.jl:8-23 does
-        if isinstance(model.emissions, SmallOutputEmissions):
-            raise TGPError(_lib.TGP_EUNSUPPORTED, "missing data with vector observations is not built yet")
         return transform_model_and_obs(model, y)
     return model, y, 0
 
@@ -247,27 +268,58 @@ def posterior(model: LGSSM, y, handle: Optional[Handle] = None) -> LGSSM:
     return LGSSM(tr, model.emissions)
 
 
+def _emission_dim(model: LGSSM) -> int:
+    return model.emissions.M if isinstance(model.emissions, SmallOutputEmissions) else 0
+
+
 def marginals(model: LGSSM, handle: Optional[Handle] = None) -> Tuple[np.ndarray, np.ndarray]:
-    """marginals(model::LGSSM) — lgssm.jl:99-115. -> (means (T,), variances (T,)) in emission space."""
+    """marginals(model::LGSSM) — lgssm.jl:99-115. Scalar emissions -> (means (T,), variances (T,)); vector emissions ->
+    (means (T, M), covariances (T, M, M))."""
     h = handle or default_handle()
     mm = _Marshalled(model)
-    mean = np.empty(mm.T)
-    var = np.empty(mm.T)
-    h.marginals(mm.desc, mean, var)
+    M = _emission_dim(model)
+    if M == 0:
+        mean = np.empty(mm.T)
+        var = np.empty(mm.T)
+        h.marginals(mm.desc, mean, var)
+        return mean, var
+    mean = np.empty((mm.T, M))
+    cov = np.empty((mm.T, M, M))
+    h.marginals(mm.desc, mean, cov)
+    return mean, np.swapaxes(cov, 1, 2)
+
+
+def marginals_diag(model: LGSSM, handle: Optional[Handle] = None) -> Tuple[np.ndarray, np.ndarray]:
+    """marginals_diag(model::LGSSM) — lgssm.jl:125-141 (predict_marginals, LGC:63-68): means and the DIAGONAL of the emission-space
+    covariances, (T,) / (T, M)."""
+    h = handle or default_handle()
+    mm = _Marshalled(model)
+    M = _emission_dim(model)
+    shape = (mm.T,) if M == 0 else (mm.T, M)
+    mean = np.empty(shape)
+    var = np.empty(shape)
+    h.marginals_diag(mm.desc, mean, var)
     return mean, var
 
 
 def posterior_marginals(model: LGSSM, y, Rs_new, handle: Optional[Handle] = None, return_lml: bool = False):
-    """marginals(replace_observation_noise_cov(posterior(model, y), Rs_new)) — the chain of
-    posterior_lti_sde.jl:27-36 fused in one library call; (G, g, Sigma) are never materialised."""
+    """marginals_diag(replace_observation_noise_cov(posterior(model, y), Rs_new)) — the chain of posterior_lti_sde.jl:27-36 in one
+    library call (scalar observations, Forward: fused, (G, g, Sigma) never materialised)."""
     _check_inputs(model, y)
     h = handle or default_handle()
     model, y, n_missing = _maybe_missing(model, y)
     mm = _Marshalled(model)
-    Rn, sRn = _per_step(Rs_new if isinstance(Rs_new, Fill) or np.ndim(Rs_new) else Fill(Rs_new, mm.T), mm.T, 0)
-    Rn = np.atleast_1d(Rn)
-    mean = np.empty(mm.T)
-    var = np.empty(mm.T)
+    M = _emission_dim(model)
+    if M == 0:
+        Rn, sRn = _per_step(Rs_new if isinstance(Rs_new, Fill) or np.ndim(Rs_new) else Fill(Rs_new, mm.T), mm.T, 0)
+        Rn = np.atleast_1d(Rn)
+        shape = (mm.T,)
+    else:
+        dense = model.emissions.r_dense
+        Rn, sRn = _per_step(Rs_new, mm.T, 2 if dense else 1, dense)
+        shape = (mm.T, M)
+    mean = np.empty(shape)
+    var = np.empty(shape)
     lml = np.zeros(1)
     h.posterior_marginals(mm.desc, _host_y(y), Rn, sRn, mean, var, lml)
     if return_lml:
