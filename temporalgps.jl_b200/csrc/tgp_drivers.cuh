@@ -140,9 +140,27 @@ int filter_general(tgp_ctx* h, const tgp_lgssm& d, const double* dy, FilterReq& 
     if (tv) k_filter_reduce<D, true><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wagg, nwarps);
     else    k_filter_reduce<D, false><<<(unsigned)grid, kBlock, 0, st>>>(dm, cm, L, nthreads, excl, wagg, nwarps);
     TGP_LAUNCH_CHECK(h);
-    TGP_K(h, "k_filter_mid");
-    k_filter_mid<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, rq.x0buf, wstate, rq.xT);
-    TGP_LAUNCH_CHECK(h);
+    if (nwarps > 4 * kMidThreads) {     // many aggregates: scan them in groups of 32 on the whole GPU, chain only the group aggregates
+        const int64_t ngroups = (nwarps + 31) / 32;
+        double *gexcl, *gagg, *gstate;
+        TGP_TRY(dalloc(h, (size_t)Elem<D>::N * nwarps, &gexcl));
+        TGP_TRY(dalloc(h, (size_t)Elem<D>::N * ngroups, &gagg));
+        TGP_TRY(dalloc(h, (size_t)SN * ngroups, &gstate));
+        const unsigned mg = (unsigned)((ngroups * 32 + kBlock - 1) / kBlock);
+        TGP_K(h, "k_mid_scan");
+        k_mid_scan<D><<<mg, kBlock, 0, st>>>(wagg, nwarps, gexcl, gagg, ngroups);
+        TGP_LAUNCH_CHECK(h);
+        TGP_K(h, "k_filter_mid");
+        k_filter_mid<D><<<1, kMidThreads, 0, st>>>(gagg, ngroups, rq.x0buf, gstate, rq.xT);
+        TGP_LAUNCH_CHECK(h);
+        TGP_K(h, "k_mid_apply");
+        k_mid_apply<D><<<(unsigned)((nwarps + kBlock - 1) / kBlock), kBlock, 0, st>>>(gexcl, gstate, nwarps, ngroups, wstate);
+        TGP_LAUNCH_CHECK(h);
+    } else {
+        TGP_K(h, "k_filter_mid");
+        k_filter_mid<D><<<1, kMidThreads, 0, st>>>(wagg, nwarps, rq.x0buf, wstate, rq.xT);
+        TGP_LAUNCH_CHECK(h);
+    }
     FilterOut fo;
     const int64_t o0 = rev ? tl - 1 : 0;  // memory index of scan step 0
     const int64_t sg = rev ? -1 : 1;

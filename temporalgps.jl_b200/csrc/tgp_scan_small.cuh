@@ -209,6 +209,38 @@ k_filter_mid(const double* __restrict__ wagg, long long nwarps, const double* __
     }
 }
 
+// Middle level in parallel: with T = 1e7 there are ~2e4 warp aggregates, too many for one CTA to chain (651 us in round 1).
+//   k_mid_scan   every warp (of many CTAs) scans 32 consecutive aggregates: group-exclusive prefixes + one aggregate per group;
+//   k_filter_mid (above, one CTA) then only sees the ~600 group aggregates and emits the state entering every group;
+//   k_mid_apply  one thread per warp aggregate: group state, then its group-exclusive prefix -> the state entering the warp.
+template <int D>
+__global__ void __launch_bounds__(kBlock)
+k_mid_scan(const double* __restrict__ wagg, long long nwarps, double* __restrict__ gexcl, double* __restrict__ gagg, long long ngroups) {
+    const long long j = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    Elem<D> E = j < nwarps ? load_elem<D>(wagg, nwarps, j) : elem_identity<D>();
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        const Elem<D> O = shfl_up_elem(E, off);
+        if (lane >= off) E = combine(O, E);
+    }
+    Elem<D> X = shfl_up_elem(E, 1);
+    if (lane == 0) X = elem_identity<D>();
+    if (j < nwarps) store_elem(gexcl, nwarps, j, X);
+    if (lane == 31 && (j >> 5) < ngroups) store_elem(gagg, ngroups, j >> 5, E);
+}
+template <int D>
+__global__ void __launch_bounds__(kBlock)
+k_mid_apply(const double* __restrict__ gexcl, const double* __restrict__ gstate, long long nwarps, long long ngroups, double* __restrict__ wstate) {
+    const long long j = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (j >= nwarps) return;
+    Vec<D> m;
+    Sym<D> P;
+    load_state<D>(gstate, ngroups, j >> 5, m, P);
+    apply_elem(load_elem<D>(gexcl, nwarps, j), m, P);
+    store_state<D>(wstate, nwarps, j, m, P);
+}
+
 // Total of all warp aggregates as ONE element in the ABI's shard format (A, b, C, eta, J with full
 // column-major matrices): phase 1 of the time-sharded path (include/tgp_b200.h, tgp_shard_reduce).
 template <int D>

@@ -427,3 +427,55 @@ def test_space_time_separable_logpdf(pkg, regular):
     lml2 = pkg.gp.logpdf(fx2, y2.reshape(-1))
     ref2 = O.logpdf(mo2, y2)
     assert abs(lml2 - ref2) <= LML_RTOL * abs(ref2)
+
+
+# ---- small observation noise (the reference's DEFAULT is 1e-12, lti_sde.jl:27-29) and non-contractive dynamics -------------------
+@pytest.mark.parametrize("regular", [True, False])
+@pytest.mark.parametrize("s2", [1e-6, 1e-9, 1e-12])
+@pytest.mark.parametrize("kname", ["m52", "m32", "sum_m12_m32"])
+def test_small_noise_parity(pkg, handle, kname, s2, regular):
+    """logpdf (1e-6), filtering means / covariances and posterior marginals (1e-5) at observation noise down to the reference's
+    default 1e-12, through the steady-state kernels (regular grid) and the general 5-tuple scan (irregular grid). Covariance entries
+    are compared relative to the largest entry (a state observed with noise 1e-12 has variances spanning 12 decades)."""
+    kp, ko = KERNELS[kname]
+    rng = np.random.default_rng(int(-np.log10(s2)) * 10 + regular)
+    T, dt = 6000, 0.01
+    tp = pkg.RegularSpacing(0.0, dt, T) if regular else np.sort(rng.uniform(0, dt * T, T))
+    to = O.RegularSpacing(0.0, dt, T) if regular else np.array(tp)
+    y = O.sample_prior(O.build_lgssm(ko(), to, 0.1), rng)
+    mo = O.build_lgssm(ko(), to, s2)
+    fx = pkg.to_sde(pkg.GP(kp(pkg)))(tp, s2)
+    ref = O.logpdf(mo, y)
+    lml = pkg.gp.logpdf(fx, y)
+    assert abs(lml - ref) <= LML_RTOL * abs(ref), (lml, ref)
+    ms_o, Ps_o, _ = O.filter_(mo, y)
+    ms, Ps = pkg.lgssm._filter(fx.build_lgssm(), y, handle)
+    np.testing.assert_allclose(ms, ms_o, rtol=MV_RTOL, atol=1e-7)
+    np.testing.assert_allclose(Ps, Ps_o, rtol=MV_RTOL, atol=1e-9 * np.abs(Ps_o).max())
+    mu, var = pkg.gp.marginals(pkg.gp.posterior(fx, y)(tp, 1e-2))
+    mu_o, var_o = O.gp_posterior_marginals(ko(), to, s2, y, None, 1e-2)
+    np.testing.assert_allclose(mu, mu_o, rtol=MV_RTOL, atol=1e-7)
+    np.testing.assert_allclose(var, var_o, rtol=MV_RTOL)
+
+
+def test_non_contractive_dynamics_are_right_or_loud(pkg, handle):
+    """The reference's fixtures use A = I + 0.1 randn (test/models/model_test_utils.jl:29-31), which is not contractive. At its own
+    lengths (N <= 49) the scan must simply agree; on a long horizon the intermediate scan elements of an UNSTABLE model overflow —
+    then the call has to fail loudly (TGP_ENOTPD from the non-finite innovation variance), never return a wrong number."""
+    rng = np.random.default_rng(99)
+    D = 3
+    for T in (49, 400, 4000):
+        n = T
+        As = np.stack([np.eye(D) + 0.1 * rng.standard_normal((D, D)) for _ in range(n)])
+        from tests.util import random_psd
+        m = O.LGSSM("forward", As, rng.standard_normal((n, D)) * 0.3, np.stack([random_psd(rng, D) for _ in range(n)]),
+                    rng.standard_normal(D), random_psd(rng, D, 0.5, 2.0), rng.standard_normal((n, D)), rng.standard_normal(n) * 0.2,
+                    rng.uniform(0.05, 1.0, n))
+        y = rng.standard_normal(T)
+        ref = O.logpdf(m, y)
+        try:
+            lml = pkg.lgssm.logpdf(to_pkg_model(pkg, m), y, handle)
+        except pkg.TGPError:
+            assert T > 49, "the reference's own fixture sizes must work"
+            continue
+        assert np.isfinite(ref) and abs(lml - ref) <= LML_RTOL * abs(ref), (T, lml, ref)
