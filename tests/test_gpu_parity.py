@@ -206,8 +206,18 @@ def test_errors(pkg, handle):
     big = random_lgssm(rng, 5, 7, "forward", True)     # D = 7 has no scan instantiation: runs the dense path, still correct
     yb = sample_y(rng, big)
     assert abs(pkg.lgssm.logpdf(to_pkg_model(pkg, big), yb, handle) - O.logpdf(big, yb)) <= 1e-9 * abs(O.logpdf(big, yb))
-    with pytest.raises(pkg.TGPError):                  # the smoother entry points are scan-only for now
-        pkg.lgssm.posterior_marginals(to_pkg_model(pkg, big), yb, 0.1, handle)
+    # D = 7 through the smoother entry points: the step-by-step path (tgp_seq.cu)
+    mu, var = pkg.lgssm.posterior_marginals(to_pkg_model(pkg, big), yb, np.full(5, 0.1), handle)
+    mu_o, var_o = O.marginals(O.replace_observation_noise_cov(O.posterior(big, yb), np.full(5, 0.1)))
+    np.testing.assert_allclose(mu, mu_o, rtol=MV_RTOL, atol=1e-8)
+    np.testing.assert_allclose(var, var_o, rtol=MV_RTOL)
+    huge = random_lgssm(rng, 3, 2, "forward", True)
+    huge_pm = to_pkg_model(pkg, huge)
+    huge_pm.transitions.x0 = pkg.lgssm.Gaussian(np.zeros(70), np.eye(70))      # D = 70 > 64: refused, not mis-computed
+    with pytest.raises(pkg.TGPError):
+        pkg.lgssm.marginals(pkg.lgssm.LGSSM(pkg.lgssm.GaussMarkovModel("forward", np.stack([np.eye(70)] * 3), np.zeros((3, 70)),
+                                                                       np.stack([np.eye(70)] * 3), huge_pm.transitions.x0),
+                                            pkg.lgssm.ScalarEmissions(np.ones((3, 70)), np.zeros(3), np.ones(3))), handle)
 
 
 def test_shard_reduce_prefix(pkg, handle):

@@ -1,0 +1,73 @@
+"""General-scan benchmark lines: config 2 forced through the 5-tuple scan (TGP_ALGO_SCAN) and a time-varying model (irregular grid,
+152 B/step of model + observation traffic at D = 3). Prints one JSON object; bench.py embeds it under `secondary`."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def run(pkg, h, torch, T=10_000_000, reps=5):
+    hbm = 6552.3
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        hbm = float(json.load(open(p))["hbm_gbs"])
+    out = {}
+    rng = np.random.default_rng(20261017 + 6)
+    y = torch.from_numpy(rng.standard_normal(T)).cuda()
+    lml = torch.zeros(1, dtype=torch.float64, device="cuda")
+
+    def timeit(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    f = pkg.to_sde(pkg.GP(pkg.Matern52Kernel()))
+    mm = pkg.lgssm._Marshalled(f(pkg.RegularSpacing(0.0, 0.01, T), 0.1).build_lgssm())
+    h.set_algo(pkg.TGP_ALGO_SCAN)
+    try:
+        t = timeit(lambda: h.logpdf(mm.desc, y, lml))
+        h.set_timing(True)
+        h.logpdf(mm.desc, y, lml)
+        tim = h.timing()
+        h.set_timing(False)
+    finally:
+        h.set_algo(pkg.TGP_ALGO_AUTO)
+    out["cfg2_general_scan"] = {"ms": t * 1e3, "steps_per_s": T / t, "hbm_frac_of_measured": 8.0 * T / t / 1e9 / hbm,
+                                "algorithmic_bytes_per_step": 8.0, "kernels": [(n, ms / c) for n, ms, c in tim]}
+    # time-varying: irregular grid, every per-step array resident in HBM (A 72 + Q 72 + y 8 = 152 B/step; a, H, h, R are Fills)
+    Tv = T // 2
+    tt = np.sort(rng.uniform(0.0, 0.01 * Tv, Tv))
+    model = f(tt, 0.1).build_lgssm()
+    mv = pkg.lgssm._Marshalled(model)
+    import ctypes as C
+    keep = []
+    for name in ("A", "a", "Q", "H", "h", "R", "m0", "P0"):
+        arr = None
+        for a in mv.keep:
+            if a.ctypes.data == getattr(mv.desc, name):
+                arr = a
+        tns = torch.from_numpy(arr).cuda()
+        keep.append(tns)
+        setattr(mv.desc, name, tns.data_ptr())
+    yv = y[:Tv].contiguous()
+    t = timeit(lambda: h.logpdf(mv.desc, yv, lml))
+    out["time_varying_irregular_grid"] = {"T": Tv, "ms": t * 1e3, "steps_per_s": Tv / t, "hbm_frac_of_measured": 152.0 * Tv / t / 1e9 / hbm,
+                                          "algorithmic_bytes_per_step": 152.0}
+    return out
+
+
+if __name__ == "__main__":
+    import torch
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    print(json.dumps(run(pkg, pkg.default_handle(0), torch)))
