@@ -493,6 +493,12 @@ def secondary_configs(pkg, h, torch):
         h5.set_dense_math(pkg.lgssm.TGP_DENSE_F64)
     out["cfg5_logpdf_D768_M256_T1e5_fp32_tensorcore"] = {"s": t5, "steps_per_s": T5 / t5, "dtype": "f32 storage, 3xTF32 tcgen05, FP64 Cholesky / means",
                                                          "lml": float(lml5[0])}
+    # the algorithm north_star names, un-specialised: config 2 forced through the general 5-tuple scan, and a time-varying model
+    try:
+        from tools import bench_general
+        out.update(bench_general.run(pkg, h, torch))
+    except Exception as exc:      # noqa: BLE001
+        out["general_scan_error"] = f"{type(exc).__name__}: {exc}"
     return out
 
 

@@ -1,20 +1,22 @@
 # TemporalGPsB200.jl — the Julia side of the drop-in: a storage tag that routes the LGSSM hot path of
-# TemporalGPs.jl (logpdf / _filter / posterior / marginals on to_sde-wrapped GPs) to libtgpb200.so through
-# `ccall`. Pure marshalling: models are still built by TemporalGPs' own `lgssm_components` on the host.
+# TemporalGPs.jl (logpdf / _filter / posterior / marginals / marginals_diag on to_sde-wrapped GPs) to libtgpb200.so
+# through `ccall`. Pure marshalling: models are still built by TemporalGPs' own `lgssm_components` on the host.
 #
-# NOT EXECUTED IN THE BUILD CONTAINER (no Julia there); the same C ABI is exercised from Python by
-# temporalgps.jl_b200/_lib.py, which mirrors this file call for call. See INTEGRATION.md.
+# NOT EXECUTED IN THE BUILD CONTAINER (no Julia there). The same C ABI is exercised (a) from Python by
+# temporalgps.jl_b200/_lib.py, which mirrors this file call for call, and (b) by tests/abi_c/abi_layout.c, a C program
+# that hands the library buffers laid out exactly as `reinterpret(Float64, ::Vector{SMatrix})` / `Fill` produce them.
+# See INTEGRATION.md.
 #
 #   using TemporalGPs, TemporalGPsB200
 #   f  = to_sde(GP(Matern52Kernel()), B200Storage(Float64))
 #   fx = f(RegularSpacing(0.0, 0.01, 10_000_000), 0.1)
-#   logpdf(fx, y); marginals(posterior(fx, y)(x, 1e-2))
+#   logpdf(fx, y); marginals(posterior(fx, y)(x, 1e-2)); logpdf(posterior(fx, y)(x_pr, 0.1), y_pr)
 module TemporalGPsB200
 
-using TemporalGPs, AbstractGPs, StaticArrays, FillArrays, StructArrays, LinearAlgebra
-import TemporalGPs: StorageType, SArrayStorage, LGSSM, GaussMarkovModel, Forward, Reverse, Gaussian,
-    lgssm_components, build_lgssm, LTISDE, ordering, x0, transitions, emissions,
-    replace_observation_noise_cov, _filter, transform_model_and_obs, _logpdf_volume_compensation
+using TemporalGPs, AbstractGPs, StaticArrays, FillArrays, StructArrays, LinearAlgebra, Random
+import TemporalGPs: StorageType, SArrayStorage, ArrayStorage, LGSSM, GaussMarkovModel, Forward, Reverse, Gaussian,
+    ScalarOutputLGC, SmallOutputLGC, build_lgssm, LTISDE, ordering, x0, transitions, emissions,
+    replace_observation_noise_cov, _filter, transform_model_and_obs, _logpdf_volume_compensation, marginals_diag
 import AbstractGPs: logpdf, marginals, posterior
 
 export B200Storage
@@ -39,12 +41,17 @@ function handle(dev::Int)
 end
 # Arithmetic of the large-state / vector-observation path follows the storage tag's element type (tgp_b200.h: TGP_OPT_DENSE_MATH):
 # Float32 -> FP32 storage on the tcgen05 tensor cores (3xTF32), otherwise FP64. The small-state scan kernels are FP64 either way.
-set_dense_math(h, ::Type{T}) where {T} =
-    ccall((:tgp_set_option, LIB), Cint, (Ptr{Cvoid}, Cint, Int64), h, 6, T === Float32 ? 1 : 0)
+set_dense_math(h, f32::Bool) = ccall((:tgp_set_option, LIB), Cint, (Ptr{Cvoid}, Cint, Int64), h, 6, f32 ? 1 : 0)
+
+# status -> exception. TGP_ENOTPD carries the failing time index in its message ("... at time index N (0-based)"): the reference's
+# `cholesky` throws PosDefException(info) with the index of the failing pivot; here `info` is the 1-based TIME index.
 function check(h, rc)
     rc == 0 && return nothing
     msg = unsafe_string(ccall((:tgp_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
-    rc == 2 && throw(PosDefException(0))                 # TGP_ENOTPD  <- cholesky failure in the reference
+    if rc == 2
+        m = match(r"time index (\d+)", msg)
+        throw(PosDefException(m === nothing ? 0 : parse(Int, m.captures[1]) + 1))
+    end
     error("libtgpb200 ($rc): $msg")                       # ErrorException, as lgssm.jl:202-208
 end
 
@@ -56,13 +63,29 @@ struct Desc
     m0::Ptr{Float64}; P0::Ptr{Float64}
 end
 
-# A per-step array as (flat Float64 buffer, stride): `Fill` -> one element, stride 0 (lti_sde.jl:148-160);
-# Vector{SMatrix}/Vector{SVector}/Vector{Float64} -> reinterpret, stride = length of one element.
-flat(x::Fill) = (collect(Float64, vec(collect(FillArrays.getindex_value(x)))), 0)
-flat(x::AbstractVector{<:Real}) = (convert(Vector{Float64}, x), 1)
-flat(x::AbstractVector{<:StaticArray}) = (collect(reinterpret(Float64, x)), length(first(x)))
-flat(x::AbstractVector{<:AbstractArray}) = (reduce(vcat, vec.(x)), length(first(x)))
-flat(x::AbstractVector{<:Adjoint}) = flat(map(parent, x))       # emissions store H as adjoint vectors
+# One per-step ELEMENT as a flat column-major Float64 vector. Adjoint row vectors (the `h'` of ScalarOutputLGC, lti_sde.jl:88-101)
+# and Diagonal noise matrices are unwrapped here, so every container method below is generic in the element.
+elem(x::Real) = Float64[x]
+elem(x::Adjoint{<:Any,<:AbstractVector}) = collect(Float64, parent(x))
+elem(x::Diagonal) = collect(Float64, diag(x))
+elem(x::AbstractArray) = collect(Float64, vec(x))          # column-major, as the ABI wants it
+
+# A per-step array as (flat Float64 buffer, stride in elements): `Fill` -> ONE element, stride 0 (lti_sde.jl:148-160); any other
+# vector -> its elements back to back. `Fill` is matched first, so there is no overlap with the AbstractVector method.
+flat(x::Fill) = (elem(FillArrays.getindex_value(x)), 0)
+function flat(x::AbstractVector)
+    isempty(x) && return (Float64[], 0)
+    n = length(elem(first(x)))
+    buf = Vector{Float64}(undef, n * length(x))
+    for (t, v) in enumerate(x)
+        buf[(t-1)*n+1:t*n] = elem(v)
+    end
+    (buf, n)
+end
+
+r_kind(::Type{<:Real}) = 0                                  # TGP_R_SCALAR
+r_kind(::Type{<:Diagonal}) = 1                              # TGP_R_DIAG
+r_kind(::Type{<:AbstractMatrix}) = 2                        # TGP_R_DENSE
 
 struct Marshalled
     bufs::Vector{Vector{Float64}}
@@ -71,14 +94,21 @@ end
 function Marshalled(model::LGSSM)
     tr, em = transitions(model), emissions(model)
     (A, sA), (a, sa), (Q, sQ) = flat(tr.As), flat(tr.as), flat(tr.Qs)
-    (H, sH), (h, sh), (R, sR) = flat(em.A), flat(em.a), flat(em.Q)  # ScalarOutputLGC fields (lti_sde.jl:88-101)
+    (H, sH), (h, sh), (R, sR) = flat(em.A), flat(em.a), flat(em.Q)   # StructArray fields .A, .a, .Q of the emission LGCs
     m0 = collect(Float64, x0(model).m); P0 = collect(Float64, vec(x0(model).P))
     D = length(m0)
+    scalar = eltype(em) <: ScalarOutputLGC
+    M = scalar ? 1 : length(elem(first(em.a)))
+    kind = scalar ? 0 : r_kind(eltype(em.Q))
     ord = ordering(model) isa Forward ? 0 : 1
-    d = Desc(D, 1, length(model), ord, 0, pointer(A), sA, pointer(a), sa, pointer(Q), sQ,
+    d = Desc(D, M, length(model), ord, kind, pointer(A), sA, pointer(a), sa, pointer(Q), sQ,
              pointer(H), sH, pointer(h), sh, pointer(R), sR, pointer(m0), pointer(P0))
     Marshalled([A, a, Q, H, h, R, m0, P0], d)
 end
+obs_dim(mm::Marshalled) = Int(mm.desc.M)
+# observations as the ABI takes them: T x M doubles, M fastest
+yflat(y::AbstractVector{<:Real}) = convert(Vector{Float64}, y)
+yflat(y::AbstractVector{<:AbstractVector}) = reduce(vcat, map(v -> convert(Vector{Float64}, v), y))
 
 # ---- wrapper model: what build_lgssm returns for B200Storage -----------------------------------------
 struct B200LGSSM{Tm<:LGSSM}
@@ -87,25 +117,32 @@ struct B200LGSSM{Tm<:LGSSM}
     f32::Bool          # storage tag was B200Storage{Float32}: large-state products on the tensor cores (TGP_DENSE_TF32X3)
 end
 B200LGSSM(model, device::Int) = B200LGSSM(model, device, false)
-# handle of the model's device with the dense-path arithmetic of its storage tag selected
-function handle(m::B200LGSSM)
+function handle(m::B200LGSSM)       # handle of the model's device with the dense-path arithmetic of its storage tag selected
     h = handle(m.device)
-    set_dense_math(h, m.f32 ? Float32 : Float64)
+    set_dense_math(h, m.f32)
     h
 end
 Base.length(m::B200LGSSM) = length(m.model)
+ordering(m::B200LGSSM) = ordering(m.model)
+emissions(m::B200LGSSM) = emissions(m.model)
 
-lgssm_components(k, t::AbstractVector, s::B200Storage{T}) where {T} = lgssm_components(k, t, SArrayStorage(T))
+# The ONLY method added to the reference's construction chain: build the components with the reference's own static-array code
+# (scalar GPs) or dense-array code (space-time grids) by swapping the storage tag, then wrap. No `lgssm_components` method is
+# defined here, so nothing can become ambiguous with the reference's (::Separable, ::SpaceTimeGrid, ::StorageType) method.
+host_storage(f::LTISDE, x) = x isa TemporalGPs.RectilinearGrid ? ArrayStorage(Float64) : SArrayStorage(Float64)
 function build_lgssm(f::LTISDE{<:GP,<:B200Storage}, x::AbstractVector, Σys::AbstractVector)
     # the ABI takes Float64 arrays; with a Float32 tag the library converts to FP32 storage on the device
-    inner = build_lgssm(LTISDE(f.f, SArrayStorage(Float64)), x, Σys)
+    inner = build_lgssm(LTISDE(f.f, host_storage(f, x)), x, Σys)
     B200LGSSM(inner, f.storage.device, eltype(f.storage) === Float32)
 end
 
+check_lengths(m, y) = length(m) == length(y) ||
+    error("Dimension mismatch. length(prior) is $(length(m)), but length(y) is $(length(y))")
+
 # logpdf(model, y) — src/models/lgssm.jl:147-151
-function logpdf(m::B200LGSSM, y::AbstractVector{<:Real})
-    length(m) == length(y) || error("Dimension mismatch. length(prior) is $(length(m)), but length(y) is $(length(y))")
-    h = handle(m); mm = Marshalled(m.model); yy = convert(Vector{Float64}, y); out = Ref(0.0)
+function logpdf(m::B200LGSSM, y::AbstractVector{<:Union{AbstractVector{<:Real},Real}})
+    check_lengths(m, y)
+    h = handle(m); mm = Marshalled(m.model); yy = yflat(y); out = Ref(0.0)
     GC.@preserve mm yy begin
         check(h, ccall((:tgp_logpdf, LIB), Cint, (Ptr{Cvoid}, Ref{Desc}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
                        h, mm.desc, yy, out, C_NULL))
@@ -118,9 +155,10 @@ function logpdf(m::B200LGSSM, y::AbstractVector{Union{Missing,T}}) where {T}
     logpdf(B200LGSSM(model2, m.device, m.f32), y2) + _logpdf_volume_compensation(y, m.model)
 end
 
-# _filter(model, y) — src/models/lgssm.jl:171-173: Vector{Gaussian{SVector{D},SMatrix{D,D}}} written in place
-function _filter(m::B200LGSSM, y::AbstractVector{<:Real})
-    h = handle(m); mm = Marshalled(m.model); yy = convert(Vector{Float64}, y)
+# _filter(model, y) — src/models/lgssm.jl:171-173: the records (m, P) of Vector{Gaussian{SVector{D},SMatrix{D,D}}} written in place
+function _filter(m::B200LGSSM, y::AbstractVector{<:Union{AbstractVector{<:Real},Real}})
+    check_lengths(m, y)
+    h = handle(m); mm = Marshalled(m.model); yy = yflat(y)
     D = Int(mm.desc.D); T = length(m); rec = D + D * D
     buf = Vector{Float64}(undef, rec * T)
     GC.@preserve mm yy buf begin
@@ -130,40 +168,87 @@ function _filter(m::B200LGSSM, y::AbstractVector{<:Real})
     end
     [Gaussian(SVector{D}(buf[(t-1)*rec+1:(t-1)*rec+D]), SMatrix{D,D}(buf[(t-1)*rec+D+1:t*rec])) for t in 1:T]
 end
+function _filter(m::B200LGSSM, y::AbstractVector{Union{Missing,T}}) where {T}
+    model2, y2 = transform_model_and_obs(m.model, y)
+    _filter(B200LGSSM(model2, m.device, m.f32), y2)
+end
 
-# posterior(model, y) — lazy: marginals(replace_observation_noise_cov(posterior(model, y), Σ)) is ONE library
-# call (tgp_posterior_marginals; src/gp/posterior_lti_sde.jl:27-36); the materialised Reverse LGSSM of
-# lgssm.jl:193-200 is available through `materialise` (tgp_posterior).
+# ---- posterior ---------------------------------------------------------------------------------------
+# posterior(model, y) is LAZY: marginals(replace_observation_noise_cov(posterior(model, y), Σ)) — the chain of
+# src/gp/posterior_lti_sde.jl:27-36 — is ONE library call (tgp_posterior_marginals) that never materialises (G, g, Σ);
+# everything else (logpdf, rand, marginals with full covariances) goes through `materialise`, which runs tgp_posterior and
+# returns the reference's own Reverse-ordered LGSSM (lgssm.jl:193-200), wrapped again so its calls come back to the library.
 struct B200Posterior{Tm<:B200LGSSM,Ty,TΣ}
     prior::Tm
     y::Ty
     Σs_new::TΣ
 end
-posterior(m::B200LGSSM, y::AbstractVector) = B200Posterior(m, y, nothing)
+posterior(m::B200LGSSM, y::AbstractVector) = (check_lengths(m, y); B200Posterior(m, y, nothing))
 replace_observation_noise_cov(p::B200Posterior, Σs) = B200Posterior(p.prior, p.y, Σs)
+replace_observation_noise_cov(m::B200LGSSM, Σs) = B200LGSSM(replace_observation_noise_cov(m.model, Σs), m.device, m.f32)
+Base.length(p::B200Posterior) = length(p.prior)
 
-function marginals(p::B200Posterior)
-    m = p.prior; h = handle(m.device)
-    model, y = eltype(p.y) >: Missing ? transform_model_and_obs(m.model, p.y) : (m.model, p.y)
-    mm = Marshalled(model); yy = convert(Vector{Float64}, y)
+observed(p::B200Posterior) = eltype(p.y) >: Missing ? transform_model_and_obs(p.prior.model, p.y) : (p.prior.model, p.y)
+
+"The posterior as the reference's Reverse-ordered LGSSM (tgp_posterior: G, g, Σ per step and x0 = the last filtering distribution)."
+function materialise(p::B200Posterior)
+    m = p.prior; h = handle(m)
+    model, y = observed(p)
+    mm = Marshalled(model); yy = yflat(y)
+    D = Int(mm.desc.D); T = length(m)
+    G = Vector{Float64}(undef, D * D * T); g = Vector{Float64}(undef, D * T); S = Vector{Float64}(undef, D * D * T)
+    mT = Vector{Float64}(undef, D); PT = Vector{Float64}(undef, D * D)
+    GC.@preserve mm yy begin
+        check(h, ccall((:tgp_posterior, LIB), Cint,
+                       (Ptr{Cvoid}, Ref{Desc}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       h, mm.desc, yy, G, g, S, mT, PT))
+    end
+    As = [SMatrix{D,D}(G[(t-1)*D*D+1:t*D*D]) for t in 1:T]
+    as = [SVector{D}(g[(t-1)*D+1:t*D]) for t in 1:T]
+    Qs = [SMatrix{D,D}(S[(t-1)*D*D+1:t*D*D]) for t in 1:T]
+    new_order = ordering(model) isa Forward ? Reverse() : Forward()
+    ems = p.Σs_new === nothing ? emissions(model) : emissions(replace_observation_noise_cov(model, p.Σs_new))
+    inner = LGSSM(GaussMarkovModel(new_order, As, as, Qs, Gaussian(SVector{D}(mT), SMatrix{D,D}(PT))), ems)
+    B200LGSSM(inner, m.device, m.f32)
+end
+
+# logpdf(::FinitePosteriorLTISDE, y) and rand reach here through replace_observation_noise_cov(posterior(model, ys), Σ)
+# (src/gp/posterior_lti_sde.jl:49-78)
+logpdf(p::B200Posterior, y::AbstractVector) = logpdf(materialise(p), y)
+_filter(p::B200Posterior, y::AbstractVector) = _filter(materialise(p), y)
+Base.rand(rng::AbstractRNG, p::B200Posterior) = rand(rng, materialise(p).model)      # sampling stays on the host (lgssm.jl:65-91)
+
+function marginals_diag(p::B200Posterior)
+    m = p.prior; h = handle(m)
+    model, y = observed(p)
+    mm = Marshalled(model); yy = yflat(y); M = obs_dim(mm)
     (Rn, sRn) = flat(p.Σs_new === nothing ? emissions(model).Q : p.Σs_new)
-    T = length(m); mu = Vector{Float64}(undef, T); v = Vector{Float64}(undef, T)
+    T = length(m); mu = Vector{Float64}(undef, T * M); v = Vector{Float64}(undef, T * M)
     GC.@preserve mm yy Rn begin
         check(h, ccall((:tgp_posterior_marginals, LIB), Cint,
                        (Ptr{Cvoid}, Ref{Desc}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                        h, mm.desc, yy, Rn, sRn, mu, v, C_NULL))
     end
-    [Gaussian(mu[t], v[t]) for t in 1:T]
+    M == 1 ? [Gaussian(mu[t], v[t]) for t in 1:T] :
+             [Gaussian(mu[(t-1)*M+1:t*M], Diagonal(v[(t-1)*M+1:t*M])) for t in 1:T]
 end
+# scalar emissions: the marginal IS its diagonal (what posterior_lti_sde.jl:27-36 asks for); vector emissions: full covariances
+marginals(p::B200Posterior) = obs_dim(Marshalled(observed(p)[1])) == 1 ? marginals_diag(p) : marginals(materialise(p))
 
-# marginals(model) — src/models/lgssm.jl:99-101 (data-free)
-function marginals(m::B200LGSSM)
-    h = handle(m.device); mm = Marshalled(m.model); T = length(m)
-    mu = Vector{Float64}(undef, T); v = Vector{Float64}(undef, T)
+# marginals(model) / marginals_diag(model) — src/models/lgssm.jl:99-141 (data-free)
+function emit_marginals(m::B200LGSSM, diag::Bool)
+    h = handle(m); mm = Marshalled(m.model); T = length(m); M = obs_dim(mm)
+    nc = diag ? M : M * M
+    mu = Vector{Float64}(undef, T * M); c = Vector{Float64}(undef, T * nc)
     GC.@preserve mm begin
-        check(h, ccall((:tgp_marginals, LIB), Cint, (Ptr{Cvoid}, Ref{Desc}, Ptr{Float64}, Ptr{Float64}), h, mm.desc, mu, v))
+        check(h, ccall((diag ? :tgp_marginals_diag : :tgp_marginals, LIB), Cint, (Ptr{Cvoid}, Ref{Desc}, Ptr{Float64}, Ptr{Float64}),
+                       h, mm.desc, mu, c))
     end
-    [Gaussian(mu[t], v[t]) for t in 1:T]
+    M == 1 && return [Gaussian(mu[t], c[t]) for t in 1:T]
+    diag ? [Gaussian(mu[(t-1)*M+1:t*M], Diagonal(c[(t-1)*M+1:t*M])) for t in 1:T] :
+           [Gaussian(mu[(t-1)*M+1:t*M], reshape(c[(t-1)*nc+1:t*nc], M, M)) for t in 1:T]
 end
+marginals(m::B200LGSSM) = emit_marginals(m, false)
+marginals_diag(m::B200LGSSM) = emit_marginals(m, true)
 
 end # module
