@@ -68,6 +68,7 @@ struct FirArgs {
     double* result;               // lml of this shard (device)
     double* lml_user;             // caller's device destination, nullable
     unsigned stagger_ns;          // initial delay between the four warp groups of a CTA (0: none)
+    unsigned long long* trace;    // optional (TGP_FIR_TRACE): 8 globaltimer stamps per CTA, see fir_trace()
     int early_trigger;            // let the next call's CTAs in as this call's CTAs leave (only when a call fills every SM: then at most
                                   // two calls are ever in flight, which is what the parity-indexed workspace allows)
     FirXchg x;
@@ -120,6 +121,19 @@ __device__ __forceinline__ void fir_issue_tile(double* buf, const double* __rest
     const double* src = ys + 2 * lane;
 #pragma unroll
     for (int k = 0; k < kFirL / 2; ++k) fir_cp16(dst + k * 2 * kFirRow, src + 64 * k, pol);
+}
+// The same for the PARTIAL last tile of a series: chunks beyond `nvalid` observations are zero-filled (cp.async src-size), nothing is
+// read past the end of y.
+static __device__ __noinline__ void fir_issue_tile_zfill(double* buf, const double* __restrict__ ys, int nvalid, int lane, unsigned long long pol) {
+    double* dst = buf + (lane >> 4) * kFirRow + (lane & 15) * 2;
+#pragma unroll 1
+    for (int k = 0; k < kFirL / 2; ++k) {
+        const int e = 64 * k + 2 * lane;                                   // first observation of the chunk
+        const int nbytes = max(0, min(2, nvalid - e)) * 8;
+        const double* src = ys + (nbytes ? e : 0);                          // a valid address even when nothing is read
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + k * 2 * kFirRow);
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(sa), "l"(src), "r"(nbytes), "l"(pol) : "memory");
+    }
 }
 __device__ __forceinline__ void fir_read_tile(const double* buf, int lane, double (&yv)[kFirL]) {
     const double2* row = reinterpret_cast<const double2*>(buf + lane * kFirRow);
@@ -198,20 +212,22 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double 
     if (lane == 0) m = vzero<D>();
     // ---- carry: state entering the tile from the nb entries before it (lane k D + i fetches component i of entry r - 1 - k) ---------
     double val = 0.0;
-    if (lane < pl.nb * D) {
-        const int want = r - 1 - lane / D;
-        const double2* wptr = sring + fir_slot(want) * D + lane % D;
-        int tag;
+    {
+        // every lane takes part in the loop (lanes >= nb D are ready at once) and leaves it on a warp-uniform vote: the warp never
+        // diverges here, so the shuffles below stay on the fast (converged) path
+        const bool poller = lane < pl.nb * D;
+        const int want = r - 1 - (poller ? lane / D : 0);
+        const double2* wptr = sring + fir_slot(want) * D + (poller ? lane % D : 0);
         unsigned spins = 0;
         unsigned long long t0 = 0ull;
         for (;;) {
-            fir_ld_word(wptr, val, tag);
-            if (tag == want) break;
+            int tag = want;
+            if (poller) fir_ld_word(wptr, val, tag);
+            if (__all_sync(0xffffffffu, tag == want)) break;
             fir_spin_check(spins, t0);                 // cannot end short of a lost peer rank (halo): fail loudly, do not hang
             __nanosleep(20);
         }
     }
-    __syncwarp();
     {
         Vec<D> c;
 #pragma unroll
@@ -231,7 +247,16 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double 
     return fir_pass_b2<D, TAIL>(pl, yv, u, m, TAIL ? nvalid - lane * kFirL : kFirL);
 }
 
-// Partial / unaligned / halo tiles: guarded scalar loads straight from global memory, one out-of-line copy.
+// The staged partial tile (zero-filled beyond nvalid): out of line, masked sums.
+template <int D>
+__device__ __noinline__ double fir_tile_staged_tail(const FirPlan<D>& pl, const double* buf, int r, int nvalid, bool pub, bool full,
+                                                    const double* __restrict__ splane, double2* sring, int lane) {
+    double yv[kFirL];          // (its own copy: handing the caller's register array to an out-of-line function would force it into
+    fir_read_tile(buf, lane, yv);   //  local memory for every tile)
+    return fir_tile_compute<D, true>(pl, yv, r, nvalid, pub, full, splane, sring, lane);
+}
+
+// Unaligned series: guarded scalar loads straight from global memory, one out-of-line copy.
 template <int D>
 __device__ __noinline__ double fir_tile_guarded(const FirPlan<D>& pl, const double* __restrict__ ys, int r, int nvalid, bool pub, bool full,
                                                 const double* __restrict__ splane, double2* sring, int lane) {
@@ -366,6 +391,11 @@ __device__ __noinline__ double fir_head(const FirPlan<D>& pl, const FirArgs& ar,
     return tot;
 }
 
+// Debug timeline (TGP_FIR_TRACE=1): stamp `slot` of this CTA with the global nanosecond timer.
+__device__ __forceinline__ void fir_trace(const FirArgs& ar, int slot) {
+    if (ar.trace) ar.trace[(size_t)blockIdx.x * 8 + slot] = fir_now_ns();
+}
+
 template <int D>
 __global__ void __launch_bounds__(kFirThreads, 1)
 k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirArgs ar) {
@@ -378,7 +408,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     __shared__ int s_last, s_push_cnt;
     int* s_push = &s_push_cnt;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    if (tid == 0) s_push_cnt = 0;
+    if (tid == 0) { s_push_cnt = 0; fir_trace(ar, 0); }
     const long long G = gridDim.x, b = blockIdx.x;
     // Programmatic dependent launch: the next call's CTAs may take an SM as soon as this call's CTA leaves it (the calls share
     // nothing: counters / partials / result alternate by call parity).
@@ -403,22 +433,29 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     const long long first = c0 + wp + (deferred ? kFirWarps : 0);       // this warp: tiles first, first + 16, ... < c1
     int n_main = c1 > first ? (int)((c1 - first + kFirWarps - 1) / kFirWarps) : 0;
     // all of them are full tiles except, possibly, the very last tile of the series
-    const bool last_partial = n_main > 0 && (first + (long long)(n_main - 1) * kFirWarps + 1) * kFirTile > Ts;
-    const int n_fast = pl.aligned ? n_main - (last_partial ? 1 : 0) : 0;
+    // all of them are full tiles except, possibly, the very last tile of the series (staged too, zero-filled beyond its end)
+    const int n_fast = pl.aligned ? n_main : 0;
     double* buf = smem + wp * kFirBufDoubles;
     const unsigned long long pol = fir_policy_evict_first();
-    // ---- this warp's staged items, in order: [A] its deferred tile, pass A only; [B] its full tiles first, first + 16, ...;
+    // ---- this warp's staged items, in order: [A] its deferred tile, pass A only; [B] its tiles first, first + 16, ...;
     // [C] (warp 0 of CTA 0 on a shard with rank > 0) the nb halo tiles, pass A only; [D] the deferred tile, pass B. ------------------
     const int nA = (deferred && pl.aligned) ? 1 : 0, nC = (exch_halo && wp == 0 && pl.aligned) ? pl.nb : 0, nD = nA;
     const int n_items = nA + n_fast + nC + nD;
-    struct Item { const double* src; int r; bool pub, full; };
+    struct Item { const double* src; int r; int nvalid; bool pub, full; };
     auto item = [&](int it) -> Item {
-        if (it < nA) return Item{ys + (c0 + wp) * kFirTile, wp + kFirNbMax, true, false};
+        if (it < nA) return Item{ys + (c0 + wp) * kFirTile, wp + kFirNbMax, kFirTile, true, false};
         it -= nA;
-        if (it < n_fast) return Item{ys + (first + (long long)it * kFirWarps) * kFirTile, (int)(first - c0) + it * kFirWarps + kFirNbMax, true, true};
+        if (it < n_fast) {
+            const long long t = first + (long long)it * kFirWarps;
+            return Item{ys + t * kFirTile, (int)(t - c0) + kFirNbMax, (int)min((long long)kFirTile, Ts - t * kFirTile), true, true};
+        }
         it -= n_fast;
-        if (it < nC) return Item{ar.x.halo + (size_t)it * kFirTile, kFirNbMax - (pl.nb - it), true, false};      // tile -(nb - it)
-        return Item{ys + (c0 + wp) * kFirTile, wp + kFirNbMax, false, true};
+        if (it < nC) return Item{ar.x.halo + (size_t)it * kFirTile, kFirNbMax - (pl.nb - it), kFirTile, true, false};      // tile -(nb - it)
+        return Item{ys + (c0 + wp) * kFirTile, wp + kFirNbMax, kFirTile, false, true};
+    };
+    auto issue = [&](const Item& x) {
+        if (x.nvalid == kFirTile) fir_issue_tile(buf, x.src, lane, pol);
+        else fir_issue_tile_zfill(buf, x.src, x.nvalid, lane, pol);
     };
     auto wait_halo = [&]() {      // the predecessor's push of THIS epoch's ring slot
         if (ar.x.halo_flag) {
@@ -438,12 +475,17 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     // over the nb tiles BEFORE the chunk (re-read from HBM) — staged like any other tile, and first in the queue.
     const int halo_k = (b > 0 && wp >= kFirWarps - pl.nb) ? kFirWarps - wp : 0;      // tile c0 - halo_k
     const bool halo_fast = halo_k > 0 && pl.aligned;
+    if (ar.stagger_ns && (wp >> 2)) __nanosleep((unsigned)(wp >> 2) * ar.stagger_ns);   // de-phase the 4 warps of each scheduler
+    // the lane powers first (one load per thread: ahead of, not behind, the 128 KB of observations this SM is about to request)
+    static_assert(D * D * 32 <= kFirThreads, "one lane-power entry per thread");
+    const double plane_v = tid < D * D * 32 ? __ldg(ar.plane + tid) : 0.0;
     if (halo_fast) fir_issue_tile(buf, ys + (c0 - halo_k) * kFirTile, lane, pol);
-    else if (n_items > 0 && !(nA + n_fast == 0 && nC > 0)) fir_issue_tile(buf, item(0).src, lane, pol);   // first tile on its way before anything else
+    else if (n_items > 0 && !(nA + n_fast == 0 && nC > 0)) issue(item(0));            // first tile on its way before anything else
     fir_cp_commit();
-    for (int i = tid; i < D * D * 32; i += kFirThreads) splane[i] = __ldg(ar.plane + i);
+    if (tid < D * D * 32) splane[tid] = plane_v;
     for (int i = tid; i < (kFirRing + 2 * kFirNbMax) * D; i += kFirThreads) fir_st_word(sring + i, 0.0, -1);
     __syncthreads();
+    if (tid == 0) fir_trace(ar, 1);
     // ---- what precedes the chunk --------------------------------------------------------------------------------------
     if (b == 0 && !exch_halo) {
         const double qh = fir_head<D>(pl, ar, sscan, sred, sring);
@@ -455,7 +497,13 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
             __syncwarp();
             fir_read_tile(buf, lane, yv);
             __syncwarp();
-            fir_tile_compute<D, false>(pl, yv, kFirNbMax - halo_k, kFirTile, true, false, splane, sring, lane, buf, n_items > 0 ? item(0).src : nullptr, pol);
+            const double* nx = nullptr;
+            if (n_items > 0) {
+                const Item x0 = item(0);
+                if (x0.nvalid == kFirTile) nx = x0.src;
+                else { fir_issue_tile_zfill(buf, x0.src, x0.nvalid, lane, pol); }
+            }
+            fir_tile_compute<D, false>(pl, yv, kFirNbMax - halo_k, kFirTile, true, false, splane, sring, lane, buf, nx, pol);
         } else {
             fir_tile_guarded<D>(pl, ys + (c0 - halo_k) * kFirTile, kFirNbMax - halo_k, kFirTile, true, false, splane, sring, lane);
         }
@@ -484,7 +532,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         __syncwarp();
         if (lane == 0 && atomicAdd(s_push, 1) == kFirPushWarps - 1) *reinterpret_cast<volatile unsigned long long*>(ar.x.push_flag) = ar.epoch;
     };
-    if (ar.stagger_ns && (wp >> 2)) __nanosleep((unsigned)(wp >> 2) * ar.stagger_ns);   // de-phase the 4 warps of each scheduler
+    if (tid == 0) fir_trace(ar, 2);
     // ---- the chunk --------------------------------------------------------------------------------------------------------
     double q = 0.0;
     if (deferred && !pl.aligned)
@@ -492,26 +540,42 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
                             splane, sring, lane);
     if (nA + n_fast == 0 && nC > 0) {      // nothing staged before the halo: its first tile could not be prefetched above
         wait_halo();
-        fir_issue_tile(buf, item(0).src, lane, pol);
+        issue(item(0));
         fir_cp_commit();
     }
 #pragma unroll 1
     for (int it = 0; it < n_items; ++it) {
-        double yv[kFirL];
         const Item cur = item(it);
         fir_cp_wait_all();
         __syncwarp();
+        if (cur.nvalid != kFirTile) {      // the partial last tile of the series (zero-filled beyond its end): masked sums
+            double yt[kFirL];
+            fir_read_tile(buf, lane, yt);
+            q += fir_tile_compute<D, true>(pl, yt, cur.r, cur.nvalid, cur.pub, cur.full, splane, sring, lane);
+            __syncwarp();
+            if (it + 1 < n_items) {        // (only when one CTA runs the whole series)
+                if (nC > 0 && it + 1 == nA + n_fast) wait_halo();
+                issue(item(it + 1));
+            }
+            fir_cp_commit();
+            continue;
+        }
+        double yv[kFirL];
         fir_read_tile(buf, lane, yv);
         __syncwarp();
         const double* __restrict__ next = nullptr;
         if (it + 1 < n_items) {
             if (nC > 0 && it + 1 == nA + n_fast) wait_halo();      // the next item is the first halo tile: its data must have arrived
-            next = item(it + 1).src;
+            const Item nx = item(it + 1);
+            if (nx.nvalid == kFirTile) next = nx.src;              // its copies are spread over this tile's pass A
+            else fir_issue_tile_zfill(buf, nx.src, nx.nvalid, lane, pol);   // the partial last tile: zero-filled copies, issued now
         }
         q += pl.zero_mean ? fir_tile_compute<D, false, true>(pl, yv, cur.r, kFirTile, cur.pub, cur.full, splane, sring, lane, buf, next, pol)
                           : fir_tile_compute<D, false, false>(pl, yv, cur.r, kFirTile, cur.pub, cur.full, splane, sring, lane, buf, next, pol);
         if (pusher && it == 0) push_done();
+        if (tid == 0 && it == 0) fir_trace(ar, 3);
     }
+    if (tid == 0) fir_trace(ar, 4);
     if (pusher && n_items == 0) push_done();
 #pragma unroll 1
     for (int it = n_fast; it < n_main; ++it) {      // unaligned series (all tiles) or the partial last tile
@@ -537,6 +601,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     if (lane == 0) sred[wp] = q;
     __syncthreads();
     if (tid == 0) {
+        fir_trace(ar, 5);
         double t = 0.0;
 #pragma unroll
         for (int i = 0; i < kFirWarps; ++i) t += sred[i];
@@ -545,6 +610,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         // have been vacated — never overlaps the previous one, so at most two calls are in flight and the parity-indexed
         // counters / partials / result below (and the exchange ring) are never shared by two live calls.
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        fir_trace(ar, 6);
         __stcg(ar.partials + b, t);
         if (b == 0 && exch_halo) __stcg(ar.partials + G, 0.0);
         __threadfence();
@@ -567,6 +633,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         const double lml = pl.c0 - 0.5 * (__ldcg(ar.partials + G) + pl.invS * t);
         *ar.result = lml;
         if (ar.lml_user) *ar.lml_user = lml;
+        fir_trace(ar, 7);
         ar.counters[0] = 0u;
         if (ar.x.ack_out)      // the halo of this call has been consumed (and so have those of all earlier calls: see the wait above)
             *reinterpret_cast<volatile unsigned long long*>(ar.x.ack_out) = ar.epoch;
@@ -671,6 +738,14 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     if (stagger < 0) { const char* e = getenv("TGP_FIR_STAGGER"); stagger = e ? atoi(e) : 0; }
     if (pdl < 0) { const char* e = getenv("TGP_FIR_PDL"); pdl = e ? atoi(e) : 1; }
     ar.stagger_ns = (unsigned)stagger;
+    static int trace = -1;
+    if (trace < 0) trace = getenv("TGP_FIR_TRACE") ? 1 : 0;
+    unsigned long long* dtrace = nullptr;
+    if (trace) {
+        TGP_TRY(dalloc(h, (size_t)G * 8, &dtrace));
+        TGP_CUDA(h, cudaMemsetAsync(dtrace, 0, (size_t)G * 64, h->stream));
+        ar.trace = dtrace;
+    }
     ar.early_trigger = (pdl && (int)G == h->sm_count) ? 1 : 0;
     TGP_K(h, "k_fir_logpdf");
     constexpr size_t smem = FirSmem<D>::bytes;
@@ -693,6 +768,30 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
         TGP_CUDA(h, cudaLaunchKernelEx(&cfg, k_fir_logpdf<D>, pl, ar));
     }
     TGP_LAUNCH_CHECK(h);
+    if (trace) {      // debug timeline: per stamp, the earliest / latest CTA relative to the first CTA's entry (microseconds)
+        std::vector<unsigned long long> tr((size_t)G * 8);
+        TGP_CUDA(h, cudaMemcpyAsync(tr.data(), dtrace, tr.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+        TGP_CUDA(h, cudaStreamSynchronize(h->stream));
+        unsigned long long t0 = ~0ull;
+        for (unsigned c = 0; c < G; ++c) t0 = std::min(t0, tr[(size_t)c * 8]);
+        static const char* nm[8] = {"entry", "plane+ring ready", "head/halo done", "first item done", "items done", "CTA done", "prev call complete", "lml written"};
+        fprintf(stderr, "[tgp fir trace] T=%lld G=%u N0=%lld nb=%d\n", (long long)pl.T, G, (long long)pl.N0, pl.nb);
+        for (int k = 0; k < 8; ++k) {
+            unsigned long long lo = ~0ull, hi = 0, c0v = tr[k];
+            for (unsigned c = 0; c < G; ++c) { const unsigned long long v = tr[(size_t)c * 8 + k]; if (v) { lo = std::min(lo, v); hi = std::max(hi, v); } }
+            if (hi) fprintf(stderr, "   %-20s min %7.2f  max %7.2f  CTA0 %7.2f us\n", nm[k], (lo - t0) * 1e-3, (hi - t0) * 1e-3, c0v ? (c0v - t0) * 1e-3 : -1.0);
+        }
+        {   // the five slowest CTAs
+            std::vector<std::pair<unsigned long long, unsigned>> v;
+            for (unsigned c = 0; c < G; ++c) v.push_back({tr[(size_t)c * 8 + 5], c});
+            std::sort(v.begin(), v.end());
+            for (size_t i = v.size() > 5 ? v.size() - 5 : 0; i < v.size(); ++i) {
+                const unsigned c = v[i].second;
+                fprintf(stderr, "   slow CTA %3u: ready %6.2f pre %6.2f first %6.2f items %6.2f done %6.2f\n", c, (tr[c * 8 + 1] - t0) * 1e-3,
+                        (tr[c * 8 + 2] - t0) * 1e-3, (tr[c * 8 + 3] - t0) * 1e-3, (tr[c * 8 + 4] - t0) * 1e-3, (tr[c * 8 + 5] - t0) * 1e-3);
+            }
+        }
+    }
     *handled = true;
     if (lml_out && !ar.lml_user) {
         TGP_CUDA(h, cudaMemcpyAsync(h->pinned + 8, ar.result, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
