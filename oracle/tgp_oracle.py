@@ -409,6 +409,17 @@ def posterior_and_lml_large(m, P, H, h, R, y):
     return m_post, P_post, lml
 
 
+def posterior_and_lml_bottleneck(m, P, H, h, A, a, Q, y):
+    """BottleneckLGC(H, h, LargeOutputLGC(A, a, Q)), LGC:305-335: project onto z = H x + h (jitter 1e-12, _project :305-309),
+    condition z with the fan-out LargeOutputLGC, then integrate x | z against z | y (jitter 1e-12 in the Cholesky, :330)."""
+    K = H.shape[0]
+    zm, zP = H @ m + h, H @ P @ H.T + 1e-12 * np.eye(K)
+    zpm, zpP, lml = posterior_and_lml_large(zm, zP, A, a, Q, y)
+    U = np.linalg.cholesky(_symmetric(zP + 1e-12 * np.eye(K))).T
+    Gt = np.linalg.solve(U, np.linalg.solve(U.T, H @ P))
+    return m + Gt.T @ (zpm - zm), P + Gt.T @ (zpP - zP) @ Gt, lml
+
+
 def _update(model: LGSSM, t, m, P, y):
     if model.scalar:
         return posterior_and_lml_scalar(m, P, model.Hs[t], float(model.hs[t]), float(model.Rs[t]), float(y))

@@ -12,6 +12,7 @@ from .build import build
 from .gp import (GP, ApproxPeriodicKernel, ArrayStorage, B200Storage, ConstantKernel, FiniteLTISDE, Matern12Kernel,
                  Matern32Kernel, Matern52Kernel, RectilinearGrid, RegularSpacing, SArrayStorage, SEKernel, Separable, to_sde,
                  with_lengthscale)
-from .lgssm import LGSSM, Fill, Forward, Gaussian, GaussMarkovModel, Reverse, ScalarEmissions, SmallOutputEmissions
+from .lgssm import (LGSSM, BottleneckEmissions, Fill, Forward, Gaussian, GaussMarkovModel, LargeOutputEmissions, Reverse,
+                    ScalarEmissions, SmallOutputEmissions)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -94,6 +94,53 @@ class SmallOutputEmissions:
 
 
 @dataclass
+class LargeOutputEmissions(SmallOutputEmissions):
+    """StructArray{LargeOutputLGC} (linear_gaussian_conditionals.jl:153-204): the same conditional y | x ~ N(H x + h, R) as
+    SmallOutputLGC, which the reference evaluates by another route (Cholesky in the latent space, jitter 1e-10) when Dobs > Dlat.
+    The library has ONE route for vector observations, so this marshals exactly like SmallOutputEmissions; results agree with the
+    reference's to its own jitter (~1e-10 relative, inside the 1e-6 / 1e-5 parity band)."""
+
+
+@dataclass
+class BottleneckEmissions:
+    """StructArray{BottleneckLGC} (linear_gaussian_conditionals.jl:258-335): y | x ~ N(A (H x + h) + a, Q) with a low-dimensional
+    projection (H, h) and a fan-out LargeOutputLGC (A, a, Q). Marshalled as the equivalent single conditional
+    N((A H) x + (A h + a), Q); the reference's 1e-12 jitters on the projected covariance are below the parity band."""
+    Hs: object        # Fill | (T, K, D)
+    hs: object        # Fill | (T, K)
+    fan_out: LargeOutputEmissions   # A: (T, M, K), a: (T, M), Q
+
+    def collapse(self, T) -> SmallOutputEmissions:
+        f = self.fan_out
+        fills = all(isinstance(v, Fill) for v in (self.Hs, self.hs, f.Hs, f.hs))
+        n = 1 if fills else T
+        H = _dense_steps(self.Hs, n)
+        h = _dense_steps(self.hs, n)
+        A = _dense_steps(f.Hs, n)
+        a = _dense_steps(f.hs, n)
+        Hs = np.einsum("tmk,tkd->tmd", A, H)
+        hs = np.einsum("tmk,tk->tm", A, h) + a
+        if fills:
+            return SmallOutputEmissions(Fill(Hs[0], T), Fill(hs[0], T), f.Rs)
+        return SmallOutputEmissions(Hs, hs, f.Rs)
+
+    @property
+    def M(self):
+        return self.fan_out.M
+
+    @property
+    def r_dense(self):
+        return self.fan_out.r_dense
+
+
+def _dense_steps(v, n):
+    if isinstance(v, Fill):
+        return np.broadcast_to(v.value, (n,) + v.value.shape)
+    v = np.asarray(v, dtype=np.float64)
+    return v if v.shape[0] == n else np.broadcast_to(v[0], (n,) + v.shape[1:])
+
+
+@dataclass
 class LGSSM:
     """lgssm.jl:9-12."""
     transitions: GaussMarkovModel
@@ -139,6 +186,8 @@ class _Marshalled:
         tr, em = model.transitions, model.emissions
         T = len(model)
         D = model.D
+        if isinstance(em, BottleneckEmissions):
+            em = em.collapse(T)
         d = tgp_lgssm()
         vector = isinstance(em, SmallOutputEmissions)
         M = em.M if vector else 1
@@ -188,6 +237,8 @@ def transform_model_and_obs(model: LGSSM, y):
     miss = np.ma.getmaskarray(y)
     y = np.array(np.ma.getdata(y), dtype=np.float64, copy=True)
     T = len(model)
+    if isinstance(model.emissions, BottleneckEmissions):
+        model = replace(model, emissions=model.emissions.collapse(T))
     em = model.emissions
     Rs = em.Rs
     if not isinstance(em, SmallOutputEmissions):
@@ -223,7 +274,10 @@ def _maybe_missing(model, y):
 
 def replace_observation_noise_cov(model: LGSSM, Rs_new) -> LGSSM:
     """missings.jl:35-41."""
-    return replace(model, emissions=replace(model.emissions, Rs=Rs_new))
+    em = model.emissions
+    if isinstance(em, BottleneckEmissions):
+        return replace(model, emissions=replace(em, fan_out=replace(em.fan_out, Rs=Rs_new)))
+    return replace(model, emissions=replace(em, Rs=Rs_new))
 
 
 # ---- the five entry points -----------------------------------------------------------------------
@@ -269,7 +323,7 @@ def posterior(model: LGSSM, y, handle: Optional[Handle] = None) -> LGSSM:
 
 
 def _emission_dim(model: LGSSM) -> int:
-    return model.emissions.M if isinstance(model.emissions, SmallOutputEmissions) else 0
+    return model.emissions.M if isinstance(model.emissions, (SmallOutputEmissions, BottleneckEmissions)) else 0
 
 
 def marginals(model: LGSSM, handle: Optional[Handle] = None) -> Tuple[np.ndarray, np.ndarray]:

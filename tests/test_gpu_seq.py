@@ -176,3 +176,54 @@ def test_space_time_posterior_matches_dense_gp(pkg, regular):
         z = np.linalg.solve(Lc, y_post - mu_d)
         lp_d = -0.5 * (len(mu_d) * np.log(2 * np.pi) + 2 * np.log(np.diag(Lc)).sum() + z @ z)
         assert abs(lp - lp_d) <= 1e-6 + 1e-6 * abs(lp_d), (lp, lp_d, order)
+
+
+@pytest.mark.parametrize("ordering", ["forward", "reverse"])
+def test_large_output_and_bottleneck_emissions(pkg, handle, ordering):
+    """LargeOutputLGC (LGC:153-204, Dobs > Dlat) and BottleneckLGC (LGC:258-335) emissions: logpdf and the filtering distributions
+    against the reference's OWN arithmetic for those types (oracle: posterior_and_lml_large / _bottleneck, incl. their jitters)."""
+    rng = np.random.default_rng(31)
+    from tests.util import random_psd, _stable
+    T, D, M, K = 23, 3, 7, 2
+    As = np.stack([_stable(0.9 * np.eye(D) + 0.1 * rng.standard_normal((D, D))) for _ in range(T)])
+    as_ = rng.standard_normal((T, D)) * 0.3
+    Qs = np.stack([random_psd(rng, D) for _ in range(T)])
+    m0, P0 = rng.standard_normal(D), random_psd(rng, D, 0.5, 2.0)
+    L = pkg.lgssm
+    tr = L.GaussMarkovModel(ordering, As, as_, Qs, L.Gaussian(m0, P0))
+    idx = range(T) if ordering == "forward" else range(T - 1, -1, -1)
+
+    def run_oracle(update):
+        m, P, lmls, ms = m0, P0, np.zeros(T), np.zeros((T, D))
+        for t in idx:
+            if ordering == "forward":
+                m, P = O.predict(m, P, As[t], as_[t], Qs[t])
+                m, P, lmls[t] = update(t, m, P)
+                ms[t] = m
+            else:
+                m, P, lmls[t] = update(t, m, P)
+                ms[t] = m
+                m, P = O.predict(m, P, As[t], as_[t], Qs[t])
+        return lmls.sum(), ms
+
+    # LargeOutputLGC: Dobs = 7 > Dlat = 3
+    Hs = rng.standard_normal((T, M, D)); hs = rng.standard_normal((T, M)) * 0.2
+    Rs = np.stack([random_psd(rng, M, 0.1, 1.0) for _ in range(T)])
+    y = rng.standard_normal((T, M))
+    ref, ms_o = run_oracle(lambda t, m, P: O.posterior_and_lml_large(m, P, Hs[t], hs[t], Rs[t], y[t]))
+    model = L.LGSSM(tr, L.LargeOutputEmissions(Hs, hs, Rs))
+    lml = L.logpdf(model, y, handle)
+    assert abs(lml - ref) <= 1e-6 * abs(ref), (lml, ref)
+    ms, _ = L._filter(model, y, handle)
+    np.testing.assert_allclose(ms, ms_o, rtol=1e-5, atol=1e-7)
+    # BottleneckLGC: project D = 3 -> K = 2, fan out to M = 7
+    Hp = rng.standard_normal((T, K, D)); hp = rng.standard_normal((T, K)) * 0.2
+    Af = rng.standard_normal((T, M, K)); af = rng.standard_normal((T, M)) * 0.2
+    ref, ms_o = run_oracle(lambda t, m, P: O.posterior_and_lml_bottleneck(m, P, Hp[t], hp[t], Af[t], af[t], Rs[t], y[t]))
+    model = L.LGSSM(tr, L.BottleneckEmissions(Hp, hp, L.LargeOutputEmissions(Af, af, Rs)))
+    lml = L.logpdf(model, y, handle)
+    assert abs(lml - ref) <= 1e-6 * abs(ref), (lml, ref)
+    ms, _ = L._filter(model, y, handle)
+    np.testing.assert_allclose(ms, ms_o, rtol=1e-5, atol=1e-7)
+    mu, var = L.marginals_diag(model, handle)        # predict_marginals(x, ::BottleneckLGC) (LGC:311-313)
+    assert mu.shape == (T, M) and np.all(var > 0)
