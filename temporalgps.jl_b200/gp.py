@@ -480,7 +480,8 @@ def merge_datasets(x1, x2, S1, S2, y1, y2):
     x_raw = np.concatenate([_times(_time_axis(x1)), _times(_time_axis(x2))])
     idx = np.argsort(x_raw, kind="stable")
     inv = np.argsort(idx, kind="stable")
-    n1 = len(_time_axis(x1))
+    n1, n2 = len(_time_axis(x1)), len(_time_axis(x2))
+    S1, S2 = (_dense(S, n) if isinstance(S, Fill) else np.asarray(S) for S, n in ((S1, n1), (S2, n2)))
     S = np.concatenate([S1, S2])[idx]
     ys = np.concatenate([y1, y2])[idx]
     x = RectilinearGrid(x1.xl, x_raw[idx]) if _is_grid(x1) else x_raw[idx]
