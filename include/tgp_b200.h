@@ -144,6 +144,20 @@ int tgp_marginals(tgp_handle h, const tgp_lgssm* model, double* mean_out, double
  */
 int tgp_marginals_diag(tgp_handle h, const tgp_lgssm* model, double* mean_out, double* var_out);
 
+/* tgp_lti_components replaces broadcast_components((F, q, H), x0, t::AbstractVector, storage)   src/gp/lti_sde.jl:136-147
+ *              — the model construction of an IRREGULAR time grid, on the device: with t' = vcat(t[0] - 1, t),
+ *                  A[i] = exp(F * (t'[i+1] - t'[i])),   Q[i] = P - A[i] P A[i]'      (P read as Symmetric: upper triangle)
+ *              written as T x D x D arrays, column-major per step — exactly what tgp_lgssm.A / .Q take with sA = sQ = D * D, so a
+ *              caller holding (F, P, t) ships 8 B/step (t) instead of 16 D^2 B/step and spends no host matrix exponentials.
+ *              F, P (and F0) are D x D column-major on the HOST; t (T doubles) and the outputs may be host or device. F0, if
+ *              non-NULL, is the drift of the FIRST transition (dt = 1): a kernel stretched in time (lti_sde.jl:361-373) passes
+ *              its stretched drift as F and the unstretched one as F0, block by block for a sum of kernels (lti_sde.jl:386-418).
+ *              Device outputs are stream-ordered (usable by the next call on this handle without a synchronisation).
+ *              Matrix exponential: scaling and squaring with a degree-12 Taylor polynomial at |F dt| / 2^s <= 1/4.
+ */
+int tgp_lti_components(tgp_handle h, int32_t D, int64_t T, const double* F, const double* F0, const double* P, const double* t,
+                       double* A_out, double* Q_out);
+
 /* tgp_posterior_marginals fuses the chain used by marginals(::FinitePosteriorLTISDE) at the
  *              training inputs (src/gp/posterior_lti_sde.jl:27-36):
  *              posterior(model, y) -> replace_observation_noise_cov(., R_new) -> marginals(.)

@@ -70,6 +70,8 @@ _SIGS = {
                                 C.c_void_p]),
     "tgp_marginals": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p]),
     "tgp_marginals_diag": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p]),
+    "tgp_lti_components": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
     "tgp_posterior_marginals": (C.c_int, [C.c_void_p, C.POINTER(tgp_lgssm), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
     "tgp_debug_tc_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -219,6 +221,16 @@ class Handle:
 
     def marginals_diag(self, desc, mean_out, var_out):
         self.check(lib().tgp_marginals_diag(self._h, C.byref(desc), ptr(mean_out), ptr(var_out)))
+
+    def lti_components(self, F, P, t, A_out, Q_out, F0=None):
+        """F, P, F0: (D, D) host arrays (mathematical orientation); t, A_out, Q_out: host arrays or device tensors."""
+        F = np.asfortranarray(F, dtype=np.float64)
+        P = np.asfortranarray(P, dtype=np.float64)
+        F0 = None if F0 is None else np.asfortranarray(F0, dtype=np.float64)
+        D = F.shape[0]
+        T = t.numel() if hasattr(t, "numel") else len(t)
+        self.check(lib().tgp_lti_components(self._h, D, int(T), F.ctypes.data, None if F0 is None else F0.ctypes.data, P.ctypes.data,
+                                            ptr(t), ptr(A_out), ptr(Q_out)))
 
     def posterior_marginals(self, desc, y, R_new, sRnew, mean_out, var_out, lml_out=None):
         self.check(lib().tgp_posterior_marginals(self._h, C.byref(desc), ptr(y), ptr(R_new), int(sRnew), ptr(mean_out),

@@ -70,6 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     jobs.append((os.path.join(CSRC, "tgp_dense.cu"), os.path.join(BUILD, "tgp_dense.o"), [], os.path.join(BUILD, "tgp_dense.log")))
     jobs.append((os.path.join(CSRC, "tgp_xchg.cu"), os.path.join(BUILD, "tgp_xchg.o"), [], os.path.join(BUILD, "tgp_xchg.log")))
     jobs.append((os.path.join(CSRC, "tgp_seq.cu"), os.path.join(BUILD, "tgp_seq.o"), [], os.path.join(BUILD, "tgp_seq.log")))
+    jobs.append((os.path.join(CSRC, "tgp_lti.cu"), os.path.join(BUILD, "tgp_lti.o"), [], os.path.join(BUILD, "tgp_lti.log")))
     for d in TGP_DIMS:
         jobs.append((os.path.join(CSRC, "tgp_inst.cu"), os.path.join(BUILD, f"tgp_inst_d{d}.o"), [f"-DTGP_D={d}"],
                      os.path.join(BUILD, f"tgp_inst_d{d}.log")))

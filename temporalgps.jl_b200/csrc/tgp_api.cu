@@ -282,6 +282,17 @@ int tgp_marginals_diag(tgp_handle h, const tgp_lgssm* model, double* mean_out, d
 #undef CALL
 }
 
+int tgp_lti_components(tgp_handle h, int32_t D, int64_t T, const double* F, const double* F0, const double* P, const double* t,
+                       double* A_out, double* Q_out) {
+    if (!h) return TGP_EINVAL;
+    if (D < 1 || T < 1) return fail(h, TGP_EINVAL, "D and T must be >= 1 (got D=%d, T=%lld)", D, (long long)T);
+    if (!F || !P || !t || !A_out || !Q_out) return fail(h, TGP_EINVAL, "F, P, t, A_out and Q_out must be non-NULL");
+    if (is_device_ptr(F) || is_device_ptr(P) || (F0 && is_device_ptr(F0)))
+        return fail(h, TGP_EINVAL, "F, F0 and P are read on the host (D x D doubles each)");
+    TGP_TRY(begin_call(h));
+    return lti_components(h, D, T, F, F0, P, t, A_out, Q_out);
+}
+
 int tgp_posterior_marginals(tgp_handle h, const tgp_lgssm* model, const double* y, const double* R_new, int64_t sRnew,
                             double* mean_out, double* var_out, double* lml_out) {
     TGP_TRY(validate(h, model, true, y));

@@ -31,6 +31,10 @@ int seq_marginals(tgp_ctx* h, const tgp_lgssm* m, double* mean_out, double* cov_
 int seq_posterior_marginals(tgp_ctx* h, const tgp_lgssm* m, const double* y, const double* R_new, int64_t sRnew, double* mean_out,
                             double* var_out, double* lml_out);
 
+// Device-side construction of (A[t], Q[t]) of an LTI SDE on an irregular grid (tgp_lti.cu).
+int lti_components(tgp_ctx* h, int D, int64_t T, const double* F, const double* F0, const double* P, const double* t, double* A_out,
+                   double* Q_out);
+
 // Peer-memory exchange of the time-sharded path (tgp_xchg.cu).
 int xchg_create(tgp_ctx* h, int rank, int world, int slot_doubles, void* ipc_handle_out);
 int xchg_open(tgp_ctx* h, const void* handles_all);

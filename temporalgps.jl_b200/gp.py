@@ -230,6 +230,43 @@ def lgssm_components(k: Kernel, t):
     return As, Fill(np.zeros(D), T), Qs, Fill(H, T), Fill(np.zeros(()), T), Gaussian(np.zeros(D), P)
 
 
+def sde_components(k: Kernel):
+    """(F, F0, H, P) of any kernel built from the simple kernels with +, scaling and time stretching (lti_sde.jl:334-418), as ONE
+    LTI SDE: block-diagonal drift F and stationary covariance P, concatenated H. F carries the time stretches (exp(F dt) is the
+    transition over an UNSTRETCHED step dt); F0 is the drift without them, used by the first transition (lti_sde.jl:139, 361-373)."""
+    if isinstance(k, KernelSum):
+        parts = [sde_components(kk) for kk in k.kernels]
+        return (_block_diag([p[0] for p in parts]), _block_diag([p[1] for p in parts]), np.concatenate([p[2] for p in parts]),
+                _block_diag([p[3] for p in parts]))
+    if isinstance(k, ScaledKernel):
+        F, F0, H, P = sde_components(k.kernel)
+        return F, F0, math.sqrt(k.s2) * H, P
+    if isinstance(k, TransformedKernel):
+        F, F0, H, P = sde_components(k.kernel)
+        return k.s * F, F0, H, P
+    F, H, P = _sde(k)
+    return F, F, H, P
+
+
+# Irregular grids at least this long get their transitions from the device (tgp_lti_components); shorter ones from the host loop.
+DEVICE_COMPONENTS_MIN_T = 512
+
+
+def lgssm_components_device(k: Kernel, t, handle):
+    """lgssm_components for an irregular grid with A[t], Q[t] computed and KEPT on the GPU (tgp_lti_components): the host ships the
+    time stamps (8 B/step), not the model (16 D^2 B/step), and computes no matrix exponentials."""
+    import torch
+    F, F0, H, P = sde_components(k)
+    D, T = F.shape[0], len(t)
+    dev = torch.device("cuda", handle.device)
+    tt = torch.from_numpy(np.ascontiguousarray(_times(t), dtype=np.float64)).to(dev)
+    A = torch.empty(T * D * D, dtype=torch.float64, device=dev)
+    Q = torch.empty(T * D * D, dtype=torch.float64, device=dev)
+    handle.lti_components(F, P, tt, A, Q, F0)
+    return (L.DeviceSteps(A, T, (D, D)), Fill(np.zeros(D), T), L.DeviceSteps(Q, T, (D, D)), Fill(H, T), Fill(np.zeros(()), T),
+            Gaussian(np.zeros(D), P))
+
+
 def _dense(v, T):
     if isinstance(v, Fill):
         return np.broadcast_to(v.value, (T,) + v.value.shape).copy()
@@ -340,6 +377,18 @@ def _noise_to_time_form(x, noise):
     return noise
 
 
+def _device_components_ok(f) -> bool:
+    """The device builder needs a GPU and a kernel instantiation for the composite latent dimension."""
+    import torch
+    if not torch.cuda.is_available():
+        return False          # model construction alone stays possible on a host without a GPU; inference does not
+    try:
+        D = sde_components(f.f.kernel)[0].shape[0]
+    except Exception:     # noqa: BLE001 — a kernel without an SDE form raises where it always did (lgssm_components)
+        return False
+    return D in (1, 2, 3, 4, 5, 6, 8, 10)
+
+
 def build_lgssm(f: LTISDE, x, noise) -> LGSSM:
     """build_lgssm — lti_sde.jl:71-80 (+ mean handling :112-131)."""
     if isinstance(f.f.kernel, Separable):
@@ -352,7 +401,10 @@ def build_lgssm(f: LTISDE, x, noise) -> LGSSM:
         else:
             Rs = np.asarray(noise, dtype=np.float64).reshape(T, Nr)
         return LGSSM(GaussMarkovModel(Forward, As, as_, Qs, x0), SmallOutputEmissions(Hs, hs, Rs))
-    As, as_, Qs, Hs, hs, x0 = lgssm_components(f.f.kernel, x)
+    if not isinstance(x, RegularSpacing) and len(x) >= DEVICE_COMPONENTS_MIN_T and _device_components_ok(f):
+        As, as_, Qs, Hs, hs, x0 = lgssm_components_device(f.f.kernel, x, f.storage.handle())
+    else:
+        As, as_, Qs, Hs, hs, x0 = lgssm_components(f.f.kernel, x)
     mean = f.f.mean
     if mean is not None and not callable(mean) and isinstance(hs, Fill):
         hs = Fill(hs.value + float(mean), len(x))          # ConstMean: mean_vector is a Fill, hs stays a Fill

@@ -46,6 +46,36 @@ class Fill:
         return (self.T,) + self.value.shape
 
 
+class DeviceSteps:
+    """A per-step array that already lives on the GPU in the library's layout (contiguous per step, matrices column-major), e.g.
+    the transitions written by tgp_lti_components. It crosses the boundary by address; nothing is copied or re-laid out."""
+
+    def __init__(self, tensor, T: int, inner_shape):
+        self.tensor, self.T, self.inner_shape = tensor, int(T), tuple(inner_shape)
+        if tensor.numel() != self.T * int(np.prod(self.inner_shape)):
+            raise DimensionMismatch(_lib.TGP_EINVAL, "Dimension mismatch. device per-step array has the wrong number of elements")
+
+    def __len__(self):
+        return self.T
+
+    @property
+    def shape(self):
+        return (self.T,) + self.inner_shape
+
+    def numpy(self):
+        """Host copy in mathematical orientation (T, *inner_shape) — for inspection and tests."""
+        a = self.tensor.detach().cpu().numpy().reshape((self.T,) + self.inner_shape[::-1])
+        return np.swapaxes(a, -1, -2) if len(self.inner_shape) == 2 else a
+
+
+class _DevAddr:
+    """What _Marshalled keeps alive for a DeviceSteps field (mimics the `.ctypes.data` of a host array)."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.ctypes = type("addr", (), {"data": tensor.data_ptr()})()
+
+
 @dataclass
 class Gaussian:
     """gaussian.jl:16-19."""
@@ -165,6 +195,10 @@ def _per_step(x, T, inner_ndim, colmajor=False):
         if colmajor:
             v = v.T
         return np.ascontiguousarray(v, dtype=np.float64), 0
+    if isinstance(x, DeviceSteps):
+        if len(x) != T or len(x.inner_shape) != inner_ndim:
+            raise DimensionMismatch(_lib.TGP_EINVAL, f"Dimension mismatch. per-step array has shape {x.shape}, model has T={T}")
+        return _DevAddr(x.tensor), int(np.prod(x.inner_shape))
     x = np.asarray(x, dtype=np.float64)
     if x.ndim == inner_ndim:
         return np.ascontiguousarray(x.T if colmajor else x), 0

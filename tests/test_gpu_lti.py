@@ -1,0 +1,86 @@
+"""tgp_lti_components — device-side model construction for irregular time grids: the arrays it writes are
+compared with the oracle's host construction (scipy expm: lti_sde.jl:136-147), and the GP-level calls that now use it are compared
+with the oracle end to end."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["matern12", "matern32", "matern52"])
+@pytest.mark.parametrize("spread", [1e-3, 1.0, 40.0])
+def test_components_match_host_expm(pkg, name, spread):
+    """A[t] = exp(F dt), Q[t] = P - A P A' against scipy's Pade expm, over six decades of step sizes (including dt = 0)."""
+    from scipy.linalg import expm
+    import torch
+    k = {"matern12": pkg.Matern12Kernel(), "matern32": pkg.Matern32Kernel(), "matern52": pkg.Matern52Kernel()}[name]
+    F, F0, H, P = pkg.gp.sde_components(k)
+    D = F.shape[0]
+    rng = np.random.default_rng(5)
+    T = 3000
+    dts = rng.exponential(spread, T) * 10.0 ** rng.uniform(-3, 0, T)
+    dts[7] = 0.0
+    t = np.cumsum(dts)
+    h = pkg.default_handle()
+    A = torch.empty(T * D * D, dtype=torch.float64, device="cuda")
+    Q = torch.empty(T * D * D, dtype=torch.float64, device="cuda")
+    h.lti_components(F, P, torch.from_numpy(t).cuda(), A, Q, F0)
+    h.synchronize()
+    A = np.swapaxes(A.cpu().numpy().reshape(T, D, D), 1, 2)
+    Q = np.swapaxes(Q.cpu().numpy().reshape(T, D, D), 1, 2)
+    dt_ref = np.diff(np.concatenate([[t[0] - 1.0], t]))
+    for i in list(range(0, 12)) + list(rng.integers(0, T, 200)):
+        Ar = expm(F * dt_ref[i])
+        Qr = P - Ar @ P @ Ar.T
+        assert np.allclose(A[i], Ar, rtol=1e-12, atol=1e-13 * max(1.0, np.abs(Ar).max())), (i, dt_ref[i])
+        assert np.allclose(Q[i], Qr, rtol=1e-10, atol=1e-12 * np.abs(P).max()), (i, dt_ref[i])
+        assert np.array_equal(Q[i], Q[i].T)
+
+
+def test_host_outputs_and_host_times(pkg):
+    """Every data pointer may be a host pointer: same numbers as with device buffers."""
+    import torch
+    F, F0, H, P = pkg.gp.sde_components(pkg.Matern32Kernel())
+    T = 777
+    t = np.sort(np.random.default_rng(1).uniform(0, 30, T))
+    h = pkg.default_handle()
+    Ah, Qh = np.empty(T * 4), np.empty(T * 4)
+    h.lti_components(F, P, t, Ah, Qh, F0)
+    Ad = torch.empty(T * 4, dtype=torch.float64, device="cuda")
+    Qd = torch.empty(T * 4, dtype=torch.float64, device="cuda")
+    h.lti_components(F, P, torch.from_numpy(t).cuda(), Ad, Qd)
+    h.synchronize()
+    assert np.array_equal(Ah, Ad.cpu().numpy()) and np.array_equal(Qh, Qd.cpu().numpy())
+
+
+def test_irregular_grid_gp_calls_use_the_device_builder(pkg):
+    """to_sde(GP)(t_irregular, s2): logpdf / posterior marginals / rand-free paths against the oracle's host-built model, for a sum of
+    scaled and stretched kernels (block-diagonal drift, per-block first step)."""
+    from oracle import tgp_oracle as O
+    rng = np.random.default_rng(9)
+    T = 6000
+    t = np.sort(rng.uniform(0.0, 50.0, T))
+    G = pkg.gp
+    k = G.KernelSum([G.ScaledKernel(G.TransformedKernel(pkg.Matern32Kernel(), 1.0 / 1.3), 0.8),
+                     G.ScaledKernel(G.TransformedKernel(pkg.Matern52Kernel(), 1.0 / 0.4), 1.5)])
+    ko = O.Sum([O.Scaled(0.8, O.Stretched(1.0 / 1.3, O.Matern32())), O.Scaled(1.5, O.Stretched(1.0 / 0.4, O.Matern52()))])
+    model_o = O.build_lgssm(ko, t, 0.2)
+    y = O.sample_prior(model_o, rng)
+    h = pkg.default_handle()
+    fx = pkg.to_sde(pkg.GP(k))(t, 0.2)
+    model = fx.build_lgssm()
+    assert isinstance(model.transitions.As, pkg.lgssm.DeviceSteps)           # built on the device
+    assert np.allclose(model.transitions.As.numpy(), model_o.As, rtol=1e-9, atol=1e-12)
+    assert np.allclose(model.transitions.Qs.numpy(), model_o.Qs, rtol=1e-8, atol=1e-11)
+    names = []
+    h.set_timing(True)
+    lml = pkg.gp.logpdf(fx, y)
+    names = [n for n, _, _ in h.timing()]
+    h.set_timing(False)
+    assert "k_lti_components" in names
+    ref = O.logpdf(model_o, y)
+    assert abs(lml - ref) <= 1e-6 * abs(ref)
+    tp = np.sort(rng.uniform(-1.0, 51.0, 700))
+    mu, var = pkg.gp.marginals(pkg.gp.posterior(fx, y)(tp, 0.01))
+    mu_o, var_o = O.gp_posterior_marginals(ko, t, 0.2, y, tp, 0.01)
+    assert np.allclose(mu, mu_o, rtol=1e-5, atol=1e-7) and np.allclose(var, var_o, rtol=1e-5, atol=1e-9)
