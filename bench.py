@@ -235,7 +235,12 @@ def run_ours(args):
     mm = pkg.lgssm._Marshalled(fx.build_lgssm())
     seed_of = lambda r, i: 20261017 + 2 + 97 * i + 1000 * r      # noqa: E731
     ys_host = [synth_y(T, seed_of(rank, i)) for i in range(N_BUF)]
-    ys_dev = [torch.from_numpy(v).to(dev) for v in ys_host]
+    HALO = sharded.TGP_SHARD_HALO
+    # Overlapped scatter (N > 1): every rank's buffer is [the 3072 observations before its shard | its shard]; the kernels read the
+    # halo in place, so no GPU ever waits for another. The views below are the shards themselves (what the exchange layout uses too).
+    halos = [synth_y(T, seed_of(rank - 1, i))[-HALO:] if rank > 0 else np.zeros(HALO) for i in range(N_BUF)] if world > 1 else None
+    ys_pad = [torch.from_numpy(np.concatenate([halos[i], v]) if world > 1 else v).to(dev) for i, v in enumerate(ys_host)]
+    ys_dev = [p[HALO:] if world > 1 else p for p in ys_pad]
     lml_dev = torch.zeros(1, dtype=torch.float64, device=dev)
     lml_host = np.zeros(1)
     sh = None
@@ -248,7 +253,7 @@ def run_ours(args):
         def finish():
             pass
     else:
-        sh = sharded.ShardedLogpdf(h, mm, rank, world, dev)
+        sh = sharded.ShardedLogpdf(h, mm, rank, world, dev, overlap=(args.shard_layout == "overlap"))
 
         def step(i):
             sh.logpdf(ys_dev[i % N_BUF], None, sync=False)      # one launch per shard; the partial lmls land in every rank's buffer
@@ -270,8 +275,28 @@ def run_ours(args):
     h.synchronize()
     lml_weak = float(lml_dev.item())
 
+    # ---- the other shard layout, for comparison (N > 1): same series, same kernels, halo received over NVLink vs read in place -----
+    alt = None
+    if sh is not None and sh.route == "fir":
+        alt_layout = "exchange" if sh.overlap else "overlap"
+        sh_alt = sharded.ShardedLogpdf(h, mm, rank, world, dev, overlap=(alt_layout == "overlap"))
+
+        def step_alt(i):
+            sh_alt.logpdf(ys_dev[i % N_BUF], None, sync=False)
+
+        def finish_alt():
+            sh_alt.result(lml_dev)
+        ms_alt = timed(step_alt, finish_alt)
+        step_alt(0)
+        finish_alt()
+        h.synchronize()
+        alt = {"shard_layout": alt_layout, "ms_per_step": ms_alt, "value": Tglob / (ms_alt * 1e-3), "unit": "steps/s",
+               "lml": float(lml_dev.item())}
+        assert abs(alt["lml"] - lml_weak) <= 1e-9 * abs(lml_weak), (alt["lml"], lml_weak)
+
     # ---- e2e: public API, pinned host y, H2D + D2H inside the timed region -------------------------
-    pin = [torch.from_numpy(v).pin_memory() for v in ys_host[:2]]
+    with_halo = world > 1 and rank > 0 and sh is not None and sh.overlap
+    pin = [torch.from_numpy(np.concatenate([halos[i], v]) if with_halo else v).pin_memory() for i, v in enumerate(ys_host[:2])]
     pin_np = [p.numpy() for p in pin]
     if world == 1:
         def e2e_step(i):
@@ -333,7 +358,12 @@ def run_ours(args):
         per = STRONG_T // world
         cpr = per // STRONG_CHUNK                                   # chunks per rank
         mm4 = pkg.lgssm._Marshalled(f(pkg.RegularSpacing(0.0, DT, per), SIGMA2).build_lgssm())
-        ys4 = [torch.cat([torch.from_numpy(strong_chunk(rank * cpr + c, b)) for c in range(cpr)]).to(dev) for b in range(2)]
+        def series4(b):      # [halo | this rank's chunks]: the overlapped scatter of config 4's series
+            parts = [torch.from_numpy(strong_chunk(rank * cpr - 1, b)[-HALO:]) if rank > 0 else torch.zeros(HALO, dtype=torch.float64)]
+            parts += [torch.from_numpy(strong_chunk(rank * cpr + c, b)) for c in range(cpr)]
+            return torch.cat(parts).to(dev)
+        ys4_pad = [series4(b) for b in range(2)]
+        ys4 = [p[HALO:] for p in ys4_pad]
         if world == 1:
             def step4(i):
                 h.logpdf(mm4.desc, ys4[i % 2], lml_dev)
@@ -341,7 +371,7 @@ def run_ours(args):
             def finish4():
                 pass
         else:
-            sh4 = sharded.ShardedLogpdf(h, mm4, rank, world, dev)
+            sh4 = sharded.ShardedLogpdf(h, mm4, rank, world, dev, overlap=(args.shard_layout == "overlap"))
 
             def step4(i):
                 sh4.logpdf(ys4[i % 2], None, sync=False)
@@ -356,7 +386,7 @@ def run_ours(args):
                   "scaling": "strong", "hbm_frac_per_gpu": 8.0 * per / (ms4 * 1e-3) / 1e9 / hbm, "lml": float(lml_dev.item()),
                   "note": "BASELINE config 4: the SAME series of 8e7 steps at every world size (2 rotating buffer sets); "
                           "scaling = value(N) / value(1) across the lines of a --gpus sweep"}
-        del ys4
+        del ys4, ys4_pad
         torch.cuda.empty_cache()
         ys_dev = [torch.from_numpy(v).to(dev) for v in ys_host]
 
@@ -424,6 +454,9 @@ def run_ours(args):
 
     cfg = workload_config(T, world, args.algo)
     cfg["route"] = route
+    if sh is not None:
+        cfg["shard_layout"] = ("overlap: every shard is stored with the 3072 observations before it, no inter-GPU dependency inside a step"
+                               if sh.overlap else "exchange: the 3072-observation halo is pushed over NVLink by the previous rank's kernel")
     out = {
         "metric": METRIC, "value": value, "unit": "steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -441,6 +474,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "lml_rel_err_vs_oracle": parity.get("lml_rel_err_vs_oracle"),
         "strong_scaling": strong,
+        "other_shard_layout": alt,
         "filter_emit": extra,
         "secondary": secondary,
         "clocks": clk,
@@ -519,6 +553,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-filter", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the configs 3 / 5 extras")
+    ap.add_argument("--shard-layout", choices=["overlap", "exchange"], default="overlap",
+                    help="N > 1: how the series is scattered (overlap = each shard carries its 3072-observation halo)")
     ap.add_argument("--no-strong", action="store_true", help="skip the fixed-T = 8e7 (config 4) series")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -59,6 +59,12 @@ extern "C" {
 #define TGP_OPT_DEFER_STATUS 7  /* 1: tgp_shard_phase2 calls fold their status into a sticky device block and the next call does
                                  * NOT wait for it (consecutive sharded calls queue back to back on the stream);
                                  * tgp_synchronize() reports and clears the accumulated status                  */
+#define TGP_OPT_SHARD_OVERLAP 8  /* 1: the series was scattered WITH AN OVERLAP: on every rank > 0 the TGP_SHARD_HALO observations
+                                 * that precede the shard sit in device memory directly before y (y[-TGP_SHARD_HALO .. -1]).
+                                 * tgp_shard_logpdf then reads them in place instead of receiving them from rank - 1 over the
+                                 * exchange: the step has no inter-GPU dependency at all (the partial results still go to every
+                                 * peer's buffer). Set the same value on every rank.                              */
+#define TGP_SHARD_HALO       3072
 #define TGP_DENSE_F64        0  /* FP64 throughout (reference ArrayStorage(Float64)); library GEMMs              */
 #define TGP_DENSE_TF32X3     1  /* FP32 storage (reference ArrayStorage(Float32)): covariance algebra on the tcgen05
                                  * tensor cores as 3xTF32 split products with FP32 accumulation in TMEM; innovation

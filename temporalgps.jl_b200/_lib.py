@@ -21,6 +21,8 @@ TGP_OPT_ALGO, TGP_OPT_CHUNK, TGP_OPT_SS_TOL, TGP_OPT_TIMING, TGP_OPT_SS_PREFIX =
 TGP_ALGO_AUTO, TGP_ALGO_SCAN = 0, 1
 TGP_OPT_DENSE_MATH = 6
 TGP_OPT_DEFER_STATUS = 7
+TGP_OPT_SHARD_OVERLAP = 8
+TGP_SHARD_HALO = 3072
 TGP_DENSE_F64, TGP_DENSE_TF32X3 = 0, 1
 
 

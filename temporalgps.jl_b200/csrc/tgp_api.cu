@@ -177,6 +177,9 @@ int tgp_set_option(tgp_handle h, int option, int64_t value) {
             if (value < 0 || value > (int64_t(1) << 24)) return fail(h, TGP_EINVAL, "steady-state prefix must be in 0..2^24");
             h->ss_prefix = value;
             return TGP_OK;
+        case TGP_OPT_SHARD_OVERLAP:
+            h->shard_overlap = value != 0;
+            return TGP_OK;
         case TGP_OPT_DEFER_STATUS:
             h->defer_status = value != 0;
             if (h->defer_status && !h->sticky) {

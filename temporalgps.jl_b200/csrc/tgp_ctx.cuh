@@ -125,6 +125,7 @@ struct tgp_ctx {
     void* cublas = nullptr;                             // cublasHandle_t of the FP64 dense path (tgp_dense.cu), created on first use
     void* xchg = nullptr;                               // tgp::XchgState: peer-memory exchange of the time-sharded path (tgp_xchg.cu)
     tgp_fir_state fir;
+    bool shard_overlap = false;                         // TGP_OPT_SHARD_OVERLAP
     int shard_world = 1;                                // world size of the last tgp_shard_logpdf
 };
 

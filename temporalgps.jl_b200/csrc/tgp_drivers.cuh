@@ -622,12 +622,17 @@ int do_shard_logpdf(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, i
         const unsigned long long ep = *v.epoch + 1;
         FirXchg x{};
         char* mine = v.self + v.fir_off;
-        if (rank > 0) {
+        const bool overlap = h->shard_overlap;
+        if (overlap && rank > 0) {
+            if (!is_device_ptr(y))
+                return fail(h, TGP_EINVAL, "TGP_OPT_SHARD_OVERLAP: the shard (and the TGP_SHARD_HALO observations before it) must be device-resident");
+            x.local_halo = 1;
+        } else if (rank > 0) {
             x.halo = reinterpret_cast<const double*>(mine + L::halo_off(ep));
             x.halo_flag = reinterpret_cast<const unsigned long long*>(mine + L::halo_flag_off(ep));
             x.ack_out = reinterpret_cast<unsigned long long*>(v.prev + v.fir_off + L::ack_off());
         }
-        if (v.next) {
+        if (v.next && !overlap) {
             x.push_dst = reinterpret_cast<double*>(v.next + v.fir_off + L::halo_off(ep));
             x.push_flag = reinterpret_cast<unsigned long long*>(v.next + v.fir_off + L::halo_flag_off(ep));
             x.ack_in = reinterpret_cast<const unsigned long long*>(mine + L::ack_off());

@@ -52,6 +52,7 @@ struct FirXchg {                  // time-sharded use (all null / 0 on a single 
     unsigned long long* push_flag;         // successor's halo flag (peer memory)
     const unsigned long long* ack_in;      // own ack word: wait for >= epoch - ring before overwriting the ring slot
     unsigned long long ring;      // halo ring depth
+    int local_halo;               // rank > 0 with overlapped shards: the nb tiles before y[0] are in local memory at y - nb * 1024
     char* const* peers;           // mapped exchange buffers of all ranks: the partial log-likelihood goes to every peer
     unsigned long long lml_off;   // byte offset of this rank's {lml, epoch} word (ring slot of this epoch) inside a peer buffer
     unsigned long long epoch;     // exchange epoch of this call (the same on every rank)
@@ -421,7 +422,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     {
         const long long base = ntiles / G;
         // CTA 0 also runs the transient (rank 0: one round less) or, last, the halo and its first tiles' pass B (rank > 0: two less)
-        const long long less = (ar.x.halo ? 2 : 1) * kFirWarps;
+        const long long less = ar.x.local_halo ? 0 : (ar.x.halo ? 2 : 1) * kFirWarps;   // overlapped shard: CTA 0 is like any other
         const long long t0 = (G > 1 && base >= less + 2 * kFirWarps) ? base - less : base;   // tiles of CTA 0
         const long long rest = ntiles - t0;
         c0 = b == 0 ? 0 : t0 + (G > 1 ? rest * (b - 1) / (G - 1) : 0);
@@ -473,7 +474,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     };
     // CTAs b > 0: the last nb warps (they have a tile less than warps 0, 1 when the chunk is not a multiple of 16) first run pass A
     // over the nb tiles BEFORE the chunk (re-read from HBM) — staged like any other tile, and first in the queue.
-    const int halo_k = (b > 0 && wp >= kFirWarps - pl.nb) ? kFirWarps - wp : 0;      // tile c0 - halo_k
+    const int halo_k = ((b > 0 || ar.x.local_halo) && wp >= kFirWarps - pl.nb) ? kFirWarps - wp : 0;      // tile c0 - halo_k
     const bool halo_fast = halo_k > 0 && pl.aligned;
     if (ar.stagger_ns && (wp >> 2)) __nanosleep((unsigned)(wp >> 2) * ar.stagger_ns);   // de-phase the 4 warps of each scheduler
     // the lane powers first (one load per thread: ahead of, not behind, the 128 KB of observations this SM is about to request)
@@ -487,7 +488,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     __syncthreads();
     if (tid == 0) fir_trace(ar, 1);
     // ---- what precedes the chunk --------------------------------------------------------------------------------------
-    if (b == 0 && !exch_halo) {
+    if (b == 0 && !exch_halo && !ar.x.local_halo) {
         const double qh = fir_head<D>(pl, ar, sscan, sred, sring);
         if (tid == 0) ar.partials[G] = qh;
     } else if (halo_k > 0) {
@@ -612,7 +613,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
         asm volatile("griddepcontrol.wait;" ::: "memory");
         fir_trace(ar, 6);
         __stcg(ar.partials + b, t);
-        if (b == 0 && exch_halo) __stcg(ar.partials + G, 0.0);
+        if (b == 0 && (exch_halo || ar.x.local_halo)) __stcg(ar.partials + G, 0.0);
         __threadfence();
         s_last = atomicAdd(ar.counters, 1u) == (unsigned)G - 1;
     }

@@ -13,11 +13,17 @@ Rank r owns steps [b[r], b[r+1]) of ONE series. Three routes, chosen COLLECTIVEL
   "general"  everything else: tgp_shard_reduce folds the shard into one scan element (3D^2 + 2D doubles), all_gather, every rank
              folds the elements before it into x0 (tgp_shard_prefix), ordinary tgp_logpdf from that state, all_reduce.
 
+Route "fir" has a second data layout, `overlap=True`: the series is scattered so that every shard with rank > 0 is preceded IN ITS
+OWN device buffer by the TGP_SHARD_HALO (3072) observations before it (shard_with_halo below). The kernel then reads them in place —
+nothing is pushed between GPUs, no rank ever waits for another, and the only traffic left is the 16-byte partial result per peer.
+
 The reference has no analogue (single-threaded); host logic only here — arithmetic is in the library.
 """
 from __future__ import annotations
 
 import numpy as np
+
+from ._lib import TGP_SHARD_HALO  # noqa: F401  (re-exported: the overlapped layout's halo length)
 
 
 def shard_bounds(T_total: int, world: int):
@@ -27,6 +33,18 @@ def shard_bounds(T_total: int, world: int):
     for r in range(world):
         b.append(b[-1] + base + (1 if r < rem else 0))
     return b
+
+
+def shard_with_halo(torch, y_full_host, bounds, rank, device):
+    """The overlapped scatter: -> (buffer, shard view). buffer = [halo | shard] on `device`; the view is what logpdf() takes."""
+    from ._lib import TGP_SHARD_HALO
+    lo, hi = bounds[rank], bounds[rank + 1]
+    halo = TGP_SHARD_HALO if rank > 0 else 0
+    if lo - halo < 0:
+        raise ValueError(f"shard {rank} starts at {lo}: fewer than {halo} observations precede it")
+    buf = torch.empty(TGP_SHARD_HALO + hi - lo, dtype=torch.float64, device=device)   # same offset on every rank: 32-byte aligned view
+    buf[TGP_SHARD_HALO - halo:].copy_(torch.from_numpy(np.ascontiguousarray(y_full_host[lo - halo:hi])))
+    return buf, buf[TGP_SHARD_HALO:]
 
 
 def incoming_state(prefix_fn, D, elems, rank, m0, P0):
@@ -44,7 +62,7 @@ def agree(dist, world, flag: bool) -> bool:
 
 
 class ShardedLogpdf:
-    def __init__(self, handle, marshalled, rank, world, device, dist=None, route=None):
+    def __init__(self, handle, marshalled, rank, world, device, dist=None, route=None, overlap=False):
         import torch
         self.torch = torch
         if dist is None:
@@ -85,6 +103,7 @@ class ShardedLogpdf:
                 ok = self._open_exchange()
             if ok:
                 self.route = "fir"
+        self.overlap = bool(overlap) and self.route == "fir" and world > 1
         if self.route != "fir" and route in (None, "fir", "steady") and agree(dist, world, ti and d.T >= 65536 and self.D <= 6):
             self.route = "steady"
         if route == "general":
@@ -122,6 +141,10 @@ class ShardedLogpdf:
         sync=False: nothing waits on the host; failures surface at check()."""
         h, dist = self.h, self.dist
         if self.route == "fir":
+            if getattr(h, "_shard_overlap", None) != self.overlap:     # several ShardedLogpdf objects may share the handle
+                from ._lib import TGP_OPT_SHARD_OVERLAP
+                h.set_option(TGP_OPT_SHARD_OVERLAP, 1 if self.overlap else 0)
+                h._shard_overlap = self.overlap
             try:
                 h.shard_logpdf(self.mm.desc, y_dev, self.rank, self.world)
             except Exception as exc:                     # the plan declined this model (the same decision on every rank)
@@ -179,13 +202,18 @@ class ShardedLogpdf:
             self._deferred_on = False
 
     def logpdf_host(self, y_host_pinned):
-        """End-to-end variant: the shard's observations start in pinned host memory."""
+        """End-to-end variant: the shard's observations start in pinned host memory. With the overlapped layout the host array of a
+        rank > 0 is [the TGP_SHARD_HALO observations before the shard | the shard]."""
+        from ._lib import TGP_SHARD_HALO
         torch = self.torch
-        if self._ybuf is None or self._ybuf.numel() != len(y_host_pinned):
-            self._ybuf = torch.empty(len(y_host_pinned), dtype=torch.float64, device=self.dev)
+        n = len(y_host_pinned)
+        if self._ybuf is None or self._ybuf.numel() != n:
+            self._ypad = torch.empty(TGP_SHARD_HALO + n, dtype=torch.float64, device=self.dev)
+            self._ybuf = self._ypad[TGP_SHARD_HALO:]
             self._out = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._ybuf.copy_(torch.from_numpy(y_host_pinned), non_blocking=True)
-        self.logpdf(self._ybuf, self._out)
+        halo = TGP_SHARD_HALO if (self.overlap and self.rank > 0) else 0
+        self.logpdf(self._ybuf[halo:], self._out)
         return float(self._out.item())
 
     @property

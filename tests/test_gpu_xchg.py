@@ -34,7 +34,15 @@ Ts = hi - lo                                  # this rank's shard
 h = pkg.Handle(0)
 fx = pkg.to_sde(pkg.GP(pkg.Matern52Kernel()))(pkg.RegularSpacing(0.0, 0.01, Ts), 0.1)
 mm = pkg.lgssm._Marshalled(fx.build_lgssm())
-sh = sharded.ShardedLogpdf(h, mm, rank, world, dev, dist, route=os.environ["TGP_ROUTE"])
+ov = os.environ.get("TGP_OVERLAP") == "1"    # overlapped scatter: every shard carries the 3072 observations before it
+sh = sharded.ShardedLogpdf(h, mm, rank, world, dev, dist, route=os.environ["TGP_ROUTE"], overlap=ov)
+keep = []
+def put(y):
+    if ov:
+        buf, view = sharded.shard_with_halo(torch, y, b, rank, dev)
+        keep.append(buf)
+        return view
+    return torch.from_numpy(np.ascontiguousarray(y[lo:hi])).to(dev)
 assert sh.route == os.environ["TGP_ROUTE"], (sh.route, getattr(sh, "transport_error", None))
 mo = O.build_lgssm(O.Matern52(), O.RegularSpacing(0.0, 0.01, T), 0.1)
 cm = c_oracle.Model.from_lgssm(mo)
@@ -42,7 +50,7 @@ out = torch.zeros(1, dtype=torch.float64, device=dev)
 for rep in range(4):
     rng = np.random.default_rng(100 + rep)    # same series on every rank
     y = np.sin(np.arange(T) * 0.003) + 0.4 * rng.standard_normal(T)
-    yd = torch.from_numpy(np.ascontiguousarray(y[lo:hi])).to(dev)
+    yd = put(y)
     sh.logpdf(yd, out)
     torch.cuda.synchronize()
     ref = c_oracle.logpdf(cm, y)
@@ -56,7 +64,7 @@ for rep in range(3):
     rng = np.random.default_rng(200 + rep)
     y = np.cos(np.arange(T) * 0.002) + 0.4 * rng.standard_normal(T)
     refs.append(c_oracle.logpdf(cm, y))
-    yds.append(torch.from_numpy(np.ascontiguousarray(y[lo:hi])).to(dev))
+    yds.append(put(y))
 for rep in range(3):
     sh.logpdf(yds[rep], outs[rep], sync=False)
 sh.check()
@@ -69,11 +77,13 @@ print("rank", rank, "ok")
 '''
 
 
-@pytest.mark.parametrize("route,T", [("fir", 200_000), ("fir", 200_001), ("fir", 131_073), ("steady", 200_000)])
+@pytest.mark.parametrize("route,T", [("fir", 200_000), ("fir", 200_001), ("fir", 131_073), ("steady", 200_000),
+                                     ("fir+overlap", 200_000), ("fir+overlap", 200_001)])
 def test_time_sharded_logpdf_two_processes(pkg, tmp_path, route, T):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, TGP_ROOT=ROOT, OMP_NUM_THREADS="1", TGP_ROUTE=route, TGP_T=str(T))
+    route, _, ov = route.partition("+")
+    env = dict(os.environ, TGP_ROOT=ROOT, OMP_NUM_THREADS="1", TGP_ROUTE=route, TGP_T=str(T), TGP_OVERLAP="1" if ov else "0")
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29541", str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
