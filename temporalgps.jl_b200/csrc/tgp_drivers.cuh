@@ -627,6 +627,8 @@ int do_shard_logpdf(tgp_ctx* h, const tgp_lgssm* m, const double* y, int rank, i
             if (!is_device_ptr(y))
                 return fail(h, TGP_EINVAL, "TGP_OPT_SHARD_OVERLAP: the shard (and the TGP_SHARD_HALO observations before it) must be device-resident");
             x.local_halo = 1;
+            // the ack word keeps advancing, so a later call with the exchange layout finds the ring slot free
+            x.ack_out = reinterpret_cast<unsigned long long*>(v.prev + v.fir_off + L::ack_off());
         } else if (rank > 0) {
             x.halo = reinterpret_cast<const double*>(mine + L::halo_off(ep));
             x.halo_flag = reinterpret_cast<const unsigned long long*>(mine + L::halo_flag_off(ep));

@@ -71,6 +71,21 @@ sh.check()
 for rep in range(3):
     got = float(outs[rep].item())
     assert abs(got - refs[rep]) <= 1e-6 * abs(refs[rep]), (rep, got, refs[rep])
+# both layouts interleaved on ONE handle (the exchange ring's acknowledgements must stay current while the overlap layout runs)
+if os.environ["TGP_ROUTE"] == "fir":
+    sh2 = sharded.ShardedLogpdf(h, mm, rank, world, dev, dist, route="fir", overlap=not ov)
+    order = [sh, sh, sh, sh, sh, sh, sh2, sh2, sh, sh2, sh2, sh2, sh2, sh2, sh2, sh]
+    outs = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in order]
+    rng = np.random.default_rng(300)
+    y = np.cos(np.arange(T) * 0.001) + 0.4 * rng.standard_normal(T)
+    ref = c_oracle.logpdf(cm, y)
+    buf, view = sharded.shard_with_halo(torch, y, b, rank, dev)
+    for s_, o_ in zip(order, outs):
+        s_.logpdf(view, o_, sync=False)
+    sh.check()
+    for i, o_ in enumerate(outs):
+        got = float(o_.item())
+        assert abs(got - ref) <= 1e-6 * abs(ref), ("mixed", i, got, ref)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
