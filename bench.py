@@ -526,7 +526,8 @@ def secondary_configs(pkg, h, torch):
     m5 = pkg.lgssm._Marshalled(fx5.build_lgssm())
     y5 = torch.from_numpy(np.random.default_rng(20261017 + 5).standard_normal((T5, Nr))).cuda()
     lml5 = np.zeros(1)
-    h5 = fx5._handle()           # the same handle, switched to the FP32-storage tensor-core arithmetic
+    h5 = pkg.Handle(h.device)    # its own handle and stream, switched to the FP32-storage tensor-core arithmetic
+    h5.set_dense_math(pkg.lgssm.TGP_DENSE_TF32X3)
     try:
         t5 = timeit(lambda: h5.logpdf(m5.desc, y5, lml5), 2, 1)
     finally:

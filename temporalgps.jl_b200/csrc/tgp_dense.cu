@@ -392,7 +392,10 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
     TGP_TRY(dalloc(h, 1, &w.err));
     TGP_TRY(dalloc(h, (size_t)((M + 31) / 32) * 1024, &w.Dinv));
     const bool ti = !(m->sA | m->sa | m->sQ | m->sH | m->sh | m->sR);
-    if (ti && h->algo == TGP_ALGO_AUTO) {
+    // Reverse ordering ends a step with predict(): after the freeze w.P would hold the PREDICTED covariance, which is not what
+    // P_f emits — so a Reverse model that emits P_f runs every step in full.
+    const bool may_freeze = !(m->ordering == TGP_REVERSE && P_f != nullptr);
+    if (ti && h->algo == TGP_ALGO_AUTO && may_freeze) {
         TGP_TRY(dalloc(h, (size_t)D * D, &w.Pprev));
         TGP_TRY(dalloc(h, 4, &w.conv));
         TGP_TRY(dalloc(h, 1, &w.ss_at));
