@@ -251,4 +251,21 @@ end
 marginals(m::B200LGSSM) = emit_marginals(m, false)
 marginals_diag(m::B200LGSSM) = emit_marginals(m, true)
 
+# broadcast_components((F, q, H), x0, t::AbstractVector, storage) — src/gp/lti_sde.jl:136-147 — on the device: A[i] = exp(F * dt[i]),
+# Q[i] = P - A[i] P A[i]' for an irregular grid, without T host matrix exponentials. F0: drift of the first transition (dt = 1) when
+# the kernel is stretched in time (lti_sde.jl:361-373), else F. Returns what the reference returns (Vectors of SMatrix); A_out / Q_out
+# may instead be device pointers (CuPtr from CUDA.jl) to keep the arrays resident and pass them on in a Desc.
+function lti_components(F::AbstractMatrix{<:Real}, P::AbstractMatrix{<:Real}, t::AbstractVector{<:Real}; F0 = F, device::Int = 0)
+    D = size(F, 1); T = length(t); h = handle(device)
+    Fc = Matrix{Float64}(F); F0c = Matrix{Float64}(F0); Pc = Matrix{Float64}(P); tc = Vector{Float64}(t)
+    A = Vector{Float64}(undef, T * D * D); Q = Vector{Float64}(undef, T * D * D)
+    GC.@preserve Fc F0c Pc tc A Q begin
+        check(h, ccall((:tgp_lti_components, LIB), Cint,
+                       (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       h, D, T, Fc, F0c, Pc, tc, A, Q))
+    end
+    As = collect(reinterpret(SMatrix{D,D,Float64,D * D}, A)); Qs = collect(reinterpret(SMatrix{D,D,Float64,D * D}, Q))
+    return As, Qs
+end
+
 end # module
