@@ -77,7 +77,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(_compile, jobs))
     cuda_lib = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "lib64")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart", "-lcublas", "-L" + cuda_lib, "-Xlinker", "-rpath=" + cuda_lib]
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart", "-L" + cuda_lib, "-Xlinker", "-rpath=" + cuda_lib]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("link failed:\n" + p.stderr[-4000:])

@@ -122,7 +122,6 @@ struct tgp_ctx {
     // instead of being resolved by the next call, so consecutive sharded calls queue back to back; tgp_synchronize reads it.
     bool defer_status = false;
     unsigned long long* sticky = nullptr;
-    void* cublas = nullptr;                             // cublasHandle_t of the FP64 dense path (tgp_dense.cu), created on first use
     void* xchg = nullptr;                               // tgp::XchgState: peer-memory exchange of the time-sharded path (tgp_xchg.cu)
     tgp_fir_state fir;
     bool shard_overlap = false;                         // TGP_OPT_SHARD_OVERLAP

@@ -4,23 +4,25 @@
 //     predict   m <- A m + a;  P <- (A * Symmetric(P)) * A' + Q                                  (LGC:46-52)
 //     update    V = H P;  S = chol(Symmetric(V H' + R));  B = U' \ V;  alpha = U' \ (y - H m - h)
 //               lml = -(M log 2pi + logdet S + alpha'alpha)/2;  m += B' alpha;  P -= B'B          (LGC:129-141)
-// In this round the GEMM-shaped pieces are LIBRARY calls (cuBLAS D/Sgemm, symm, trsm): this is the measured baseline
-// that the hand-written tcgen05 step kernel of the next round has to beat; the Cholesky, the residual / likelihood
-// and the bookkeeping kernels are ours. For time-invariant models one step is captured into a CUDA graph (a device-side
+// Every kernel on this path is ours: the FP64 products are tgp_dense_f64.cuh (tiled DFMA GEMM, GEMV, triangular solve), the
+// Cholesky, the residual / likelihood and the bookkeeping kernels are below; no library call is left (round 1 used cuBLAS here). For time-invariant models one step is captured into a CUDA graph (a device-side
 // step counter indexes y / outputs) and replayed T times, so the host issues one launch per step instead of ~14.
-#include <cublas_v2.h>
-
 #include <algorithm>
 #include <cstdlib>
 
 #include "tgp_ctx.cuh"
+#include "tgp_dense_f64.cuh"
 
 namespace tgp {
 
-#define TGP_CUBLAS(h, call)                                                                                        \
+// one of the FP64 product kernels: name it for the timing table, launch, count
+#define TGP_F64(h, name, call)                                                                                     \
     do {                                                                                                           \
-        cublasStatus_t s_ = (call);                                                                                \
-        if (s_ != CUBLAS_STATUS_SUCCESS) return fail(h, TGP_ECUDA, "%s failed: cuBLAS status %d (%s:%d)", #call, (int)s_, __FILE__, __LINE__); \
+        TGP_K(h, name);                                                                                            \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) return fail(h, TGP_ECUDA, "%s failed: %s (%s:%d)", name, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        ++(h)->launches;                                                                                           \
+        tgp::prof_end(h);                                                                                          \
     } while (0)
 
 constexpr double kLog2PiD = 1.8378770664093454835606594728112;
@@ -244,17 +246,20 @@ struct DenseWs {
     double* lml;
     unsigned long long* err;
     double* Dinv = nullptr;              // inverses of the 32 x 32 diagonal blocks of U (k_chol_panel2)
+    double* W = nullptr;                 // U^-1 (k_tri_inv_f64): B = W'V, alpha = W'r. nullptr: M too large, triangular solves instead
+    double* al = nullptr;                // alpha (M)
+    double* gws = nullptr;               // split-K workspace of the products
+    size_t gws_doubles = 0;
     double* Pprev = nullptr;             // steady-state detection (time-invariant models only)
     unsigned long long* conv = nullptr;
     long long* ss_at = nullptr;
 };
 
 // frozen: the covariance recursion has reached its fixed point; only the mean / likelihood part of the step runs.
-static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const double* dy, const DenseWs& w, long long t /* host index or -1: use device counter */,
+static int dense_step(tgp_ctx* h, const tgp_lgssm& d, const double* dy, const DenseWs& w, long long t /* host index or -1: use device counter */,
                       bool graph_mode, double* lml_steps, double* m_f, int64_t s_m, double* P_f, int64_t s_P, bool frozen = false) {
     const int D = d.D, M = d.M;
     cudaStream_t st = h->stream;
-    const double one = 1.0, zero = 0.0, mone = -1.0;
     // In graph mode the model is time-invariant (all strides 0), so parameter pointers are fixed and only y / outputs
     // are indexed through the device counter; otherwise t is known on the host.
     const long long tt = graph_mode ? 0 : t;
@@ -267,26 +272,26 @@ static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const d
         TGP_K(h, "dense:k_load_aQ");
         k_load_aQ<<<nb, 256, 0, st>>>(w.mt, frozen ? nullptr : w.Pn, D, d.a, d.sa, d.Q, d.sQ, w.step);
         TGP_LAUNCH_CHECK(h);
-        TGP_CUBLAS(h, cublasDgemv(cb, CUBLAS_OP_N, D, D, &one, A, D, w.m, 1, &one, w.mt, 1));                 // mt = A m + a
+        TGP_F64(h, "dense:k_dgemv_n", dgemv(st, Op::N, D, D, 1.0, A, D, w.m, 1.0, w.mt));                          // mt = A m + a
         if (frozen) {
             TGP_CUDA(h, cudaMemcpyAsync(w.m, w.mt, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
-            h->launches += 2;
+            h->launches += 1;
             return TGP_OK;
         }
-        TGP_CUBLAS(h, cublasDsymm(cb, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, D, D, &one, w.P, D, A, D, &zero, w.T1, D));  // A * Symmetric(P)
-        TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, D, D, D, &one, w.T1, D, A, D, &one, w.Pn, D)); // Pn = T1 A' + Q
+        TGP_F64(h, "dense:k_dgemm", dgemm(st, Op::N, Op::N, true, D, D, D, 1.0, A, D, w.P, D, 0.0, w.T1, D, w.gws, w.gws_doubles));          // A * Symmetric(P)
+        TGP_F64(h, "dense:k_dgemm", dgemm(st, Op::N, Op::T, false, D, D, D, 1.0, w.T1, D, A, D, 1.0, w.Pn, D, w.gws, w.gws_doubles));        // Pn = T1 A' + Q
         TGP_CUDA(h, cudaMemcpyAsync(w.m, w.mt, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
         TGP_CUDA(h, cudaMemcpyAsync(w.P, w.Pn, sizeof(double) * D * D, cudaMemcpyDeviceToDevice, st));
-        h->launches += 5;
+        h->launches += 2;
         return TGP_OK;
     };
     auto update = [&]() -> int {
       if (!frozen) {
-        TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_N, M, D, D, &one, H, M, w.P, D, &zero, w.V, M));   // V = H P
+        TGP_F64(h, "dense:k_dgemm", dgemm(st, Op::N, Op::N, false, M, D, D, 1.0, H, M, w.P, D, 0.0, w.V, M, w.gws, w.gws_doubles));          // V = H P
         TGP_K(h, "dense:k_expand_R");
         k_expand_R<<<std::min((M * M + 255) / 256, 1184), 256, 0, st>>>(w.S, M, d.R, d.sR, d.R_kind, w.step);
         TGP_LAUNCH_CHECK(h);
-        TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_N, CUBLAS_OP_T, M, M, D, &one, w.V, M, H, M, &one, w.S, M));    // S = V H' + R
+        TGP_F64(h, "dense:k_dgemm", dgemm(st, Op::N, Op::T, false, M, M, D, 1.0, w.V, M, H, M, 1.0, w.S, M, w.gws, w.gws_doubles));          // S = V H' + R
         for (int k0 = 0; k0 < M; k0 += kCholNB) {
             const int nbk = std::min(kCholNB, M - k0);
             TGP_K(h, "dense:k_chol_panel2");
@@ -302,20 +307,34 @@ static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const d
         TGP_K(h, "dense:k_clear_lower");
         k_clear_lower<<<std::min((M * M + 255) / 256, 1184), 256, 0, st>>>(w.S, M);
         TGP_LAUNCH_CHECK(h);
-        TGP_CUDA(h, cudaMemcpyAsync(w.B, w.V, sizeof(double) * M * D, cudaMemcpyDeviceToDevice, st));
-        TGP_CUBLAS(h, cublasDtrsm(cb, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, D, &one, w.S, M, w.B, M));  // B = U' \ V
+        if (w.W) {
+            TGP_K(h, "dense:k_tri_inv_f64");
+            k_tri_inv_f64<<<(M + 7) / 8, 256, tri_inv_smem(M), st>>>(w.S, M, w.Dinv, w.W);
+            TGP_LAUNCH_CHECK(h);
+            TGP_F64(h, "dense:k_dgemm", dgemm(st, Op::T, Op::N, false, M, D, M, 1.0, w.W, M, w.V, M, 0.0, w.B, M, w.gws, w.gws_doubles));  // B = U' \ V = W' V
+        } else {
+            TGP_CUDA(h, cudaMemcpyAsync(w.B, w.V, sizeof(double) * M * D, cudaMemcpyDeviceToDevice, st));
+            ++h->launches;
+            TGP_F64(h, "dense:k_trsm_ut", trsm_ut(st, M, D, w.S, M, w.B, M));                                          // B = U' \ V
+        }
       }
         TGP_K(h, "dense:k_residual0");
         k_residual0<<<(M + 255) / 256, 256, 0, st>>>(w.r, M, dy, d.h, d.sh, w.step);
         TGP_LAUNCH_CHECK(h);
-        TGP_CUBLAS(h, cublasDgemv(cb, CUBLAS_OP_N, M, D, &mone, H, M, w.m, 1, &one, w.r, 1));                    // r = y - h - H m
-        TGP_CUBLAS(h, cublasDtrsv(cb, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, w.S, M, w.r, 1));   // alpha = U' \ r
+        TGP_F64(h, "dense:k_dgemv_n", dgemv(st, Op::N, M, D, -1.0, H, M, w.m, 1.0, w.r));                              // r = y - h - H m
+        const double* alpha = w.r;
+        if (w.W) {
+            TGP_F64(h, "dense:k_dgemv_t", dgemv(st, Op::T, M, M, 1.0, w.W, M, w.r, 0.0, w.al));                        // alpha = U' \ r = W' r
+            alpha = w.al;
+        } else {
+            TGP_F64(h, "dense:k_trsm_ut", trsm_ut(st, M, 1, w.S, M, w.r, M));                                          // alpha = U' \ r
+        }
         TGP_K(h, "dense:k_lml");
-        k_lml<<<1, 256, 0, st>>>(w.S, w.r, M, lml_steps, w.lml, w.step);
+        k_lml<<<1, 256, 0, st>>>(w.S, alpha, M, lml_steps, w.lml, w.step);
         TGP_LAUNCH_CHECK(h);
-        TGP_CUBLAS(h, cublasDgemv(cb, CUBLAS_OP_T, M, D, &one, w.B, M, w.r, 1, &one, w.m, 1));                    // m += B' alpha
+        TGP_F64(h, "dense:k_dgemv_t", dgemv(st, Op::T, M, D, 1.0, w.B, M, alpha, 1.0, w.m));                           // m += B' alpha
         if (!frozen) {
-            TGP_CUBLAS(h, cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, D, D, M, &mone, w.B, M, w.B, M, &one, w.P, D));  // P -= B'B
+            TGP_F64(h, "dense:k_dgemm", dgemm(st, Op::T, Op::N, false, D, D, M, -1.0, w.B, M, w.B, M, 1.0, w.P, D, w.gws, w.gws_doubles));   // P -= B'B
             if (w.conv) {
                 TGP_K(h, "dense:k_conv_check");
                 k_conv_check<<<nb, 256, 0, st>>>(w.P, w.Pprev, (long long)D * D, w.conv);
@@ -327,7 +346,6 @@ static int dense_step(tgp_ctx* h, cublasHandle_t cb, const tgp_lgssm& d, const d
             k_emit_state<<<nb, 256, 0, st>>>(w.m, w.P, D, m_f, s_m, P_f, s_P, w.step);
             TGP_LAUNCH_CHECK(h);
         }
-        h->launches += frozen ? 3 : 8;
         return TGP_OK;
     };
     if (!rev) { TGP_TRY(predict()); TGP_TRY(update()); }
@@ -348,15 +366,8 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
     const int D = m->D, M = m->M;
     const int64_t T = m->T;
     cudaStream_t st = h->stream;
-    if (!h->cublas) {            // one cuBLAS handle per library handle (= per device and stream owner), not per process
-        cublasHandle_t nb = nullptr;
-        TGP_CUBLAS(h, cublasCreate(&nb));
-        h->cublas = nb;
-    }
-    cublasHandle_t cb = (cublasHandle_t)h->cublas;
-    TGP_CUBLAS(h, cublasSetStream(cb, st));
-    TGP_CUBLAS(h, cublasSetPointerMode(cb, CUBLAS_POINTER_MODE_HOST));
-    TGP_CUBLAS(h, cublasSetMathMode(cb, CUBLAS_PEDANTIC_MATH));   // plain FP64: no down-conversion anywhere
+    if ((size_t)M * sizeof(double) > 48 * 1024)
+        return fail(h, TGP_EUNSUPPORTED, "observation dimension M=%d too large for the FP64 triangular solve (M <= 6144)", M);
 
     // stage the model
     tgp_lgssm d = *m;
@@ -391,6 +402,14 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
     TGP_TRY(dalloc(h, 1, &w.lml));
     TGP_TRY(dalloc(h, 1, &w.err));
     TGP_TRY(dalloc(h, (size_t)((M + 31) / 32) * 1024, &w.Dinv));
+    TGP_TRY(dalloc(h, M, &w.al));
+    if (tri_inv_smem(M) <= 200 * 1024) {
+        TGP_TRY(dalloc(h, (size_t)M * M, &w.W));
+        if (tri_inv_smem(M) > 48 * 1024)
+            TGP_CUDA(h, cudaFuncSetAttribute(k_tri_inv_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tri_inv_smem(M)));
+    }
+    w.gws_doubles = std::min<size_t>((size_t)8 * D * D, (size_t)1 << 25);       // split-K partial products (<= 256 MB)
+    TGP_TRY(dalloc(h, w.gws_doubles, &w.gws));
     const bool ti = !(m->sA | m->sa | m->sQ | m->sH | m->sh | m->sR);
     // Reverse ordering ends a step with predict(): after the freeze w.P would hold the PREDICTED covariance, which is not what
     // P_f emits — so a Reverse model that emits P_f runs every step in full.
@@ -403,10 +422,6 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
         TGP_CUDA(h, cudaMemsetAsync(w.conv, 0, 4 * sizeof(unsigned long long), st));
         TGP_CUDA(h, cudaMemsetAsync(w.ss_at, 0xFF, sizeof(long long), st));
     }
-    void* cbws;
-    const size_t cbws_bytes = size_t(32) << 20;
-    TGP_TRY(dalloc(h, cbws_bytes / 8, (double**)&cbws));
-    TGP_CUBLAS(h, cublasSetWorkspace(cb, cbws, cbws_bytes));
     TGP_CUDA(h, cudaMemcpyAsync(w.m, d.m0, sizeof(double) * D, cudaMemcpyDeviceToDevice, st));
     TGP_CUDA(h, cudaMemcpyAsync(w.P, d.P0, sizeof(double) * D * D, cudaMemcpyDeviceToDevice, st));
     TGP_CUDA(h, cudaMemsetAsync(w.lml, 0, sizeof(double), st));
@@ -426,7 +441,7 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
         for (int fz = 0; fz < (w.conv ? 2 : 1); ++fz) {
             TGP_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             const int64_t l0 = h->launches;
-            int rc = dense_step(h, cb, d, dy, w, -1, true, lml_steps, m_f, dsm, P_f, dsP, fz == 1);
+            int rc = dense_step(h, d, dy, w, -1, true, lml_steps, m_f, dsm, P_f, dsP, fz == 1);
             per_replay[fz] = h->launches - l0;    // kernels of one replay; nothing ran during the capture itself
             h->launches = l0;
             cudaError_t ce = cudaStreamEndCapture(st, &graph[fz]);
@@ -458,7 +473,7 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
         // through the device counter, the cuBLAS calls through host-computed pointers.
         for (int64_t n = 0; n < T; ++n) {
             const long long t = rev ? T - 1 - n : n;
-            TGP_TRY(dense_step(h, cb, d, dy, w, t, false, lml_steps, m_f, dsm, P_f, dsP));
+            TGP_TRY(dense_step(h, d, dy, w, t, false, lml_steps, m_f, dsm, P_f, dsP));
         }
     }
     if (w.conv && getenv("TGP_DEBUG")) {
@@ -484,7 +499,7 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
 
 namespace tgp {
 void dense_release(tgp_ctx* h) {
-    if (h->cublas) { cublasDestroy((cublasHandle_t)h->cublas); h->cublas = nullptr; }
+    (void)h;   // nothing to release: the FP64 path owns no library handle any more
 }
 }  // namespace tgp
 

@@ -443,11 +443,15 @@ def test_space_time_separable_logpdf(pkg, regular):
 @pytest.mark.parametrize("regular", [True, False])
 @pytest.mark.parametrize("s2", [1e-6, 1e-9, 1e-12])
 @pytest.mark.parametrize("kname", ["m52", "m32", "sum_m12_m32"])
-def test_small_noise_parity(pkg, handle, kname, s2, regular):
+def test_small_noise_parity(pkg, handle, kname, s2, regular, monkeypatch):
     """logpdf (1e-6), filtering means / covariances and posterior marginals (1e-5) at observation noise down to the reference's
     default 1e-12, through the steady-state kernels (regular grid) and the general 5-tuple scan (irregular grid). Covariance entries
     are compared relative to the largest entry (a state observed with noise 1e-12 has variances spanning 12 decades)."""
     kp, ko = KERNELS[kname]
+    # Same transitions, bit for bit, on both sides (host-built): at sigma^2 = 1e-12 the result is sensitive to the LAST bits of
+    # Q_t = P - A_t P A_t' (catastrophic cancellation for small gaps), so an independently rounded exp(F dt) — the device builder's,
+    # or Julia's — moves the answer by ~1e-5 relative. tests/test_gpu_lti.py measures exactly that for the device builder.
+    monkeypatch.setattr(pkg.gp, "DEVICE_COMPONENTS_MIN_T", 10 ** 9)
     rng = np.random.default_rng(int(-np.log10(s2)) * 10 + regular)
     T, dt = 6000, 0.01
     tp = pkg.RegularSpacing(0.0, dt, T) if regular else np.sort(rng.uniform(0, dt * T, T))
