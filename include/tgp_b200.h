@@ -65,7 +65,7 @@ extern "C" {
                                  * exchange: the step has no inter-GPU dependency at all (the partial results still go to every
                                  * peer's buffer). Set the same value on every rank.                              */
 #define TGP_SHARD_HALO       3072
-#define TGP_DENSE_F64        0  /* FP64 throughout (reference ArrayStorage(Float64)); library GEMMs              */
+#define TGP_DENSE_F64        0  /* FP64 throughout (reference ArrayStorage(Float64)); own DFMA kernels           */
 #define TGP_DENSE_TF32X3     1  /* FP32 storage (reference ArrayStorage(Float32)): covariance algebra on the tcgen05
                                  * tensor cores as 3xTF32 split products with FP32 accumulation in TMEM; innovation
                                  * Cholesky, means and the log-likelihood stay FP64                               */

@@ -470,7 +470,7 @@ int dense_filter(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_ou
         }
     } else {
         // time-varying parameters: pointers depend on t, issue the step's launches directly. The custom kernels index
-        // through the device counter, the cuBLAS calls through host-computed pointers.
+        // through the device counter, the products through host-computed pointers.
         for (int64_t n = 0; n < T; ++n) {
             const long long t = rev ? T - 1 - n : n;
             TGP_TRY(dense_step(h, d, dy, w, t, false, lml_steps, m_f, dsm, P_f, dsP));
