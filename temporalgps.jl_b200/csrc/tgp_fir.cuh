@@ -37,8 +37,16 @@
 
 namespace tgp {
 
-constexpr int kFirThreads = 512;
-constexpr int kFirWarps = kFirThreads / 32;
+// CTA shape: TGP_FIR_WARPS warps, kFirCtasPerSM CTAs per SM (16 warps per SM either way: the register file is full at 128 registers).
+// Two 8-warp CTAs per SM instead of one 16-warp CTA let the NEXT call's CTA start (prologue, first loads) in the half of an SM that the
+// current call has already vacated while the other half is still streaming.
+#ifndef TGP_FIR_WARPS
+#define TGP_FIR_WARPS 8
+#endif
+constexpr int kFirWarps = TGP_FIR_WARPS;
+constexpr int kFirThreads = kFirWarps * 32;
+constexpr int kFirCtasPerSM = 16 / kFirWarps;
+constexpr int kFirHeadLess = 16;                     // tiles CTA 0 is spared for running the transient (twice that when it waits for a halo)
 constexpr int kFirPushWarps = 4;                     // warps of the last CTA that copy the halo to the successor rank
 constexpr int kFirRing = 64;                          // tile words kept in shared memory (>= 2 rounds of 16 warps + look-back)
 constexpr int kFirRow = kFirL + 2;                    // doubles between the rows of a staging buffer
@@ -92,7 +100,7 @@ __device__ __forceinline__ unsigned long long fir_policy_evict_first() {
 __device__ __forceinline__ void fir_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void fir_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // Waits on another warp / another GPU give up (trap: the caller sees a CUDA error instead of a hung device) only after kFirGiveUpNs.
-constexpr unsigned long long kFirGiveUpNs = 120ull * 1000000000ull;
+constexpr unsigned long long kFirGiveUpNs = 60ull * 1000000000ull;
 __device__ __forceinline__ unsigned long long fir_now_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -398,7 +406,7 @@ __device__ __forceinline__ void fir_trace(const FirArgs& ar, int slot) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(kFirThreads, 1)
+__global__ void __launch_bounds__(kFirThreads, kFirCtasPerSM)
 k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirArgs ar) {
     using SM = FirSmem<D>;
     extern __shared__ __align__(16) double smem[];
@@ -422,7 +430,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     {
         const long long base = ntiles / G;
         // CTA 0 also runs the transient (rank 0: one round less) or, last, the halo and its first tiles' pass B (rank > 0: two less)
-        const long long less = ar.x.local_halo ? 0 : (ar.x.halo ? 2 : 1) * kFirWarps;   // overlapped shard: CTA 0 is like any other
+        const long long less = ar.x.local_halo ? 0 : (ar.x.halo ? 2 : 1) * kFirHeadLess;   // overlapped shard: CTA 0 is like any other
         const long long t0 = (G > 1 && base >= less + 2 * kFirWarps) ? base - less : base;   // tiles of CTA 0
         const long long rest = ntiles - t0;
         c0 = b == 0 ? 0 : t0 + (G > 1 ? rest * (b - 1) / (G - 1) : 0);
@@ -478,12 +486,14 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     const bool halo_fast = halo_k > 0 && pl.aligned;
     if (ar.stagger_ns && (wp >> 2)) __nanosleep((unsigned)(wp >> 2) * ar.stagger_ns);   // de-phase the 4 warps of each scheduler
     // the lane powers first (one load per thread: ahead of, not behind, the 128 KB of observations this SM is about to request)
-    static_assert(D * D * 32 <= kFirThreads, "one lane-power entry per thread");
+    static_assert(D * D * 32 <= 2 * kFirThreads, "at most two lane-power entries per thread");
     const double plane_v = tid < D * D * 32 ? __ldg(ar.plane + tid) : 0.0;
+    const double plane_v2 = tid + kFirThreads < D * D * 32 ? __ldg(ar.plane + tid + kFirThreads) : 0.0;
     if (halo_fast) fir_issue_tile(buf, ys + (c0 - halo_k) * kFirTile, lane, pol);
     else if (n_items > 0 && !(nA + n_fast == 0 && nC > 0)) issue(item(0));            // first tile on its way before anything else
     fir_cp_commit();
     if (tid < D * D * 32) splane[tid] = plane_v;
+    if (tid + kFirThreads < D * D * 32) splane[tid + kFirThreads] = plane_v2;
     for (int i = tid; i < (kFirRing + 2 * kFirNbMax) * D; i += kFirThreads) fir_st_word(sring + i, 0.0, -1);
     __syncthreads();
     if (tid == 0) fir_trace(ar, 1);
@@ -559,6 +569,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
                 issue(item(it + 1));
             }
             fir_cp_commit();
+            if (pusher && it == 0) push_done();      // (a pusher warp whose first item is the partial tile must still report its push)
             continue;
         }
         double yv[kFirL];
@@ -715,9 +726,10 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     memcpy(&pl, st.plan.data(), sizeof pl);
     // ---- workspace ---------------------------------------------------------------------------------------------------
     const long long ntiles = pl.ntiles;
-    const unsigned G = (unsigned)std::max<long long>(1, std::min<long long>(h->sm_count, ntiles / 8));   // one 16-warp CTA per SM
+    const int full_grid = h->sm_count * kFirCtasPerSM;                                                       // 16 warps per SM
+    const unsigned G = (unsigned)std::max<long long>(1, std::min<long long>(full_grid, ntiles / (kFirWarps / 2)));
     // counters / partials / result alternate with the parity of the call, so two consecutive calls may overlap (PDL)
-    const size_t pstride = ((size_t)h->sm_count + 8) & ~size_t(7);
+    const size_t pstride = ((size_t)full_grid + 8) & ~size_t(7);
     TGP_TRY(fir_grow(h, &st.partials, &st.partials_cap, 2 * pstride * sizeof(double), false));
     if (!st.counters) {
         TGP_CUDA(h, cudaMalloc((void**)&st.counters, 64 * sizeof(unsigned)));
@@ -747,12 +759,13 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
         TGP_CUDA(h, cudaMemsetAsync(dtrace, 0, (size_t)G * 64, h->stream));
         ar.trace = dtrace;
     }
-    ar.early_trigger = (pdl && (int)G == h->sm_count) ? 1 : 0;
+    ar.early_trigger = (pdl && (int)G == full_grid) ? 1 : 0;
     TGP_K(h, "k_fir_logpdf");
     constexpr size_t smem = FirSmem<D>::bytes;
     static bool attr_set[64] = {false};
     if (!attr_set[h->device & 63]) {
         TGP_CUDA(h, cudaFuncSetAttribute(k_fir_logpdf<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TGP_CUDA(h, cudaFuncSetAttribute(k_fir_logpdf<D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[h->device & 63] = true;
     }
     {
