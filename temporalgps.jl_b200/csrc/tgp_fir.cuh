@@ -76,7 +76,8 @@ struct FirArgs {
     double* partials;             // gridDim.x per-CTA sums of v^2, [gridDim.x]: the transient's sum of v^2 / S_t
     double* result;               // lml of this shard (device)
     double* lml_user;             // caller's device destination, nullable
-    unsigned stagger_ns;          // initial delay between the four warp groups of a CTA (0: none)
+    unsigned stagger_ns;
+    int head_less;                // tiles CTA 0 is spared (0: kFirHeadLess); TGP_FIR_HEADLESS, a tuning knob          // initial delay between the four warp groups of a CTA (0: none)
     unsigned long long* trace;    // optional (TGP_FIR_TRACE): 8 globaltimer stamps per CTA, see fir_trace()
     int early_trigger;            // let the next call's CTAs in as this call's CTAs leave (only when a call fills every SM: then at most
                                   // two calls are ever in flight, which is what the parity-indexed workspace allows)
@@ -430,7 +431,7 @@ k_fir_logpdf(const __grid_constant__ FirPlan<D> pl, const __grid_constant__ FirA
     {
         const long long base = ntiles / G;
         // CTA 0 also runs the transient (rank 0: one round less) or, last, the halo and its first tiles' pass B (rank > 0: two less)
-        const long long less = ar.x.local_halo ? 0 : (ar.x.halo ? 2 : 1) * kFirHeadLess;   // overlapped shard: CTA 0 is like any other
+        const long long less = ar.x.local_halo ? 0 : (ar.x.halo ? 2 : 1) * (ar.head_less ? ar.head_less : kFirHeadLess);   // overlapped shard: CTA 0 is like any other
         const long long t0 = (G > 1 && base >= less + 2 * kFirWarps) ? base - less : base;   // tiles of CTA 0
         const long long rest = ntiles - t0;
         c0 = b == 0 ? 0 : t0 + (G > 1 ? rest * (b - 1) / (G - 1) : 0);
@@ -751,6 +752,9 @@ int logpdf_fir(tgp_ctx* h, const tgp_lgssm* m, const double* y, double* lml_out,
     if (stagger < 0) { const char* e = getenv("TGP_FIR_STAGGER"); stagger = e ? atoi(e) : 0; }
     if (pdl < 0) { const char* e = getenv("TGP_FIR_PDL"); pdl = e ? atoi(e) : 1; }
     ar.stagger_ns = (unsigned)stagger;
+    static int head_less = -1;
+    if (head_less < 0) { const char* e = getenv("TGP_FIR_HEADLESS"); head_less = e ? atoi(e) : 0; }
+    ar.head_less = head_less;
     static int trace = -1;
     if (trace < 0) trace = getenv("TGP_FIR_TRACE") ? 1 : 0;
     unsigned long long* dtrace = nullptr;
