@@ -92,7 +92,7 @@ print("rank", rank, "ok")
 '''
 
 
-@pytest.mark.parametrize("route,T", [("fir", 200_000), ("fir", 200_001), ("fir", 131_073), ("steady", 200_000),
+@pytest.mark.parametrize("route,T", [("fir", 200_000), ("fir", 200_001), ("fir", 131_073), ("fir", 203_000), ("fir", 207_300), ("steady", 200_000),
                                      ("fir+overlap", 200_000), ("fir+overlap", 200_001)])
 def test_time_sharded_logpdf_two_processes(pkg, tmp_path, route, T):
     script = tmp_path / "worker.py"
