@@ -106,7 +106,10 @@ __global__ void __launch_bounds__(128) k_sm_head_fwd(const DevModel dm, const do
     double lml = 0.0;
     long long N0 = Nmax;
     int conv = 0;
+    double y_next = __ldg(dm.y);                                     // the observation is fetched one step ahead: its latency is off the chain
     for (long long t = 0; t < Nmax; ++t) {
+        const double y_t = y_next;
+        if (t + 1 < Nmax) y_next = __ldg(dm.y + t + 1);
         bk_mm<D>(sA, sP, sT);
         bk_mmT_add<D>(sT, sA, sQ, sPp);                              // P_p = A P A' + Q
         if (tid < D) {
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(128) k_sm_head_fwd(const DevModel dm, const do
 #pragma unroll
         for (int k = 0; k < D; ++k) { S = fma(sh[k], sV[k], S); pred = fma(sh[k], smp[k], pred); }
         if (!(S > 1e-300) || !(S < 1e300)) { if (tid == 0) atomicMin(err_step, (unsigned long long)t); S = 1.0; }
-        const double invS = 1.0 / S, v = __ldg(dm.y + t) - pred;
+        const double invS = 1.0 / S, v = y_t - pred;
         if (tid == 0) { sSq[(t & 1023) * 2] = S; sSq[(t & 1023) * 2 + 1] = v * v * invS; }
         if ((t & 1023) == 1023) {                                   // drain: the logs of 1024 steps, in parallel
             __syncthreads();
@@ -367,9 +370,24 @@ __global__ void __launch_bounds__(128) k_sm_head_bwd(const DevModel dm, const Sm
     if (tid == 0) *flag = cst->conv_f && cst->conv_b;
     __syncthreads();
     const double h0 = cst->h0;
+    // (G_t, g_t, Sigma_t) travel one step ahead in registers (D * D <= 128: one entry per thread), so the global-memory latency of
+    // step t - 1 is covered by the products of step t
+    static_assert(D * D <= 128, "one entry of G and Sigma per thread");
+    double pG = 0.0, pS = 0.0, pg = 0.0, pR = 0.0;
+    if (N0 - 1 >= 1) {
+        if (tid < D * D) { pG = GG[(N0 - 1) * D * D + tid]; pS = SS[(N0 - 1) * D * D + tid]; }
+        if (tid < D) pg = gg[(N0 - 1) * D + tid];
+        if (tid == 127) pR = Rn[(N0 - 2) * sR];
+    }
     for (long long t = N0 - 1; t >= 1; --t) {
-        for (int e = tid; e < D * D; e += 128) { sG[e] = GG[t * D * D + e]; sSig[e] = SS[t * D * D + e]; }
-        if (tid < D) { sg[tid] = gg[t * D + tid]; sd[tid] = sm[tid]; }
+        if (tid < D * D) { sG[tid] = pG; sSig[tid] = pS; }
+        if (tid < D) { sg[tid] = pg; sd[tid] = sm[tid]; }
+        const double R_t = pR;
+        if (t - 1 >= 1) {
+            if (tid < D * D) { pG = GG[(t - 1) * D * D + tid]; pS = SS[(t - 1) * D * D + tid]; }
+            if (tid < D) pg = gg[(t - 1) * D + tid];
+            if (tid == 127) pR = Rn[(t - 2) * sR];
+        }
         __syncthreads();
         bk_mm<D>(sG, sP, sT);
         bk_mmT_add<D>(sT, sG, sSig, sN);
@@ -393,7 +411,7 @@ __global__ void __launch_bounds__(128) k_sm_head_bwd(const DevModel dm, const Sm
 #pragma unroll
             for (int i = 0; i < D; ++i) { mu = fma(sh[i], sm[i], mu); v = fma(sh[i], sV[i], v); }
             mean[t - 1] = mu;
-            var[t - 1] = v + Rn[(t - 1) * sR];
+            var[t - 1] = v + R_t;
         }
     }
 }
