@@ -207,17 +207,12 @@ int tgp_shard_phase2(tgp_handle h, const double* xchg_all, double* lml_partial);
  * (tgp_shard_phase2: TGP_ENOTPD / TGP_EUNSUPPORTED "not converged"). The next call on the handle does the same. */
 int tgp_synchronize(tgp_handle h);
 
-/* Peer-memory exchange for the sharded path (one process per GPU, NVLink / NVSwitch P2P): direct stores into every peer's buffer
- * + a flag, all stream-ordered on the handle's stream (no NCCL call, no host round trip).
- * tgp_xchg_create allocates this rank's buffer and returns its 64-byte CUDA IPC handle; the caller gathers the handles of
- * all ranks (any transport) and passes them, rank-ordered, to tgp_xchg_open. put copies n doubles (n <= slot_doubles) into
- * this rank's slot of `channel` (0 or 1) on EVERY rank and raises the slot's flag; wait mode 0 waits for the ranks before
- * this one and copies their slots to dst[p*n ..]; mode 1 waits for all ranks and writes the sum over ranks to dst[0..n).
- * src / dst are device pointers. Every rank must issue the same sequence of put / wait calls. */
+/* Peer-memory exchange buffers for the sharded path (one process per GPU, NVLink / NVSwitch P2P): tgp_shard_logpdf's kernel stores
+ * straight into its peers' buffers (no NCCL call, no host round trip). tgp_xchg_create allocates this rank's buffer and returns its
+ * 64-byte CUDA IPC handle; the caller gathers the handles of all ranks (any transport) and passes them, rank-ordered, to
+ * tgp_xchg_open. slot_doubles: size of the general-purpose record slots kept in the buffer (16 is enough). */
 int tgp_xchg_create(tgp_handle h, int rank, int world, int slot_doubles, void* ipc_handle_out);
 int tgp_xchg_open(tgp_handle h, const void* ipc_handles_all);
-int tgp_xchg_put(tgp_handle h, int channel, const double* src, int n);
-int tgp_xchg_wait(tgp_handle h, int channel, int n, double* dst, int mode);
 
 /* ONE-LAUNCH SHARDED LOGPDF (the path BASELINE config 4 runs; needs an opened exchange when world > 1). `shard` describes this
  * rank's steps [rank*T, ...) of ONE Forward, time-invariant, scalar-observation series (D <= 4); its (m0, P0) is the prior of the

@@ -88,8 +88,6 @@ _SIGS = {
     "tgp_shard_partial": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tgp_xchg_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tgp_xchg_open": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "tgp_xchg_put": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
-    "tgp_xchg_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "tgp_shard_prefix": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
@@ -268,12 +266,6 @@ class Handle:
 
     def xchg_open(self, handles_all: bytes):
         self.check(lib().tgp_xchg_open(self._h, handles_all))
-
-    def xchg_put(self, channel, src, n):
-        self.check(lib().tgp_xchg_put(self._h, int(channel), ptr(src), int(n)))
-
-    def xchg_wait(self, channel, n, dst, mode):
-        self.check(lib().tgp_xchg_wait(self._h, int(channel), int(n), ptr(dst), int(mode)))
 
     def shard_phase2(self, xchg_all, lml_partial):
         self.check(lib().tgp_shard_phase2(self._h, ptr(xchg_all), ptr(lml_partial)))

@@ -417,14 +417,6 @@ int tgp_xchg_open(tgp_handle h, const void* ipc_handles_all) {
     TGP_CUDA(h, cudaSetDevice(h->device));
     return xchg_open(h, ipc_handles_all);
 }
-int tgp_xchg_put(tgp_handle h, int channel, const double* src, int n) {
-    if (!h) return TGP_EINVAL;
-    return xchg_put(h, channel, src, n);
-}
-int tgp_xchg_wait(tgp_handle h, int channel, int n, double* dst, int mode) {
-    if (!h) return TGP_EINVAL;
-    return xchg_wait(h, channel, n, dst, mode);
-}
 
 int tgp_synchronize(tgp_handle h) {
     if (!h) return TGP_EINVAL;

@@ -38,8 +38,6 @@ int lti_components(tgp_ctx* h, int D, int64_t T, const double* F, const double* 
 // Peer-memory exchange of the time-sharded path (tgp_xchg.cu).
 int xchg_create(tgp_ctx* h, int rank, int world, int slot_doubles, void* ipc_handle_out);
 int xchg_open(tgp_ctx* h, const void* handles_all);
-int xchg_put(tgp_ctx* h, int ch, const double* src, int n);
-int xchg_wait(tgp_ctx* h, int ch, int n, double* dst, int mode);
 void xchg_destroy(tgp_ctx* h);
 // Device view of an opened exchange (false: none is open) and its per-channel epochs, for the kernels that put / wait themselves.
 struct XchgView { char* const* peers; char* self; int slot, world, rank; unsigned long long flag_off; };

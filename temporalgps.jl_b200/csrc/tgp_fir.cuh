@@ -4,8 +4,8 @@
 //
 // Past the covariance transient (host plan, tgp_fir_plan.h) the filter is the constant-coefficient recursion
 //      m_t = Abar m_{t-1} + K y_t + c,    v_t = y_t - w'm_{t-1} - hh,    lml_t = -(log 2pi + log S + v_t^2 / S) / 2.
-// The steady steps are cut into tiles of 1024 = 32 lanes x 32 steps. One 16-warp CTA per SM owns a CONTIGUOUS chunk of tiles, its
-// warps take them round-robin. A lane keeps its 32 observations in registers and works on blocks of 8 steps:
+// The steady steps are cut into tiles of 1024 = 32 lanes x 32 steps. Each CTA (two 8-warp CTAs per SM) owns a CONTIGUOUS chunk of
+// tiles, its warps take them round-robin. A lane keeps its 32 observations in registers and works on blocks of 8 steps:
 //   pass A   u_b = zc + sum_j (Abar^(7-j) K) y_j ;  z <- Abar^8 z + u_b          zero-state response of the lane's run
 //   scan     5 shuffle levels with Abar^(32 2^k): lane-exclusive prefix; lane 31 PUBLISHES the tile's zero-state response in a
 //            shared-memory ring
@@ -48,7 +48,7 @@ constexpr int kFirThreads = kFirWarps * 32;
 constexpr int kFirCtasPerSM = 16 / kFirWarps;
 constexpr int kFirHeadLess = 16;                     // tiles CTA 0 is spared for running the transient (twice that when it waits for a halo)
 constexpr int kFirPushWarps = 4;                     // warps of the last CTA that copy the halo to the successor rank
-constexpr int kFirRing = 64;                          // tile words kept in shared memory (>= 2 rounds of 16 warps + look-back)
+constexpr int kFirRing = 64;                          // tile words kept in shared memory (>= 2 rounds of a CTA's warps + look-back)
 constexpr int kFirRow = kFirL + 2;                    // doubles between the rows of a staging buffer
 constexpr int kFirBufDoubles = 32 * kFirRow;          // staging buffer of one warp
 
@@ -257,15 +257,6 @@ __device__ __forceinline__ double fir_tile_compute(const FirPlan<D>& pl, double 
     return fir_pass_b2<D, TAIL>(pl, yv, u, m, TAIL ? nvalid - lane * kFirL : kFirL);
 }
 
-// The staged partial tile (zero-filled beyond nvalid): out of line, masked sums.
-template <int D>
-__device__ __noinline__ double fir_tile_staged_tail(const FirPlan<D>& pl, const double* buf, int r, int nvalid, bool pub, bool full,
-                                                    const double* __restrict__ splane, double2* sring, int lane) {
-    double yv[kFirL];          // (its own copy: handing the caller's register array to an out-of-line function would force it into
-    fir_read_tile(buf, lane, yv);   //  local memory for every tile)
-    return fir_tile_compute<D, true>(pl, yv, r, nvalid, pub, full, splane, sring, lane);
-}
-
 // Unaligned series: guarded scalar loads straight from global memory, one out-of-line copy.
 template <int D>
 __device__ __noinline__ double fir_tile_guarded(const FirPlan<D>& pl, const double* __restrict__ ys, int r, int nvalid, bool pub, bool full,
@@ -279,8 +270,8 @@ __device__ __noinline__ double fir_tile_guarded(const FirPlan<D>& pl, const doub
     return fir_tile_compute<D, true>(pl, yv, r, nvalid, pub, full, splane, sring, lane);
 }
 
-// The transient: steps [0, N0) with the tabulated gains, the whole CTA. Thread i owns steps [i c, (i + 1) c), c = ceil(N0 / 512): it
-// composes their affine map (M, b); shuffle scan inside the warps, the 16 warp totals through shared memory; a second sweep from the
+// The transient: steps [0, N0) with the tabulated gains, the whole CTA. Thread i owns steps [i c, (i + 1) c), c = ceil(N0 / kFirThreads): it
+// composes their affine map (M, b); shuffle scan inside the warps, the warp totals through shared memory; a second sweep from the
 // thread's start state forms the innovations. Publishes the filtered mean after step N0 - 1 as ring entry kFirNbMax - 1 (zeros before
 // it) and returns the CTA's sum of v_t^2 / S_t (valid in thread 0).
 template <int D>

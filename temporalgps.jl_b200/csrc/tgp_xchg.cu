@@ -1,10 +1,7 @@
-// tgp_xchg.cu — peer-memory exchange for the time-sharded path: the per-shard record and the partial
-// log-likelihood travel by direct NVLink / NVSwitch stores into every peer's buffer, with a flag per (channel, source rank),
-// instead of an NCCL all-gather / all-reduce. One process per GPU: the buffers are shared through CUDA IPC handles that the
-// host exchanges once (any transport; sharded.py uses torch.distributed). Everything is stream-ordered on the handle's stream:
-//     tgp_shard_phase1 -> tgp_xchg_put(0) -> tgp_xchg_wait(0) -> tgp_shard_phase2 -> tgp_xchg_put(1) -> tgp_xchg_wait(1)
-// Slots are double-buffered by epoch parity (a fast rank may start the next call before a slow one has read this call's slot;
-// it cannot get two epochs ahead because the log-likelihood channel waits for every rank).
+// tgp_xchg.cu — peer-memory exchange buffers of the time-sharded path: the halo of a shard and the partial
+// log-likelihoods travel by direct NVLink / NVSwitch stores from inside k_fir_logpdf into the peers' buffers (FirXchgLayout), instead
+// of an NCCL collective. One process per GPU: the buffers are shared through CUDA IPC handles that the host exchanges once (any
+// transport; sharded.py uses torch.distributed). This file owns the buffers and the on-demand sum of the partial results.
 #include "tgp_ctx.cuh"
 #include "tgp_dispatch.h"
 
@@ -27,50 +24,6 @@ __device__ __forceinline__ size_t xchg_data_off(int ch, int parity, int world, i
     return ((size_t)((ch * 2 + parity) * world + r) * slot) * sizeof(double);
 }
 
-// Copy n doubles into slot[rank] of every peer, then raise flag[ch][rank] = epoch there.
-__global__ void __launch_bounds__(128) k_xchg_put(char* const* __restrict__ peers, int world, int rank, int ch, int parity, int slot,
-                                                  const double* __restrict__ src, int n, unsigned long long epoch, size_t flag_off) {
-    const size_t off = xchg_data_off(ch, parity, world, slot, rank);
-    for (int e = threadIdx.x; e < n * world; e += blockDim.x) {
-        const int p = e / n, i = e % n;
-        reinterpret_cast<double*>(peers[p] + off)[i] = src[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < world) {
-        volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + flag_off) + (size_t)ch * world + rank;
-        *f = epoch;
-    }
-}
-
-// mode 0: wait for the ranks before this one, copy their slots to dst[p * n ..] (the records a shard's phase 2 folds);
-// mode 1: wait for every rank, dst[0 .. n) = sum over ranks (the log-likelihood). Bounded spin: a lost peer traps.
-__global__ void __launch_bounds__(128) k_xchg_wait(const char* __restrict__ self, int world, int rank, int ch, int parity, int slot, int n,
-                                                   unsigned long long epoch, size_t flag_off, double* __restrict__ dst, int mode) {
-    const int need = mode == 0 ? rank : world;
-    if (threadIdx.x < need) {
-        const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(self + flag_off) + (size_t)ch * world + threadIdx.x;
-        unsigned long long spins = 0;
-        while (*f < epoch) {
-            if (++spins > (1ull << 31)) __trap();
-            __nanosleep(20);
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (mode == 0) {
-        for (int e = threadIdx.x; e < need * n; e += blockDim.x) {
-            const int p = e / n, i = e % n;
-            dst[(size_t)p * n + i] = __ldcg(reinterpret_cast<const double*>(self + xchg_data_off(ch, parity, world, slot, p)) + i);
-        }
-    } else {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            double s = 0.0;
-            for (int p = 0; p < world; ++p) s += __ldcg(reinterpret_cast<const double*>(self + xchg_data_off(ch, parity, world, slot, p)) + i);
-            dst[i] = s;
-        }
-    }
-}
 
 int xchg_create(tgp_ctx* h, int rank, int world, int slot_doubles, void* ipc_handle_out) {
     if (h->xchg) return fail(h, TGP_EINVAL, "tgp_xchg_create called twice on this handle");
@@ -115,27 +68,6 @@ int xchg_open(tgp_ctx* h, const void* handles_all) {
     return TGP_OK;
 }
 
-int xchg_put(tgp_ctx* h, int ch, const double* src, int n) {
-    XchgState* x = (XchgState*)h->xchg;
-    if (!x || !x->d_peers) return fail(h, TGP_EINVAL, "exchange not opened");
-    if (ch < 0 || ch >= kXchgChannels || n < 1 || n > x->slot || !is_device_ptr(src)) return fail(h, TGP_EINVAL, "bad channel / size / pointer");
-    const unsigned long long ep = ++x->epoch[ch];
-    TGP_K(h, "k_xchg_put");
-    k_xchg_put<<<1, 128, 0, h->stream>>>(x->d_peers, x->world, x->rank, ch, (int)(ep & 1), x->slot, src, n, ep, x->flag_off);
-    TGP_LAUNCH_CHECK(h);
-    return TGP_OK;
-}
-
-int xchg_wait(tgp_ctx* h, int ch, int n, double* dst, int mode) {
-    XchgState* x = (XchgState*)h->xchg;
-    if (!x || !x->d_peers) return fail(h, TGP_EINVAL, "exchange not opened");
-    if (ch < 0 || ch >= kXchgChannels || n < 1 || n > x->slot || !is_device_ptr(dst) || (mode != 0 && mode != 1)) return fail(h, TGP_EINVAL, "bad channel / size / pointer / mode");
-    const unsigned long long ep = x->epoch[ch];
-    TGP_K(h, "k_xchg_wait");
-    k_xchg_wait<<<1, 128, 0, h->stream>>>(x->self, x->world, x->rank, ch, (int)(ep & 1), x->slot, n, ep, x->flag_off, dst, mode);
-    TGP_LAUNCH_CHECK(h);
-    return TGP_OK;
-}
 
 // Sum of the shards' log-likelihoods of the sharded call with epoch `epoch` (ring slot epoch & 3): waits for every rank's flag.
 __global__ void __launch_bounds__(128) k_fir_lml_total(const char* __restrict__ self, size_t fir_off, int world, unsigned long long epoch,
