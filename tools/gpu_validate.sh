@@ -9,6 +9,6 @@ tail -c 1500 gpurun_out/bench_n1.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench_n1.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-filter > gpurun_out/bench_under_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ss_main -s 4 -c 2 -o gpurun_out/prof_ss \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fir_logpdf -s 4 -c 2 -o gpurun_out/prof_fir \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-filter > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
