@@ -107,3 +107,32 @@ def test_device_built_transitions_at_small_noise(pkg, s2, tol):
     mu_o, var_o = O.gp_posterior_marginals(O.Matern52(), t, s2, y, None, 1e-2)
     np.testing.assert_allclose(mu, mu_o, rtol=tol, atol=1e-7)
     np.testing.assert_allclose(var, var_o, rtol=tol)
+
+
+@pytest.mark.parametrize("regular", [True, False], ids=["regular", "irregular"])
+def test_logpdf_gradient_with_respect_to_hyperparameters(pkg, regular):
+    """d logpdf / d (log variance, log lengthscale, log noise) — 4th-order central differences of the device path
+    (gp.logpdf_value_and_gradient) against the same differences of the sequential oracle, and against a second step size."""
+    from oracle import tgp_oracle as O
+    G = pkg.gp
+    rng = np.random.default_rng(17)
+    T = 8_000 if regular else 3_000
+    tp = pkg.RegularSpacing(0.0, 0.01, T) if regular else np.sort(rng.uniform(0.0, 0.01 * T, T))
+    to = O.RegularSpacing(0.0, 0.01, T) if regular else np.array(tp)
+    y = O.sample_prior(O.build_lgssm(O.Scaled(1.3, O.Stretched(1.0 / 0.7, O.Matern52())), to, 0.1), rng)
+
+    def build(th):
+        k = G.ScaledKernel(G.TransformedKernel(pkg.Matern52Kernel(), 1.0 / np.exp(th[1])), float(np.exp(th[0])))
+        return pkg.to_sde(pkg.GP(k))(tp, float(np.exp(th[2])))
+
+    def oracle_lml(th):
+        k = O.Scaled(float(np.exp(th[0])), O.Stretched(1.0 / float(np.exp(th[1])), O.Matern52()))
+        return O.logpdf(O.build_lgssm(k, to, float(np.exp(th[2]))), y)
+
+    th = np.log(np.array([1.1, 0.8, 0.12]))
+    v, g = G.logpdf_value_and_gradient(build, th, y)
+    vo, go = G.value_and_gradient(oracle_lml, th)
+    assert abs(v - vo) <= 1e-6 * abs(vo)
+    np.testing.assert_allclose(g, go, rtol=1e-5, atol=1e-5 * np.abs(go).max())
+    _, g2 = G.logpdf_value_and_gradient(build, th, y, rel_step=3e-3)
+    np.testing.assert_allclose(g, g2, rtol=1e-6, atol=1e-6 * np.abs(g).max())

@@ -113,3 +113,12 @@ def test_bottleneck_emissions_collapse(pkg):
     sf = fills.collapse(T)
     assert isinstance(sf.Hs, L.Fill) and isinstance(sf.hs, L.Fill)       # time-invariant stays O(1)
     np.testing.assert_allclose(sf.Hs.value, A[0] @ H[0])
+
+
+def test_value_and_gradient_is_fourth_order(pkg):
+    f = lambda t: float(np.sin(t[0]) * np.exp(0.3 * t[1]) + t[0] * t[1] ** 2)     # noqa: E731
+    th = np.array([0.7, -1.3])
+    v, g = pkg.gp.value_and_gradient(f, th, rel_step=1e-2)
+    ga = np.array([np.cos(th[0]) * np.exp(0.3 * th[1]) + th[1] ** 2, 0.3 * np.sin(th[0]) * np.exp(0.3 * th[1]) + 2 * th[0] * th[1]])
+    assert v == f(th)
+    np.testing.assert_allclose(g, ga, rtol=1e-8)
