@@ -103,11 +103,11 @@ class ShardedLogpdf:
                 ok = self._open_exchange()
             if ok:
                 self.route = "fir"
-        self.overlap = bool(overlap) and self.route == "fir" and world > 1
         if self.route != "fir" and route in (None, "fir", "steady") and agree(dist, world, ti and d.T >= 65536 and self.D <= 6):
             self.route = "steady"
         if route == "general":
             self.route = "general"
+        self.overlap = bool(overlap) and self.route == "fir" and world > 1
 
     def _open_exchange(self) -> bool:
         """CUDA IPC handles of the ranks' exchange buffers, gathered once. False (on every rank) if peer memory is unavailable."""
