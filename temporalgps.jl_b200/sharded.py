@@ -17,6 +17,8 @@ Route "fir" has a second data layout, `overlap=True`: the series is scattered so
 OWN device buffer by the TGP_SHARD_HALO (3072) observations before it (shard_with_halo below). The kernel then reads them in place —
 nothing is pushed between GPUs, no rank ever waits for another, and the only traffic left is the 16-byte partial result per peer.
 
+posterior_marginals_sharded: the smoother sharded the same way (halos on both sides, no exchange at all).
+
 The reference has no analogue (single-threaded); host logic only here — arithmetic is in the library.
 """
 from __future__ import annotations
@@ -45,6 +47,29 @@ def shard_with_halo(torch, y_full_host, bounds, rank, device):
     buf = torch.empty(TGP_SHARD_HALO + hi - lo, dtype=torch.float64, device=device)   # same offset on every rank: 32-byte aligned view
     buf[TGP_SHARD_HALO - halo:].copy_(torch.from_numpy(np.ascontiguousarray(y_full_host[lo - halo:hi])))
     return buf, buf[TGP_SHARD_HALO:]
+
+
+def halo_bounds(T_total, world, rank, halo):
+    """-> (lo, hi, lo_h, hi_h): the shard [lo, hi) of `rank` and the same extended by `halo` steps on both sides (clipped)."""
+    b = shard_bounds(T_total, world)
+    lo, hi = b[rank], b[rank + 1]
+    return lo, hi, max(0, lo - halo), min(int(T_total), hi + halo)
+
+
+def posterior_marginals_sharded(gp, f, x, noise, y_ext, noise_new, rank, world, halo=4096):
+    """Time-sharded marginals(posterior(f(x, noise), y)(x, noise_new)) at the training inputs of ONE regular-grid series
+    (posterior_lti_sde.jl:27-36), with NO exchange between the ranks: rank r filters and smooths its shard extended by `halo` steps on
+    both sides and keeps the interior. A stable filter forgets its start and the RTS recursion forgets its end at the same rate, so
+    the interior equals the global posterior to |Abar^halo| (config 3: 1e-30 at halo = 4096); the extended shard starts from the
+    stationary prior and ends without a successor exactly like the first and last shards of the series do.
+    gp: the mirror module (temporalgps.jl_b200.gp); f: LTISDE; x: RegularSpacing of the WHOLE series; y_ext: this rank's observations
+    [lo_h, hi_h) (halo_bounds); noise / noise_new: scalars. -> (mean, var) of the rank's own steps [lo, hi)."""
+    lo, hi, lo_h, hi_h = halo_bounds(len(x), world, rank, halo)
+    if len(y_ext) != hi_h - lo_h:
+        raise ValueError(f"rank {rank}: y_ext must hold the {hi_h - lo_h} observations [{lo_h}, {hi_h}), got {len(y_ext)}")
+    x_ext = type(x)(x.t0 + lo_h * x.dt, x.dt, hi_h - lo_h)
+    mu, var = gp.marginals(gp.posterior(f(x_ext, noise), y_ext)(x_ext, noise_new))
+    return mu[lo - lo_h:hi - lo_h], var[lo - lo_h:hi - lo_h]
 
 
 def incoming_state(prefix_fn, D, elems, rank, m0, P0):

@@ -95,3 +95,28 @@ def test_steady_logpdf_large_state_dimension(pkg, handle):
     # per-step output requested: the general kernels (the vector scan emits the sum only)
     lml2, steps = pkg.lgssm.logpdf(model, y, handle, per_step=True)
     assert abs(lml2 - ref) <= LML_RTOL * abs(ref) and abs(steps.sum() - ref) <= LML_RTOL * abs(ref)
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_time_sharded_posterior_marginals_need_no_exchange(pkg, world):
+    """sharded.posterior_marginals_sharded: every rank smooths its shard extended by a halo on both sides; the concatenation of the
+    interiors equals the single-call posterior marginals of the whole series and the sequential oracle (1e-5) — no communication."""
+    from temporalgps_jl_b200 import sharded
+    T, dt, s2 = 30_000, 0.01, 0.1
+    rng = np.random.default_rng(23)
+    x = pkg.RegularSpacing(0.0, dt, T)
+    y = np.sin(np.arange(T) * 0.004) + 0.35 * rng.standard_normal(T)
+    f = pkg.to_sde(pkg.GP(pkg.Matern52Kernel()))
+    mu_all, var_all = pkg.gp.marginals(pkg.gp.posterior(f(x, s2), y)(x, 1e-2))
+    pieces = []
+    for r in range(world):
+        lo, hi, lo_h, hi_h = sharded.halo_bounds(T, world, r, 4096)
+        pieces.append(sharded.posterior_marginals_sharded(pkg.gp, f, x, s2, y[lo_h:hi_h], 1e-2, r, world))
+        assert len(pieces[-1][0]) == hi - lo
+    mu = np.concatenate([p[0] for p in pieces])
+    var = np.concatenate([p[1] for p in pieces])
+    np.testing.assert_allclose(mu, mu_all, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var, var_all, rtol=1e-9)
+    mu_o, var_o = O.gp_posterior_marginals(O.Matern52(), O.RegularSpacing(0.0, dt, T), s2, y, None, 1e-2)
+    np.testing.assert_allclose(mu, mu_o, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(var, var_o, rtol=1e-5)
