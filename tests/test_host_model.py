@@ -122,3 +122,17 @@ def test_value_and_gradient_is_fourth_order(pkg):
     ga = np.array([np.cos(th[0]) * np.exp(0.3 * th[1]) + th[1] ** 2, 0.3 * np.sin(th[0]) * np.exp(0.3 * th[1]) + 2 * th[0] * th[1]])
     assert v == f(th)
     np.testing.assert_allclose(g, ga, rtol=1e-8)
+
+
+def test_halo_bounds_partition_the_series(pkg):
+    from temporalgps_jl_b200 import sharded
+    T, world, halo = 100_003, 7, 4096
+    owned = []
+    for r in range(world):
+        lo, hi, lo_h, hi_h = sharded.halo_bounds(T, world, r, halo)
+        assert 0 <= lo_h <= lo < hi <= hi_h <= T
+        assert lo - lo_h == min(halo, lo) and hi_h - hi == min(halo, T - hi)
+        owned.append((lo, hi))
+    assert owned[0][0] == 0 and owned[-1][1] == T and all(a[1] == b[0] for a, b in zip(owned, owned[1:]))
+    with pytest.raises(ValueError):        # wrong extended-shard length is refused before any device work
+        sharded.posterior_marginals_sharded(pkg.gp, None, pkg.RegularSpacing(0.0, 0.01, T), 0.1, np.zeros(10), 1e-2, 1, world)
