@@ -136,3 +136,33 @@ def test_halo_bounds_partition_the_series(pkg):
     assert owned[0][0] == 0 and owned[-1][1] == T and all(a[1] == b[0] for a, b in zip(owned, owned[1:]))
     with pytest.raises(ValueError):        # wrong extended-shard length is refused before any device work
         sharded.posterior_marginals_sharded(pkg.gp, None, pkg.RegularSpacing(0.0, 0.01, T), 0.1, np.zeros(10), 1e-2, 1, world)
+
+
+def test_scaling_and_squaring_taylor12_is_accurate_enough():
+    """The matrix exponential k_lti_components uses (tgp_lti.cu): scale to |F dt| / 2^s <= 1/4 with s = ilogb(norm) + 3, degree-12 Taylor
+    by Horner, s squarings — restated in NumPy and compared with SciPy's Pade-13 over twelve decades of dt for every base SDE (bound: 5e-14 max(1, |F dt|), i.e. the conditioning of the problem)."""
+    from scipy.linalg import expm
+    import math
+
+    def expm_taylor(F, dt):
+        X = F * dt
+        nrm = np.abs(X).sum(axis=0).max()
+        s = max(0, min(60, math.frexp(nrm)[1] - 1 + 3)) if nrm > 0.25 else 0
+        X = F * math.ldexp(dt, -s)
+        n = F.shape[0]
+        E = X / 12.0 + np.eye(n)
+        for k in range(11, 0, -1):
+            E = (X @ E) / k + np.eye(n)
+        for _ in range(s):
+            E = E @ E
+        return E
+
+    lam3, lam5 = math.sqrt(3.0), math.sqrt(5.0)
+    Fs = [np.array([[-1.0]]), np.array([[0.0, 1.0], [-lam3 ** 2, -2 * lam3]]),
+          np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [-lam5 ** 3, -3 * lam5 ** 2, -3 * lam5]]),
+          np.array([[0.0, -2 * math.pi * 3], [2 * math.pi * 3, 0.0]])]          # a harmonic of the approximately periodic kernel
+    for F in Fs:
+        for dt in 10.0 ** np.arange(-9.0, 3.1, 0.5):
+            A, B = expm_taylor(F, dt), expm(F * dt)
+            nrm = np.abs(F * dt).sum(axis=0).max()          # squaring s ~ log2(norm) times loses ~ norm * eps (SciPy's Pade does too)
+            assert np.abs(A - B).max() <= 5e-14 * max(1.0, nrm) * max(1.0, np.abs(B).max()), (F.shape, dt, np.abs(A - B).max())
