@@ -218,7 +218,9 @@ int tgp_xchg_open(tgp_handle h, const void* ipc_handles_all);
  * rank's steps [rank*T, ...) of ONE Forward, time-invariant, scalar-observation series (D <= 4); its (m0, P0) is the prior of the
  * whole series. The call ENQUEUES one kernel and returns: rank 0 runs the covariance transient, every other rank starts from pass A
  * over the <= 3072 observations that precede its shard, which its predecessor's kernel stores into this rank's exchange buffer over
- * NVLink at the START of its own run — shards never wait for each other's results. Each kernel ships its shard's log-likelihood
+ * NVLink at the START of its own run — shards never wait for each other's results. With TGP_OPT_SHARD_OVERLAP the caller has stored
+ * those TGP_SHARD_HALO observations directly before y instead (y[-3072 .. -1], device memory): nothing is pushed, no rank waits for
+ * another at all. Each kernel ships its shard's log-likelihood
  * into every rank's buffer. tgp_shard_result enqueues the fixed-order sum over ranks for the LAST tgp_shard_logpdf into lml_total
  * (device pointer: stream-ordered; host pointer: synchronises) — call it when the value is wanted, not necessarily per step.
  * Every rank must issue the same sequence of tgp_shard_logpdf calls. Returns TGP_EUNSUPPORTED (nothing enqueued, the same
